@@ -1,0 +1,117 @@
+"""Load the *unmodified* reference modules from /root/reference under Python 3.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Used by
+``oracle/make_golden.py`` in the build container, where ``/root/reference``
+exists, to produce the golden fixtures under ``tests/golden/``.  It is never
+used at run time on the GPU box (the reference tree does not exist there).
+
+The reference is Python 2.  Its two hot-path modules,
+``olc.py`` and ``sv_assembly.py``, are read from the reference tree, a short
+list of *syntactic* Python-2 -> Python-3 rewrites is applied to the text in
+memory, and the result is exec'd.  No reference source is written to disk or
+copied into this repository.  Rewrites (each is behaviour-preserving with
+respect to CPython 2.7):
+
+  olc.py
+    * expandtabs(8)          -- py2 treats a tab as 8 columns (olc.py:66-74)
+  sv_assembly.py
+    * drop the ``__main__`` driver (sv_assembly.py:664-691; it holds a py2
+      print statement and is broken anyway)
+    * ``from utils import *``     -> removed; ``fq_read`` is supplied below
+      (restating utils.py:681-688, the only name the live path needs)
+    * ``lambda (x,y): x+y``       -> ``lambda x_y: x_y[0]+x_y[1]``  (:171,190,191)
+    * ``len(seq)/2``              -> ``len(seq)//2``                 (:129)
+    * ``.items()[0]``/``.keys()[0]`` -> ``list(...)[0]``             (:45,:347)
+    * builtins ``map``/``filter``/``zip`` are shadowed in the module by eager,
+      list-returning versions (py2 semantics; :359,:364,:390 rely on the side
+      effects)
+
+Two behaviours of the reference depend on CPython-2 hash iteration order and
+cannot be observed anywhere.  The order policy of this
+repository is applied to the reference in the same way:
+
+  * Q9  -- ``fq_recs.items()`` order is insertion order (what dict gives on
+           Python >= 3.7); nothing to rewrite.
+  * Q13 -- ``for mer in list(x)`` in ``check_alt_reads`` (:575) iterates a set;
+           rewritten to ``sorted(x)`` (smallest mer first).
+"""
+import builtins
+import os
+import re
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("BREAKMER_REFERENCE_ROOT", "/root/reference")
+
+
+class fq_read:
+    """Restates utils.py:681-688 (the record type the assembler consumes)."""
+
+    def __init__(self, header, seq, qual, indel_only):
+        self.id = header
+        self.seq = str(seq)
+        self.qual = str(qual)
+        self.used = False
+        self.dup = False
+        self.indel_only = indel_only
+
+
+def _eager_map(*a):
+    return list(builtins.map(*a))
+
+
+def _eager_filter(f, it):
+    return list(builtins.filter(f, it))
+
+
+def _eager_zip(*a):
+    return list(builtins.zip(*a))
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "sv_assembly.py"))
+
+
+def _must_sub(pattern, repl, text, count_expected, flags=0):
+    new, n = re.subn(pattern, repl, text, flags=flags)
+    if n != count_expected:
+        raise RuntimeError(
+            "ref_shim: rewrite %r matched %d times, expected %d" % (pattern, n, count_expected))
+    return new
+
+
+def load():
+    """Return (olc_module, sv_assembly_module) built from the reference tree."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+
+    with open(os.path.join(REFERENCE_ROOT, "olc.py")) as f:
+        olc_src = f.read().expandtabs(8)
+    olc = types.ModuleType("olc")
+    olc.__file__ = os.path.join(REFERENCE_ROOT, "olc.py")
+    exec(compile(olc_src, olc.__file__, "exec"), olc.__dict__)
+
+    with open(os.path.join(REFERENCE_ROOT, "sv_assembly.py")) as f:
+        src = f.read().expandtabs(8)
+    cut = src.index("if __name__ == '__main__'")
+    src = src[:cut]
+    src = _must_sub(r"^from utils import \*\s*$", "", src, 1, flags=re.M)
+    src = _must_sub(r"lambda \(x,y\): x\+y", "lambda x_y: x_y[0]+x_y[1]", src, 3)
+    src = _must_sub(r"m = len\(seq\)/2", "m = len(seq)//2", src, 1)
+    src = _must_sub(r"akmers\.mers\.items\(\)\[0\]", "list(akmers.mers.items())[0]", src, 1)
+    src = _must_sub(r"self\.contigs\.keys\(\)\[0\]", "list(self.contigs.keys())[0]", src, 1)
+    src = _must_sub(r"for mer in list\(x\) :", "for mer in sorted(x) :", src, 1)
+
+    asm = types.ModuleType("sv_assembly")
+    asm.__file__ = os.path.join(REFERENCE_ROOT, "sv_assembly.py")
+    asm.__dict__.update(map=_eager_map, filter=_eager_filter, zip=_eager_zip, fq_read=fq_read)
+    saved = sys.modules.get("olc")
+    sys.modules["olc"] = olc
+    try:
+        exec(compile(src, asm.__file__, "exec"), asm.__dict__)
+    finally:
+        if saved is None:
+            del sys.modules["olc"]
+        else:
+            sys.modules["olc"] = saved
+    return olc, asm
