@@ -1,0 +1,376 @@
+// C ABI of breakmer_b200 (include/breakmer_b200.h).  Host orchestration only:
+// every byte of arithmetic on the hot path runs in the kernels of this
+// directory.  There is no CPU fallback -- without a CUDA device bk_create fails.
+#include "../../include/breakmer_b200.h"
+
+#include <algorithm>
+#include <memory>
+
+#include "host_util.cuh"
+#include "kmers.cuh"
+#include "nw_batch.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "pipeline.cuh"
+
+using namespace bk;
+
+struct bk_handle_s {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  int sm_count = 148;
+  Arena<false> dev;        // per-call device scratch
+  Arena<true> pin;         // per-call pinned host staging / results
+  Arena<false> resident;   // bk_batch_upload
+  KernelTimers timers;
+  std::string err;
+  std::unique_ptr<Pipeline> pipe;
+  // bk_kernel_times result storage
+  double kt_ms[KF_COUNT_];
+  int64_t kt_launches[KF_COUNT_];
+};
+
+namespace {
+
+template <typename F>
+int guarded(bk_handle_t h, F&& f) {
+  if (!h) return BK_ERR_ARG;
+  try {
+    BK_CUDA(cudaSetDevice(h->device));
+    f();
+    return BK_OK;
+  } catch (const ApiError& e) {
+    h->err = e.msg;
+    return e.code;
+  } catch (const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at api line %d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
+    h->err = buf;
+    cudaGetLastError();
+    return BK_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    h->err = "host allocation failed";
+    return BK_ERR_NOMEM;
+  }
+}
+
+template <typename T>
+T* to_device(bk_handle_t h, Arena<false>& a, const T* src, size_t n) {
+  T* d = a.get<T>(n ? n : 1);
+  if (n) BK_CUDA(cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->st));
+  return d;
+}
+
+int bits_for(uint64_t n_values) {   // bits needed to represent 0 .. n_values-1
+  int b = 0;
+  while (b < 63 && (1ull << b) < n_values) ++b;
+  return b;
+}
+
+// sort + run-length select + compaction on keys already emitted on the device.
+// Returns n_selected; device outputs through the pointers.
+struct SelectOut {
+  uint64_t* mers;
+  uint32_t* counts;
+  int64_t n;
+  uint32_t* seg_counts;   // device, n_seg (or null)
+};
+
+SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int tag_bits, int seg_bits,
+                          int mode, int64_t n_seg) {
+  SelectOut o{nullptr, nullptr, 0, nullptr};
+  cudaStream_t st = h->st;
+  if (n_seg > 0) {
+    o.seg_counts = h->dev.get<uint32_t>(n_seg);
+    BK_CUDA(cudaMemsetAsync(o.seg_counts, 0, n_seg * sizeof(uint32_t), st));
+  }
+  if (n == 0) return o;
+  const int64_t tiles = rs_num_tiles(n);
+  RadixSortScratch sc;
+  sc.keys_alt = h->dev.get<uint64_t>(n);
+  sc.vals_alt = h->dev.get<uint32_t>(n);
+  sc.table = h->dev.get<uint32_t>(256 * tiles);
+  sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
+  uint64_t* sk;
+  uint32_t* sv;
+  const int key_bits = 2 * k + tag_bits + seg_bits + 1;   // +1: the all-ones invalid key sorts last
+  radix_sort_pairs(keys, vals, n, key_bits, sc, st, &sk, &sv, h->timers);
+  RunParams rp{};
+  rp.keys = sk; rp.vals = sv; rp.n = n; rp.tag_bits = tag_bits; rp.k = k; rp.mode = mode;
+  rp.flags = h->dev.get<uint32_t>(n);
+  rp.run_count = h->dev.get<uint32_t>(n);
+  uint32_t* pos = h->dev.get<uint32_t>(n);
+  uint32_t* d_total = h->dev.get<uint32_t>(1);
+  uint32_t* scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(n));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  {
+    TimedLaunch t(h->timers, st, KF_RUN_SELECT);
+    run_select_kernel<<<blocks, 256, 0, st>>>(rp);
+  }
+  {
+    TimedLaunch t(h->timers, st, KF_SCAN, 3);
+    exclusive_scan_u32(rp.flags, pos, n, scan_tmp, d_total, st);
+  }
+  uint32_t* h_total = h->pin.get<uint32_t>(1);
+  BK_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  BK_CUDA(cudaStreamSynchronize(st));
+  o.n = *h_total;
+  o.mers = h->dev.get<uint64_t>(o.n ? o.n : 1);
+  o.counts = h->dev.get<uint32_t>(o.n ? o.n : 1);
+  rp.pos = pos; rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts;
+  {
+    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
+    run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
+  }
+  BK_CUDA(cudaGetLastError());
+  return o;
+}
+
+}  // namespace
+
+// expose helpers to pipeline.cu-style code in this TU
+#include "pipeline_impl.cuh"
+
+extern "C" {
+
+int bk_version(void) { return 1; }
+
+int bk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int bk_create(int device, bk_handle_t* out) {
+  if (!out) return BK_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return BK_ERR_CUDA; }   // no fallback
+  if (device < 0 || device >= n) return BK_ERR_ARG;
+  bk_handle_t h = new (std::nothrow) bk_handle_s();
+  if (!h) return BK_ERR_NOMEM;
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    delete h;
+    return BK_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  *out = h;
+  return BK_OK;
+}
+
+int bk_destroy(bk_handle_t h) {
+  if (!h) return BK_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->st);
+  h->pipe.reset();
+  h->dev.release();
+  h->pin.release();
+  h->resident.release();
+  cudaStreamDestroy(h->st);
+  delete h;
+  return BK_OK;
+}
+
+const char* bk_last_error(bk_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq, const int32_t* pair_a,
+                const int32_t* pair_b, int64_t n_pairs, int32_t* out, int want_aln, char* aln1, char* aln2,
+                const int64_t* aln_off, int32_t* aln_len) {
+  return guarded(h, [&] {
+    if (n_pairs < 0 || n_seq < 0 || (n_pairs > 0 && (!seqs || !seq_off || !pair_a || !pair_b || !out)))
+      fail(BK_ERR_ARG, "bk_nw_batch: null argument");
+    if (want_aln && (!aln1 || !aln2 || !aln_off || !aln_len)) fail(BK_ERR_ARG, "bk_nw_batch: alignment buffers missing");
+    if (n_pairs == 0) return;
+    h->dev.reset();
+    h->pin.reset();
+    int max_m = 0;
+    std::vector<int64_t> ptr_off;
+    int64_t ptr_total = 0, aln_total = 0;
+    if (want_aln) ptr_off.resize(n_pairs);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+      const int a = pair_a[p], b = pair_b[p];
+      if (a < 0 || a >= n_seq || b < 0 || b >= n_seq) fail(BK_ERR_ARG, "bk_nw_batch: pair %lld out of range", (long long)p);
+      const int64_t m = seq_off[a + 1] - seq_off[a], n = seq_off[b + 1] - seq_off[b];
+      if (m <= 0 || n <= 0) fail(BK_ERR_EMPTY_SEQ, "nw: empty sequence in pair %lld (olc.nw raises NameError)", (long long)p);
+      if (m > NW_MAX_LEN || n > NW_MAX_LEN)
+        fail(BK_ERR_CAPACITY, "nw: sequence longer than %d bases in pair %lld", NW_MAX_LEN, (long long)p);
+      max_m = std::max<int>(max_m, (int)m);
+      if (want_aln) {
+        ptr_off[p] = ptr_total;
+        ptr_total += (m + 1) * (n + 1);
+        aln_total = std::max<int64_t>(aln_total, aln_off[p] + m + n);
+      }
+    }
+    NwBatchParams P{};
+    P.seqs = (const uint8_t*)to_device(h, h->dev, seqs, (size_t)seq_off[n_seq]);
+    P.seq_off = to_device(h, h->dev, seq_off, (size_t)n_seq + 1);
+    P.pair_a = to_device(h, h->dev, pair_a, (size_t)n_pairs);
+    P.pair_b = to_device(h, h->dev, pair_b, (size_t)n_pairs);
+    P.n_pairs = n_pairs;
+    P.out = h->dev.get<int32_t>(n_pairs * 10);
+    int64_t want_blocks = (n_pairs + NWB_WARPS - 1) / NWB_WARPS;
+    const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)h->sm_count * 8);
+    if (max_m > 256) {
+      P.edge_stride = NW_MAX_LEN + 1;
+      P.edge = h->dev.get<int2>((size_t)grid * NWB_WARPS * 2 * P.edge_stride);
+    }
+    P.want_aln = want_aln;
+    if (want_aln) {
+      P.ptr_scratch = h->dev.get<uint8_t>(ptr_total);
+      P.ptr_off = to_device(h, h->dev, ptr_off.data(), (size_t)n_pairs);
+      P.aln1 = h->dev.get<uint8_t>(aln_total);
+      P.aln2 = h->dev.get<uint8_t>(aln_total);
+      P.aln_off = to_device(h, h->dev, aln_off, (size_t)n_pairs);
+      P.aln_len = h->dev.get<int32_t>(n_pairs);
+    }
+    {
+      TimedLaunch t(h->timers, h->st, KF_NW_BATCH);
+      nw_batch_kernel<<<grid, NWB_WARPS * 32, 0, h->st>>>(P);
+    }
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaMemcpyAsync(out, P.out, n_pairs * 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+    if (want_aln) {
+      BK_CUDA(cudaMemcpyAsync(aln1, P.aln1, aln_total, cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(aln2, P.aln2, aln_total, cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(aln_len, P.aln_len, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+    }
+    BK_CUDA(cudaStreamSynchronize(h->st));
+    if (want_aln) {
+      // the device walks the traceback from the end cell, so the strings arrive
+      // end-first (olc.py:92-102 prepends); put them in reading order
+      for (int64_t p = 0; p < n_pairs; ++p) {
+        std::reverse(aln1 + aln_off[p], aln1 + aln_off[p] + aln_len[p]);
+        std::reverse(aln2 + aln_off[p], aln2 + aln_off[p] + aln_len[p]);
+      }
+    }
+  });
+}
+
+int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int64_t n_rec, const uint32_t* rec_mult,
+                   int k, const uint64_t** mers, const uint32_t** counts, int64_t* n_out) {
+  return guarded(h, [&] {
+    if (!mers || !counts || !n_out || n_rec < 0 || (n_rec > 0 && (!bases || !rec_off)))
+      fail(BK_ERR_ARG, "bk_count_kmers: null argument");
+    if (k < 1 || k > 31) fail(BK_ERR_ARG, "bk_count_kmers: k must be in 1..31");
+    h->dev.reset();
+    h->pin.reset();
+    *mers = nullptr; *counts = nullptr; *n_out = 0;
+    // drop empty records (they hold no window) so record starts are distinct
+    std::vector<int64_t> off;
+    std::vector<uint32_t> mult;
+    off.reserve(n_rec + 1);
+    for (int64_t r = 0; r < n_rec; ++r) {
+      if (rec_off[r + 1] < rec_off[r]) fail(BK_ERR_ARG, "bk_count_kmers: rec_off not monotone");
+      if (rec_off[r + 1] > rec_off[r]) {
+        off.push_back(rec_off[r] - rec_off[0]);
+        if (rec_mult) mult.push_back(rec_mult[r]);
+      }
+    }
+    const int64_t n_bases = n_rec ? rec_off[n_rec] - rec_off[0] : 0;
+    off.push_back(n_bases);
+    if (n_bases == 0) return;
+    EmitParams E{};
+    E.bases = (const uint8_t*)to_device(h, h->dev, bases + rec_off[0], (size_t)n_bases);
+    E.n_bases = n_bases;
+    E.rec_off = to_device(h, h->dev, off.data(), off.size());
+    E.n_rec = (int64_t)off.size() - 1;
+    E.rec_mult = rec_mult ? to_device(h, h->dev, mult.data(), mult.size()) : nullptr;
+    E.k = k; E.tag = 0; E.tag_bits = 0; E.emit_rc = 0;
+    E.keys = h->dev.get<uint64_t>(n_bases);
+    E.vals = h->dev.get<uint32_t>(n_bases);
+    {
+      TimedLaunch t(h->timers, h->st, KF_EMIT);
+      kmer_emit_kernel<<<(unsigned)((n_bases + EMIT_TILE - 1) / EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
+    }
+    SelectOut so = sort_and_select(h, E.keys, E.vals, n_bases, k, 0, 0, SELECT_ALL, 0);
+    uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
+    uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
+    if (so.n) {
+      BK_CUDA(cudaMemcpyAsync(hm, so.mers, so.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(hc, so.counts, so.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    }
+    BK_CUDA(cudaStreamSynchronize(h->st));
+    *mers = hm; *counts = hc; *n_out = so.n;
+  });
+}
+
+int bk_sample_only(bk_handle_t h, int k, const uint64_t* case_mers, const uint32_t* case_counts, int64_t n_case,
+                   const uint64_t* sc_mers, int64_t n_sc, const uint64_t* ref_mers, int64_t n_ref,
+                   const uint64_t* normal_mers, int64_t n_normal, const uint64_t** mers, const uint32_t** counts,
+                   int64_t* n_out) {
+  return guarded(h, [&] {
+    if (!mers || !counts || !n_out) fail(BK_ERR_ARG, "bk_sample_only: null output");
+    if (k < 1 || k > 30) fail(BK_ERR_ARG, "bk_sample_only: k must be in 1..30");
+    if ((n_case && (!case_mers || !case_counts)) || (n_sc && !sc_mers) || (n_ref && !ref_mers) || (n_normal && !normal_mers))
+      fail(BK_ERR_ARG, "bk_sample_only: null input");
+    h->dev.reset();
+    h->pin.reset();
+    *mers = nullptr; *counts = nullptr; *n_out = 0;
+    const int64_t n = n_case + n_sc + n_ref + n_normal;
+    if (n == 0) return;
+    // one key per (mer, set); the device sorts them so that the sets of a mer
+    // become adjacent, then run_select applies (case & sc) - ref - normal
+    uint64_t* hk = h->pin.get<uint64_t>(n);
+    uint32_t* hv = h->pin.get<uint32_t>(n);
+    int64_t w = 0;
+    for (int64_t i = 0; i < n_case; ++i, ++w) { hk[w] = (case_mers[i] << 2) | TAG_CASE; hv[w] = case_counts[i]; }
+    for (int64_t i = 0; i < n_sc; ++i, ++w) { hk[w] = (sc_mers[i] << 2) | TAG_SC; hv[w] = 1; }
+    for (int64_t i = 0; i < n_ref; ++i, ++w) { hk[w] = (ref_mers[i] << 2) | TAG_REF; hv[w] = 1; }
+    for (int64_t i = 0; i < n_normal; ++i, ++w) { hk[w] = (normal_mers[i] << 2) | TAG_NORMAL; hv[w] = 1; }
+    uint64_t* dk = to_device(h, h->dev, hk, (size_t)n);
+    uint32_t* dv = to_device(h, h->dev, hv, (size_t)n);
+    SelectOut so = sort_and_select(h, dk, dv, n, k, 2, 0, SELECT_SAMPLE_ONLY, 0);
+    uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
+    uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
+    if (so.n) {
+      BK_CUDA(cudaMemcpyAsync(hm, so.mers, so.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(hc, so.counts, so.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    }
+    BK_CUDA(cudaStreamSynchronize(h->st));
+    *mers = hm; *counts = hc; *n_out = so.n;
+  });
+}
+
+int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out) {
+  return guarded(h, [&] {
+    if (!in || !out) fail(BK_ERR_ARG, "bk_compare_kmers_batch: null argument");
+    pipeline_run(h, in, /*resident=*/false, out);
+  });
+}
+
+int bk_batch_upload(bk_handle_t h, const bk_batch_input* in) {
+  return guarded(h, [&] {
+    if (!in) fail(BK_ERR_ARG, "bk_batch_upload: null argument");
+    pipeline_upload(h, in);
+  });
+}
+
+int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out) {
+  return guarded(h, [&] {
+    if (!out) fail(BK_ERR_ARG, "bk_compare_kmers_resident: null argument");
+    pipeline_run(h, nullptr, /*resident=*/true, out);
+  });
+}
+
+int bk_kernel_times(bk_handle_t h, const char** names, const double** ms, const int64_t** launches, int32_t* n) {
+  return guarded(h, [&] {
+    h->timers.collect();
+    for (int i = 0; i < KF_COUNT_; ++i) { h->kt_ms[i] = h->timers.ms[i]; h->kt_launches[i] = h->timers.launches[i]; }
+    if (names) *names = kKernelFamilyNames;
+    if (ms) *ms = h->kt_ms;
+    if (launches) *launches = h->kt_launches;
+    if (n) *n = KF_COUNT_;
+  });
+}
+
+int bk_kernel_times_reset(bk_handle_t h, int enable) {
+  return guarded(h, [&] {
+    BK_CUDA(cudaStreamSynchronize(h->st));
+    h->timers.reset();
+    h->timers.enabled = enable != 0;
+  });
+}
+
+}  // extern "C"

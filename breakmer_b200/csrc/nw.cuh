@@ -1,0 +1,233 @@
+// Overlap aligner: one warp computes BOTH directions of the reference's
+// `olc.nw` for a (contig, read) pair in a single sweep of the DP table.
+//
+// Replaces olc.py:40-107 (`nw`) as called from sv_assembly.py:451-452
+// (`v1 = nw(contig, read)`, `v2 = nw(read, contig)`).
+//
+// Observations the kernel is built on (each is checked by tests against the
+// oracle, which is pinned to the reference's own output):
+//   1. The score table of nw(b, a) is the transpose of the score table of
+//      nw(a, b): the recurrence max(diag, up-2, left-2) is symmetric.  Only the
+//      pointer priority (diag > up > left, olc.py:69-74) and the end-cell scan
+//      (last column, largest row on ties, olc.py:79-83) are direction specific.
+//   2. The caller never needs the alignment strings, only where the traceback
+//      ends.  That origin can be carried forward with the score: a cell
+//      inherits the origin of the predecessor its pointer selects, and the
+//      traceback stops at the first cell with i == 0 or j == 0 (olc.py:105).
+//      An origin is therefore a boundary cell, encoded as (j - i).
+//   3. score, pointer tag and origin pack into one 32-bit word
+//          [ score : 14 | tag : 2 | origin+32768 : 16 ]
+//      so that a signed max over the three candidates selects the score, breaks
+//      ties by pointer priority and carries the origin -- 4 integer ops per
+//      direction per cell with the DPX add-max instruction (VIADDMNMX).
+//   Two words are kept per cell, one per direction (they differ in the tag
+//   order of the two gap moves).
+//
+// Layout: the "column" sequence (length m) is spread over the 32 lanes, C
+// consecutive columns per lane in registers; rows are swept systolically (lane
+// L works on row t-L at step t, its left neighbour's column arrives by
+// shuffle).  Column sequences longer than 32*C are processed in column blocks,
+// the block boundary column travelling through a scratch buffer.
+//
+// In the terms of olc.nw, for dev-frame A = nw(colseq, rowseq): colseq is seq1
+// (index j), rowseq is seq2 (index i); B = nw(rowseq, colseq).
+#pragma once
+#include "common.cuh"
+
+namespace bk {
+
+struct NwOut {   // fields [2:7] of the tuple olc.nw returns (olc.py:107)
+  int prej, j0, prei, i0, score;
+};
+struct NwDual {
+  NwOut a;   // nw(colseq, rowseq)
+  NwOut b;   // nw(rowseq, colseq)
+};
+
+constexpr int NW_SHIFT = 18;
+constexpr int NW_BIAS = 32768;
+constexpr int NW_TAG_CLEAR = ~(3 << 16);
+constexpr int NW_ONE = 1 << NW_SHIFT;
+// candidate increments: score delta in the top field, pointer tag in bits 16-17
+constexpr int NW_D_MATCH = 1 * NW_ONE + (3 << 16);
+constexpr int NW_D_MISM = -2 * NW_ONE + (3 << 16);
+constexpr int NW_GAP_HI = -2 * NW_ONE + (2 << 16);   // the gap move with priority 2
+constexpr int NW_GAP_LO = -2 * NW_ONE + (1 << 16);   // the gap move with priority 1
+
+BK_HD void nw_decode_a(int best_q, int best_i, int m, NwOut& o) {
+  o.prej = m;
+  o.prei = best_i;
+  o.score = best_q >> NW_SHIFT;
+  if (best_i == 0) {           // pointer[0][m] == 2: one step left (olc.py:58-59,96-99)
+    o.j0 = m - 1;
+    o.i0 = 0;
+  } else {
+    int e = (best_q & 0xffff) - NW_BIAS;
+    o.j0 = e >= 0 ? e : 0;
+    o.i0 = e >= 0 ? 0 : -e;
+  }
+}
+// B = nw(rowseq, colseq): its seq1 is rowseq (length n), its rows run over colseq
+BK_HD void nw_decode_b(int best_q, int best_j, int n, NwOut& o) {
+  o.prej = n;
+  o.prei = best_j;
+  o.score = best_q >> NW_SHIFT;
+  if (best_j == 0) {
+    o.j0 = n - 1;
+    o.i0 = 0;
+  } else {
+    int e = (best_q & 0xffff) - NW_BIAS;   // dev-frame origin (i0d, j0d)
+    int j0d = e >= 0 ? e : 0, i0d = e >= 0 ? 0 : -e;
+    o.j0 = i0d;   // start in rowseq
+    o.i0 = j0d;   // start in colseq
+  }
+}
+
+#ifdef BK_SIM
+// ---------------------------------------------------------------------------
+// tests/sim only: scalar stand-in with the same contract (host debugging of the
+// assembler control logic).  Not compiled into the product library.
+// ---------------------------------------------------------------------------
+struct int2 { int x, y; };
+template <int C, bool PTR>
+inline void nw_dual_warp(const uint8_t* cs, int m, const uint8_t* rs, int n, int2*, int2*, uint8_t* ptrmat, NwDual& out) {
+  (void)ptrmat;
+  static thread_local int *qa = nullptr, *qb = nullptr;
+  static thread_local size_t cap = 0;
+  size_t need = (size_t)(m + 1) * 2;
+  if (need > cap) { delete[] qa; delete[] qb; qa = new int[need]; qb = new int[need]; cap = need; }
+  int* pa = qa; int* ca = qa + (m + 1);
+  int* pb = qb; int* cb = qb + (m + 1);
+  for (int j = 0; j <= m; ++j) pa[j] = pb[j] = NW_BIAS + j;
+  int best_a = pa[m], best_ai = 0;
+  int best_b = NW_BIAS, best_bj = 0;
+  if (n == 0) { /* unreachable: callers reject empty sequences */ }
+  for (int i = 1; i <= n; ++i) {
+    ca[0] = cb[0] = NW_BIAS - i;
+    for (int j = 1; j <= m; ++j) {
+      int s = (cs[j - 1] == rs[i - 1]) ? NW_D_MATCH : NW_D_MISM;
+      int a = pa[j - 1] + s, h = ca[j - 1] + NW_GAP_HI, v = pa[j] + NW_GAP_LO;
+      int r = a > h ? a : h; r = r > v ? r : v;
+      ca[j] = r & NW_TAG_CLEAR;
+      a = pb[j - 1] + s; h = cb[j - 1] + NW_GAP_LO; v = pb[j] + NW_GAP_HI;
+      r = a > h ? a : h; r = r > v ? r : v;
+      cb[j] = r & NW_TAG_CLEAR;
+    }
+    if ((ca[m] >> NW_SHIFT) >= (best_a >> NW_SHIFT)) { best_a = ca[m]; best_ai = i; }
+    int* t = pa; pa = ca; ca = t; t = pb; pb = cb; cb = t;
+  }
+  for (int j = 0; j <= m; ++j)
+    if ((pb[j] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = pb[j]; best_bj = j; }
+  nw_decode_a(best_a, best_ai, m, out.a);
+  nw_decode_b(best_b, best_bj, n, out.b);
+}
+#else
+// ---------------------------------------------------------------------------
+// The product kernel.
+// ---------------------------------------------------------------------------
+template <int C, bool PTR>
+__device__ __forceinline__ void nw_dual_warp(const uint8_t* __restrict__ cs, int m,
+                                             const uint8_t* __restrict__ rs, int n,
+                                             int2* edge0, int2* edge1, uint8_t* ptrmat, NwDual& out) {
+  const unsigned FULL = 0xffffffffu;
+  const int L = lane();
+  constexpr int W = 32 * C;
+  const int nblk = (m + W - 1) / W;
+  int best_a = NW_BIAS + m, best_ai = 0;        // score[0][m] = 0 (olc.py:79-83 starts at row 0)
+  int best_b = NW_BIAS, best_bj = 0;            // score[n][0] = 0
+  for (int b = 0; b < nblk; ++b) {
+    const int jb = b * W;
+    const int jfirst = jb + L * C + 1;          // 1-based column held in slot 0
+    int colA[C], colB[C], ch[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = jfirst + c;
+      colA[c] = colB[c] = NW_BIAS + j;          // row 0: score 0, origin (0, j)
+      ch[c] = (j <= m) ? (int)cs[j - 1] : 0x100;
+    }
+    int diagA = NW_BIAS + (jfirst - 1), diagB = diagA;
+    int lastA = colA[C - 1], lastB = colB[C - 1];
+    const int2* ein = (b & 1) ? edge1 : edge0;
+    int2* eout = (b & 1) ? edge0 : edge1;
+    const bool more = (b + 1 < nblk);
+    const bool has_last = (m > jb) && (m <= jb + W);
+    const int own_lane = (m - 1 - jb) / C, own_c = (m - 1 - jb) % C;
+    const int steps = n + 31;
+    for (int t = 0; t < steps; ++t) {
+      int hA = __shfl_up_sync(FULL, lastA, 1);
+      int hB = __shfl_up_sync(FULL, lastB, 1);
+      const int i = t - L + 1;
+      const bool active = (i >= 1) && (i <= n);
+      if (L == 0) {
+        if (b == 0) {
+          hA = hB = NW_BIAS - i;                // column 0: score 0, origin (i, 0)
+        } else if (active) {
+          const int2 e = ein[i];
+          hA = e.x; hB = e.y;
+        }
+      }
+      if (active) {
+        const int rc = (int)rs[i - 1];
+        int dA = diagA, dB = diagB;
+        diagA = hA; diagB = hB;
+        unsigned ptrs = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int vA = colA[c], vB = colB[c];
+          const int s = (ch[c] == rc) ? NW_D_MATCH : NW_D_MISM;
+          // direction A (olc.py:64-74): diag(3) > score[i][j-1] (2) > score[i-1][j] (1)
+          int tA = dA + s;
+          tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
+          tA = __viaddmax_s32(vA, NW_GAP_LO, tA);
+          // direction B is the transpose, so the two gap moves swap priority
+          int tB = dB + s;
+          tB = __viaddmax_s32(vB, NW_GAP_HI, tB);
+          tB = __viaddmax_s32(hB, NW_GAP_LO, tB);
+          if (PTR) ptrs |= ((unsigned)(tA >> 16) & 3u) << (2 * c);
+          dA = vA; dB = vB;
+          hA = tA & NW_TAG_CLEAR; hB = tB & NW_TAG_CLEAR;
+          colA[c] = hA; colB[c] = hB;
+        }
+        lastA = colA[C - 1]; lastB = colB[C - 1];
+        if (PTR) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if (jfirst + c <= m) ptrmat[(size_t)i * (m + 1) + jfirst + c] = (uint8_t)((ptrs >> (2 * c)) & 3u);
+        }
+        if (more && L == 31) eout[i] = make_int2(lastA, lastB);
+        if (has_last && L == own_lane) {
+          int cand = colA[0];
+#pragma unroll
+          for (int c = 1; c < C; ++c) cand = (c == own_c) ? colA[c] : cand;
+          if ((cand >> NW_SHIFT) >= (best_a >> NW_SHIFT)) { best_a = cand; best_ai = i; }
+        }
+        if (i == n) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if (jfirst + c <= m && (colB[c] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = colB[c]; best_bj = jfirst + c; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // A lives on the lane that owns column m of the last block
+  {
+    const int jb = (nblk - 1) * W;
+    const int own_lane = (m - 1 - jb) / C;
+    best_a = __shfl_sync(FULL, best_a, own_lane);
+    best_ai = __shfl_sync(FULL, best_ai, own_lane);
+  }
+  // B: max score over the last row, largest column on ties (olc.py:81 uses >=)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int oq = __shfl_xor_sync(FULL, best_b, off);
+    const int oj = __shfl_xor_sync(FULL, best_bj, off);
+    const int s0 = best_b >> NW_SHIFT, s1 = oq >> NW_SHIFT;
+    if (s1 > s0 || (s1 == s0 && oj > best_bj)) { best_b = oq; best_bj = oj; }
+  }
+  nw_decode_a(best_a, best_ai, m, out.a);
+  nw_decode_b(best_b, best_bj, n, out.b);
+}
+#endif  // BK_SIM
+
+}  // namespace bk

@@ -1,0 +1,155 @@
+/* breakmer_b200 -- C ABI of the B200-native BreaKmer k-mer assembly hot path.
+ *
+ * The reference (ccgd-profile/BreaKmer) has no FFI: its boundary for this path is
+ * a set of plain Python call sites.  Each entry point
+ * below names the reference interface it stands in for; the Python shims in
+ * breakmer_b200/ (olc.py, utils.py, sv_assembly.py, sv_processor.py) keep the
+ * reference's function names and argument meaning and call these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / CUDA types in any signature;
+ *   - inputs are caller-owned HOST buffers; they are copied to the device inside
+ *     the call (the *_dev timing entry points are the only exception);
+ *   - outputs returned through `const T**` live in library-owned pinned host
+ *     arenas and stay valid until the next call on the same handle or
+ *     bk_destroy; outputs passed as plain `T*` are caller-owned buffers;
+ *   - every function returns 0 on success or a negative BK_ERR_* code, and
+ *     bk_last_error(h) gives the message;
+ *   - one handle = one CUDA device + one stream; calls on one handle must not
+ *     overlap; distinct handles may be used from distinct host threads
+ *     (one handle per GPU is the multi-GPU model: regions are sharded by the
+ *     caller, there is no collective).
+ *   - sequences are ASCII; A/C/G/T (either case for counting) are bases, any
+ *     other byte behaves like 'N'.
+ */
+#ifndef BREAKMER_B200_H
+#define BREAKMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_OK 0
+#define BK_ERR_CUDA (-1)
+#define BK_ERR_ARG (-2)
+#define BK_ERR_NOMEM (-3)
+#define BK_ERR_CAPACITY (-4)  /* a sequence exceeds a device-side hard limit (4095 bases for nw) */
+#define BK_ERR_EMPTY_SEQ (-5) /* olc.nw raises NameError on an empty sequence (olc.py:86-87) */
+
+typedef struct bk_handle_s* bk_handle_t;
+
+int bk_version(void);
+int bk_device_count(void);
+int bk_create(int device, bk_handle_t* out);
+int bk_destroy(bk_handle_t h);
+const char* bk_last_error(bk_handle_t h);
+
+/* ---- olc.nw (olc.py:40-107; call sites sv_assembly.py:451-452) ----------------
+ * For pair p: seq1 = sequence pair_a[p], seq2 = sequence pair_b[p] of the
+ * concatenated `seqs` (seq_off has n_seq+1 entries).
+ * out[p*10 + 0..4] = fields [2:7] of nw(seq1, seq2): prej, j, prei, i, max_i
+ * out[p*10 + 5..9] = the same five fields of nw(seq2, seq1) (computed in the same
+ *                    sweep; check_align always needs both).
+ * If want_aln != 0, align1/align2 of nw(seq1, seq2) (tuple fields [0:2]) are
+ * written to aln1/aln2 at aln_off[p] (capacity len(seq1)+len(seq2) each) and
+ * their common length to aln_len[p]. */
+int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq,
+                const int32_t* pair_a, const int32_t* pair_b, int64_t n_pairs, int32_t* out,
+                int want_aln, char* aln1, char* aln2, const int64_t* aln_off, int32_t* aln_len);
+
+/* ---- run_jellyfish + load_kmers (utils.py:151-179, 287-297) --------------------
+ * Strand-specific k-mer occurrence counts over n_rec records (`bases`
+ * concatenated, rec_off has n_rec+1 entries, rec_mult optional per-record
+ * multiplicity).  Returns the distinct k-mers in ascending 2-bit code order
+ * (A<C<G<T, first base most significant) with their counts.  1 <= k <= 31. */
+int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int64_t n_rec,
+                   const uint32_t* rec_mult, int k,
+                   const uint64_t** mers, const uint32_t** counts, int64_t* n_out);
+
+/* ---- the set algebra of target.compare_kmers (sv_processor.py:621-622, 630-631)
+ * plus normal-sample subtraction.  Inputs are sorted unique k-mer
+ * arrays as bk_count_kmers returns them; normal may be null/0.
+ * Result: sample_only = (case & case_sc) - ref - normal, counts taken from case. */
+int bk_sample_only(bk_handle_t h, int k,
+                   const uint64_t* case_mers, const uint32_t* case_counts, int64_t n_case,
+                   const uint64_t* sc_mers, int64_t n_sc,
+                   const uint64_t* ref_mers, int64_t n_ref,
+                   const uint64_t* normal_mers, int64_t n_normal,
+                   const uint64_t** mers, const uint32_t** counts, int64_t* n_out);
+
+/* ---- the whole hot path for a batch of target regions -----------------------------
+ * target.compare_kmers (sv_processor.py:609-645) for n_regions targets at once:
+ * k-mer counting of the four inputs, sample-only selection, grouping of identical
+ * reads (utils.py:239-244), and init_assembly (sv_assembly.py:30-63).
+ *
+ * Per-region record ranges: region r owns records [x_reg_off[r], x_reg_off[r+1]).
+ * read_flags[i] bit0 = fq_read.indel_only of record i.
+ * If have_mers != 0 the k-mer stage is skipped and in_mers/in_counts/in_mers_off
+ * give each region's sample-only k-mers (ascending) -- this is the shape of
+ * init_assembly(mers, fq_recs, kmer_len, rc_thresh, read_len) itself.
+ * read_len may be null (then max record length per region, utils.py:236). */
+typedef struct bk_batch_input {
+  int32_t n_regions;
+  int32_t k;
+  int32_t rc_thresh;
+  int32_t have_mers;
+  const char* ref_bases;   const int64_t* ref_off;                         /* n_regions+1 */
+  const char* read_bases;  const int64_t* read_off;  const int64_t* read_reg_off;  const uint8_t* read_flags;
+  const char* sc_bases;    const int64_t* sc_off;    const int64_t* sc_reg_off;
+  const char* normal_bases; const int64_t* normal_off; const int64_t* normal_reg_off;   /* optional */
+  const uint64_t* in_mers; const uint32_t* in_counts; const int64_t* in_mers_off;      /* have_mers */
+  const int32_t* read_len;                                                             /* optional */
+} bk_batch_input;
+
+/* All arrays are library-owned (valid until the next call on the handle).
+ * Contig c of region r: c in [ctg_reg_off[r], ctg_reg_off[r+1]), acceptance order.
+ *   sequence       ctg_seq[ctg_seq_off[c] .. ctg_seq_off[c+1])
+ *   count vectors  ctg_indel_only / ctg_others [ctg_cnt_off[c] .. ctg_cnt_off[c+1])
+ *                  (their length can differ from the sequence length)
+ *   kmer_locs      ctg_kmer_locs[ctg_seq_off[c] .. ) one int per base
+ *   reads          ctg_reads[ctg_reads_off[c] .. ) = record index (into the input
+ *                  read arrays) of the representative (first) record of each
+ *                  unique read in contig.reads
+ *   k-mer tuples   ctg_kmer_mer/pos/lth/dist/order [ctg_kmers_off[c] .. ) ; order
+ *                  0='for' 1='rev' 2='mid' (sv_assembly.py:130,142)
+ * Unique reads (fq_recs keys, insertion order): region r owns
+ * [uniq_reg_off[r], uniq_reg_off[r+1]); uniq_rec = representative record index,
+ * uniq_mult = len(fq_recs[seq]). */
+typedef struct bk_batch_result {
+  int32_t n_regions;
+  int64_t n_contigs;
+  const int64_t* so_off;  const uint64_t* so_mers;  const uint32_t* so_counts;
+  const int64_t* uniq_reg_off; const int32_t* uniq_rec; const uint32_t* uniq_mult;
+  const int64_t* ctg_reg_off;
+  const int64_t* ctg_seq_off;   const char* ctg_seq;   const int32_t* ctg_kmer_locs;
+  const int64_t* ctg_cnt_off;   const int32_t* ctg_indel_only; const int32_t* ctg_others;
+  const int64_t* ctg_reads_off; const int32_t* ctg_reads;
+  const int64_t* ctg_kmers_off; const uint64_t* ctg_kmer_mer; const int32_t* ctg_kmer_pos;
+  const int32_t* ctg_kmer_lth;  const int32_t* ctg_kmer_dist; const int32_t* ctg_kmer_order;
+  const int32_t* region_status;      /* 0 or BK_ERR_CAPACITY per region */
+  /* work counters of this call (for roofline arithmetic) */
+  int64_t n_check_align;             /* contig.check_align calls (each = two olc.nw) */
+  int64_t n_dp_cells;                /* sum over those of len(contig)*len(read) (one sweep each) */
+  int64_t n_kmer_occurrences;        /* windows emitted by the k-mer stage */
+  double  gpu_ms;                    /* device time of the call, CUDA events */
+} bk_batch_result;
+
+int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out);
+
+/* ---- timing support for bench.py ------------------------------------------------------
+ * bk_batch_upload copies a batch to the device once; bk_compare_kmers_resident then runs
+ * the whole device pipeline on the resident copy (no host->device input traffic in the
+ * call; results still come back).  bk_kernel_times returns the accumulated device time
+ * (ms, CUDA events on the handle's stream) and launch count per kernel family since the
+ * last bk_kernel_times_reset; names is a ';'-separated list in the same order. */
+int bk_batch_upload(bk_handle_t h, const bk_batch_input* in);
+int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out);
+int bk_kernel_times(bk_handle_t h, const char** names, const double** ms, const int64_t** launches, int32_t* n);
+int bk_kernel_times_reset(bk_handle_t h, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREAKMER_B200_H */

@@ -1,0 +1,82 @@
+"""GPU parity: bk_nw_batch (the olc.nw drop-in) against the reference's own
+outputs (golden) and against the oracle on fresh seeded pairs."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import nw_py
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from breakmer_b200 import _lib
+    h = _lib.Handle(0)
+    yield h
+    h.close()
+
+
+def _run(handle, pairs, want_aln=False):
+    seqs = []
+    pa, pb = [], []
+    for a, b in pairs:
+        pa.append(len(seqs)); seqs.append(a)
+        pb.append(len(seqs)); seqs.append(b)
+    return handle.nw_batch(seqs, pa, pb, want_aln=want_aln)
+
+
+def test_golden_pairs_both_directions(handle):
+    cases = golden("nw_golden.json")["cases"]
+    out, _ = _run(handle, [(c["seq1"], c["seq2"]) for c in cases])
+    for c, o in zip(cases, out):
+        assert list(o[:5]) == c["out"][2:], (c["seq1"], c["seq2"])
+        assert list(o[5:]) == list(nw_py.nw_fast(c["seq2"], c["seq1"])[2:])
+
+
+def test_golden_alignment_strings(handle):
+    cases = golden("nw_golden.json")["cases"]
+    out, alns = _run(handle, [(c["seq1"], c["seq2"]) for c in cases], want_aln=True)
+    for c, o, (a1, a2) in zip(cases, out, alns):
+        assert [a1, a2] + list(o[:5]) == c["out"]
+
+
+def test_random_pairs_incl_long_and_n(handle):
+    rng = random.Random(11)
+    pairs = []
+    for t in range(600):
+        la = rng.choice([1, 2, 17, 100, 101, 128, 129, 190, 256, 257, 300, 513, 700])
+        lb = rng.choice([1, 3, 31, 32, 33, 64, 100, 150, 260, 400])
+        g = "".join(rng.choice("ACGT") for _ in range(la + lb))
+        a = g[:la]
+        if t % 3 == 0:
+            b = "".join(rng.choice("ACGTN") for _ in range(lb))
+        elif t % 3 == 1:
+            ov = rng.randint(1, min(la, lb))
+            b = (a[la - ov:] + g[la:])[:lb]
+        else:
+            b = g[max(0, la - lb // 2):][:lb]
+        b = "".join(c if rng.random() > 0.02 else rng.choice("ACGTN") for c in b)
+        pairs.append((a, b) if t % 2 else (b, a))
+    out, _ = _run(handle, pairs)
+    for (a, b), o in zip(pairs, out):
+        assert list(o[:5]) == list(nw_py.nw_fast(a, b)[2:]), (a, b)
+        assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (a, b)
+
+
+def test_max_length_and_limits(handle):
+    from breakmer_b200 import _lib
+    rng = random.Random(3)
+    a = "".join(rng.choice("ACGT") for _ in range(4095))
+    b = a[3000:] + "".join(rng.choice("ACGT") for _ in range(500))
+    out, _ = _run(handle, [(a, b), (b, a)])
+    assert list(out[0][:5]) == list(nw_py.nw_fast(a, b)[2:])
+    assert list(out[1][:5]) == list(nw_py.nw_fast(b, a)[2:])
+    with pytest.raises(_lib.BreakmerError) as e:
+        _run(handle, [(a + "A", b)])
+    assert e.value.code == _lib.BK_ERR_CAPACITY
+    with pytest.raises(_lib.BreakmerError) as e:
+        _run(handle, [("", "ACGT")])
+    assert e.value.code == _lib.BK_ERR_EMPTY_SEQ      # the reference raises NameError here
