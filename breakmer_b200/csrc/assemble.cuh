@@ -1,0 +1,787 @@
+// Per-region greedy k-mer assembler: the reference's `init_assembly` and all it
+// drives (sv_assembly.py:11-63, 102-155, 160-267, 272-366, 379-411, 416-649),
+// executed by ONE WARP PER TARGET REGION, many regions per launch.
+//
+// The algorithm is a sequential, stateful state machine;
+// the device version keeps the reference's order of events exactly and spends
+// the warp's 32 lanes inside each step: the overlap DP (nw.cuh), scanning
+// posting lists, enumerating contig k-mers, vector updates.  All control flow is
+// warp-uniform; scalars are replicated in registers, shared state lives in
+// global memory (L1/L2 resident, a few hundred KB per region) and is written by
+// lane-strided loops or by lane 0, with __syncwarp() between producer and
+// consumer phases.
+//
+// Line citations are into /root/reference/sv_assembly.py; Q-numbers refer to
+// SURVEY.md section 8.1.  The CPU restatement of the same behaviour is
+// oracle/assembler_py.py (pinned to the reference); tests compare the two.
+//
+// Order policy for the two hash-order dependent spots: reads are
+// numbered in fq_recs insertion order and ties keep that order (Q9); the
+// alt-read candidate set is walked in ascending mer order (Q13).
+#pragma once
+#include "common.cuh"
+#include "nw.cuh"
+
+namespace bk {
+
+constexpr int ASM_CAP = 4096;          // contig / count-vector capacity (NW_MAX_LEN + 1)
+constexpr int ASM_BUF = 3 * ASM_CAP;   // gap buffers: data starts at ASM_CAP, may grow both ways
+constexpr int ASM_KCAP = 2 * ASM_CAP;  // contig k-mer tuple list capacity
+constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
+
+// ---- batch-wide inputs / state (device pointers) -----------------------------
+struct AsmParams {
+  int n_regions;
+  int k;
+  int rc_thresh;
+  // reads: raw records + unique-read table (fq_recs, utils.py:239-244, Q28)
+  const uint8_t* rbases;
+  const int64_t* roff;             // n_rec + 1
+  const int64_t* u_off;            // n_regions + 1 : unique reads of a region
+  const int32_t* u_rec;            // representative (first) record of each unique read
+  const uint32_t* u_mult;          // len(fq_recs[seq])
+  const uint8_t* u_io;             // reads[0].indel_only
+  const int32_t* read_len;         // per region: max record length (utils.py:236)
+  // sample-only k-mers (ascending per region) and derived tables
+  const int64_t* so_off;           // n_regions + 1
+  const uint64_t* so_mer;
+  const uint32_t* so_cnt;
+  const int32_t* seed_order;       // per region: local mer indices by (count, mer) descending (Q7)
+  const int64_t* post_off;         // total mers + 1 : k-mer -> read posting lists
+  const int32_t* post_read;        // local unique-read index, ascending within a list
+  const int32_t* post_pos;         // first position of the mer in that read
+  // mutable per-mer / per-read state (zero-initialised except m_alive)
+  uint8_t* m_alive;                // akmers.mers membership (homopolymers start dead, Q5)
+  uint8_t* m_used;                 // buffer.used_mers
+  uint32_t* m_checked;             // contig serial in whose checked_kmers the mer is
+  uint32_t* m_taken;               // finalize serial (check_alt_reads' mer_set)
+  uint8_t* r_used;                 // fq_read.used
+  uint8_t* r_deleted;              // key removed from fq_recs
+  uint8_t* r_queued;               // 1: contig pending in buffer.contigs, 2: left it
+  uint32_t* r_buf;                 // contig serial whose .buffer holds the read
+  uint32_t* r_inreads;             // contig serial whose .reads holds the read
+  int32_t* q_read;                 // buffer.contigs FIFO (per region slice of size U)
+  int32_t* q_seed;
+  int32_t* l_alt;                  // read_batch.alt / .delete, find_reads results (size U each)
+  int32_t* l_del;
+  int32_t* hit_u; int32_t* hit_pos; int32_t* hit2_u; int32_t* hit2_pos;
+  // per-warp scratch, slot = global warp index
+  uint8_t* w_cseq;                 // ASM_BUF bytes
+  int32_t* w_cnt;                  // 4 * ASM_BUF ints: io[2], ot[2]
+  int32_t* w_K;                    // 3 * ASM_KCAP ints: s, x, meta
+  int32_t* w_NK;                   // 3 * ASM_KCAP
+  uint64_t* w_wcode;               // ASM_CAP
+  int32_t* w_diff;                 // ASM_CAP + 1
+  int2* w_edge;                    // 2 * ASM_CAP int2, or null if no read is longer than 256
+  // work distribution
+  int* work_counter;
+  const int32_t* work_order;       // regions, most expensive first
+  // output arena (bump allocated)
+  unsigned long long* out_cursor;  // [0]=seq bytes [1]=count ints [2]=read ints [3]=kmer tuples [4]=contigs
+  unsigned long long cap_seq, cap_cnt, cap_reads, cap_kmers, cap_ctg;
+  uint8_t* o_seq; int32_t* o_locs;
+  int32_t* o_io; int32_t* o_ot;
+  int32_t* o_reads;
+  uint64_t* o_kmer_mer; int32_t* o_kmer_pos; int32_t* o_kmer_meta;
+  int64_t* o_desc;                 // per contig 10 x int64: region, ordinal, seq_off, seq_len, cnt_off, cnt_len,
+                                   //                        reads_off, n_reads, kmers_off, n_kmers
+  int32_t* region_status;
+  int32_t* region_ncontigs;
+  unsigned long long* stats;       // [0] check_align calls, [1] DP cells, [2] find_reads, [3] seeds
+};
+
+// ---- small warp helpers -----------------------------------------------------------------
+BK_DEV unsigned lane_lt_mask() { return (1u << lane()) - 1u; }
+BK_DEV int warp_min_i(int v) {
+#ifndef BK_SIM
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+BK_DEV int warp_max_i(int v) {
+#ifndef BK_SIM
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+
+// 2-bit code of the k-mer starting at seq[x]; false if it holds a non-ACGT byte
+BK_DEV bool window_code(const uint8_t* seq, int x, int k, uint64_t& code) {
+  uint64_t c = 0;
+  bool ok = true;
+  for (int t = 0; t < k; ++t) {
+    const int b = base_code_strict(seq[x + t]);
+    ok = ok && (b < 4);
+    c = (c << 2) | (uint64_t)(b & 3);
+  }
+  code = c;
+  return ok;
+}
+
+struct RegionCtx {
+  const AsmParams* P;
+  int region, k;
+  // mers
+  int S; int64_t gm0;
+  const uint64_t* mer; const uint32_t* cnt; const int32_t* seed_order;
+  uint8_t* alive; uint8_t* mused; uint32_t* checked; uint32_t* taken;
+  // reads
+  int U; int64_t gu0;
+  const int32_t* u_rec; const uint32_t* u_mult; const uint8_t* u_io;
+  uint8_t* r_used; uint8_t* r_deleted; uint8_t* r_queued; uint32_t* r_buf; uint32_t* r_inreads;
+  int32_t* q_read; int32_t* q_seed; int q_head, q_tail;
+  int32_t* l_alt; int32_t* l_del; int n_alt, n_del;
+  int32_t* hit_u; int32_t* hit_pos; int32_t* hit2_u; int32_t* hit2_pos;
+  // contig under construction
+  uint8_t* cseq; int c0, clen;
+  int32_t* cnt_buf; int cur, k0, klen;
+  int32_t* K; int nK;
+  int32_t* NK; int nNK;
+  uint64_t* wcode; int32_t* diff; int2* edge;
+  uint32_t serial, fin_serial;
+  bool ct_setup, ct_finalized;
+  int ct_init_read;
+  int status;
+  int n_out;
+  // staging (shared memory on the device)
+  uint8_t* s_read; uint8_t* s_contig;
+
+  BK_DEV int32_t* io_vec(int which) const { return cnt_buf + (size_t)which * ASM_BUF; }
+  BK_DEV int32_t* ot_vec(int which) const { return cnt_buf + (size_t)(2 + which) * ASM_BUF; }
+  BK_DEV int read_len_of(int u) const {
+    const int rec = u_rec[u];
+    return (int)(P->roff[rec + 1] - P->roff[rec]);
+  }
+  BK_DEV const uint8_t* read_ptr(int u) const { return P->rbases + P->roff[u_rec[u]]; }
+};
+
+// binary search of a code in the region's ascending mer table; -1 if absent
+BK_DEV int find_mer(const RegionCtx& c, uint64_t code) {
+  int lo = 0, hi = c.S;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint64_t v = c.mer[mid];
+    if (v < code) lo = mid + 1; else hi = mid;
+  }
+  return (lo < c.S && c.mer[lo] == code) ? lo : -1;
+}
+
+BK_DEV int stage_read(RegionCtx& c, int u) {
+  const int n = c.read_len_of(u);
+  const uint8_t* src = c.read_ptr(u);
+  syncwarp();
+  for (int x = lane(); x < n; x += WARP) c.s_read[x] = src[x];
+  syncwarp();
+  return n;
+}
+BK_DEV void sync_contig_to_smem(RegionCtx& c) {
+  syncwarp();
+  for (int x = lane(); x < c.clen; x += WARP) c.s_contig[x] = c.cseq[c.c0 + x];
+  syncwarp();
+}
+
+// ---- get_read_kmers_ordered (:126-143; Q8 skips the last window, Q26 floor) ----
+// windows of seq[base .. base+nlen) that are live sample-only mers, appended to
+// the contig's k-mer tuple list in the requested order
+BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, int order) {
+  const int k = c.k;
+  const int nwin = nlen - k;              // range(0, len - l)
+  if (nwin <= 0) return;
+  const int m = nlen / 2;
+  const unsigned lt = lane_lt_mask();
+  int32_t* Ks = c.K; int32_t* Kx = c.K + ASM_KCAP; int32_t* Km = c.K + 2 * ASM_KCAP;
+  // pass 0: ascending x over [lo0, hi0) ; pass 1: descending x over [lo1, hi1)
+  int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  if (order == ORDER_FOR) { lo0 = 0; hi0 = nwin; }
+  else if (order == ORDER_REV) { lo1 = 0; hi1 = nwin; }
+  else { lo0 = m < nwin ? m : nwin; hi0 = nwin; lo1 = 0; hi1 = m < nwin ? m : nwin; }   // sorted by (x<m, |x-m|) (:142)
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lo = pass == 0 ? lo0 : lo1, hi = pass == 0 ? hi0 : hi1;
+    for (int b = 0; b < hi - lo; b += WARP) {
+      const int t = b + lane();
+      const int x = pass == 0 ? lo + t : hi - 1 - t;
+      int s = -1;
+      if (t < hi - lo) {
+        uint64_t code;
+        if (window_code(seq + base, x, k, code)) {
+          s = find_mer(c, code);
+          if (s >= 0 && !c.alive[s]) s = -1;
+        }
+      }
+      const unsigned mk = ballot(s >= 0);
+      if (s >= 0) {
+        const int dst = c.nK + popc(mk & lt);
+        if (dst < ASM_KCAP) {
+          Ks[dst] = s; Kx[dst] = x;
+          const int lth = x < m ? 1 : 0, dist = x < m ? m - x : x - m;
+          Km[dst] = lth | (order << 1) | (dist << 3);
+        }
+      }
+      c.nK += popc(mk);
+    }
+  }
+  if (c.nK > ASM_KCAP) { c.nK = ASM_KCAP; c.status = ST_CAPACITY; }
+  syncwarp();
+}
+
+BK_DEV void set_kmers(RegionCtx& c) {                               // :548-550
+  c.ct_setup = true;
+  c.nK = 0;
+  append_kmers(c, c.s_contig, 0, c.clen, ORDER_MID);
+}
+
+// ---- assembly_counts (:160-221) ---------------------------------------------------
+BK_DEV void set_counts(RegionCtx& c, int start, int end, int n, bool io) {      // :195-199
+  int32_t* v = (io ? c.io_vec(c.cur) : c.ot_vec(c.cur)) + c.k0;
+  if (end > c.klen) end = c.klen;                                   // python slice clipping
+  for (int x = start + lane(); x < end; x += WARP) v[x] += n;
+  syncwarp();
+}
+BK_DEV void extend_counts(RegionCtx& c, int l, int n, bool io, bool post) {     // :201-221
+  int32_t* vi = c.io_vec(c.cur);
+  int32_t* vo = c.ot_vec(c.cur);
+  const int at = post ? c.k0 + c.klen : c.k0 - l;
+  for (int x = lane(); x < l; x += WARP) { vi[at + x] = io ? n : 0; vo[at + x] = io ? 0 : n; }
+  if (!post) c.k0 -= l;
+  c.klen += l;
+  syncwarp();
+}
+// contig replaced by read u; old counts re-added at [start, end) with python's
+// zip-truncate / slice-assign semantics (:181-193, Q17).  s_read holds read u.
+BK_DEV void set_superseq(RegionCtx& c, int u, int lr, int start, int end) {
+  const int n = (int)c.u_mult[u];
+  const bool io = c.u_io[u] != 0;
+  const int bio = io ? n : 0, bot = io ? 0 : n;
+  const int32_t* oi = c.io_vec(c.cur) + c.k0;
+  const int32_t* oo = c.ot_vec(c.cur) + c.k0;
+  int32_t* ni = c.io_vec(c.cur ^ 1) + ASM_CAP;
+  int32_t* no = c.ot_vec(c.cur ^ 1) + ASM_CAP;
+  const int span = end - start;
+  const int mid = span < c.klen ? span : c.klen;
+  const int tail = lr - end;
+  const int nl = start + mid + tail;
+  for (int x = lane(); x < nl; x += WARP) {
+    int a = bio, b = bot;
+    if (x >= start && x < start + mid) { a += oi[x - start]; b += oo[x - start]; }
+    ni[x] = a; no[x] = b;
+  }
+  c.cur ^= 1; c.k0 = ASM_CAP; c.klen = nl;
+  c.c0 = ASM_CAP; c.clen = lr;
+  for (int x = lane(); x < lr; x += WARP) { const uint8_t ch = c.s_read[x]; c.cseq[ASM_CAP + x] = ch; c.s_contig[x] = ch; }
+  syncwarp();
+}
+
+// first occurrence of mer `code` in seq[a, b) (str.find on the slice); -1 if none
+BK_DEV int find_in_slice(const uint8_t* seq, int a, int b, int k, uint64_t code) {
+  const int nwin = b - a - k + 1;
+  int best = 0x7fffffff;
+  for (int t = 0; t < nwin; t += WARP) {
+    const int x = t + lane();
+    bool hit = false;
+    if (x < nwin) {
+      uint64_t w;
+      hit = window_code(seq, a + x, k, w) && w == code;
+    }
+    const unsigned mk = ballot(hit);
+    if (mk) { best = t + ffs(mk) - 1; break; }
+  }
+  return best == 0x7fffffff ? -1 : best;
+}
+
+// ---- contig.__init__ (:417-426) ---------------------------------------------------------
+BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
+  c.serial += 1;
+  const int lr = stage_read(c, u);
+  c.c0 = ASM_CAP; c.clen = lr;
+  c.cur = 0; c.k0 = ASM_CAP; c.klen = lr;
+  const int n = (int)c.u_mult[u];
+  const bool io = c.u_io[u] != 0;
+  int32_t* vi = c.io_vec(0) + ASM_CAP;
+  int32_t* vo = c.ot_vec(0) + ASM_CAP;
+  for (int x = lane(); x < lr; x += WARP) {
+    const uint8_t ch = c.s_read[x];
+    c.cseq[ASM_CAP + x] = ch; c.s_contig[x] = ch;
+    vi[x] = io ? n : 0; vo[x] = io ? 0 : n;
+  }
+  c.nK = 0; c.nNK = 0;
+  c.ct_setup = false; c.ct_finalized = false; c.ct_init_read = u;
+  c.n_alt = 0; c.n_del = 0;
+  if (lane() == 0) { c.checked[seed_s] = c.serial; c.r_buf[u] = c.serial; }    // checked_kmers=[seed] (Q24), buffer={read}
+  syncwarp();
+}
+
+// ---- contig.check_align (:449-504) and the two overlap cases (:506-546) ------------------
+BK_DEV void contig_overlap_read(RegionCtx& c, const NwOut& v1, int u, int lr, bool grow) {
+  const int lc = c.clen;
+  if (v1.j0 == 0) {                                                 // :508 (prej == len always, Q15)
+    set_superseq(c, u, lr, v1.i0, v1.prei);
+    if (grow) set_kmers(c);
+    return;
+  }
+  const int plen = lr - v1.prei;                                    // post_seq = read[aln[4]:]
+  if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
+  for (int x = lane(); x < plen; x += WARP) {
+    const uint8_t ch = c.s_read[v1.prei + x];
+    c.cseq[c.c0 + lc + x] = ch; c.s_contig[lc + x] = ch;
+  }
+  c.clen = lc + plen;
+  syncwarp();
+  const int n = (int)c.u_mult[u];
+  const bool io = c.u_io[u] != 0;
+  set_counts(c, v1.j0, lc, n, io);                                  // add_postseq :243-250
+  extend_counts(c, plen, n, io, true);
+  if (grow) append_kmers(c, c.s_contig, lc - (c.k - 1), (c.k - 1) + plen, ORDER_FOR);   // :521,525-527
+}
+
+BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, int lr, bool grow) {
+  const int n = (int)c.u_mult[u];
+  const bool io = c.u_io[u] != 0;
+  if (v2.j0 == 0) {                                                 // :531
+    set_counts(c, v2.i0, v2.prei, n, io);
+    return;
+  }
+  const int plen = v2.j0;                                           // pre_seq = read[0:aln[3]]
+  const int lc = c.clen;
+  if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
+  for (int x = lane(); x < plen; x += WARP) c.cseq[c.c0 - plen + x] = c.s_read[x];
+  c.c0 -= plen; c.clen = lc + plen;
+  sync_contig_to_smem(c);
+  set_counts(c, v2.i0, v2.prei, n, io);                             // add_preseq :255-262 (old coordinates)
+  extend_counts(c, plen, n, io, false);
+  const int head = (c.k - 1) < lc ? (c.k - 1) : lc;
+  if (grow) append_kmers(c, c.s_contig, 0, plen + head, ORDER_REV);  // :539,543-545
+}
+
+BK_DEV bool check_align(RegionCtx& c, int u, int seed_s, bool grow) {
+  const int lr = stage_read(c, u);
+  const int lc = c.clen;
+  NwDual r;
+  // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
+  if (lr <= 128) nw_dual_warp<4, false>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, nullptr, r);
+  else nw_dual_warp<8, false>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, nullptr, r);
+  const NwOut v1 = r.b, v2 = r.a;
+  if (lane() == 0) {
+    atomic_add(&c.P->stats[0], 1ull);
+    atomic_add(&c.P->stats[1], (unsigned long long)lc * (unsigned long long)lr);
+  }
+  const int s1 = v1.score, s2 = v2.score;
+  const int mn = lc < lr ? lc : lr;
+  // :459-464 in integers (Q27)
+  const bool bad1 = (4 * s1 < mn) || (200 * s1 < 179 * (v1.prej - v1.j0));
+  const bool bad2 = (4 * s2 < mn) || (200 * s2 < 179 * (v2.prej - v2.j0));
+  if (bad1 && bad2) return false;
+  if (s1 == s2 && v1.j0 == 0 && v1.i0 == 0 && lc == lr) return true;            // :466 (Q16)
+  const int n = (int)c.u_mult[u];
+  const bool io = c.u_io[u] != 0;
+  if (s1 == s2) {
+    if (lc < lr || v1.j0 == 0) {                                     // :471
+      set_superseq(c, u, lr, v1.i0, v1.prei);
+      if (grow) set_kmers(c);
+      return true;
+    }
+    if (lr < lc || v2.j0 == 0) {                                     // :480
+      set_counts(c, v2.i0, v2.prei, n, io);
+      return true;
+    }
+    // :485-496 -- alignment strings minus '-' are the aligned spans themselves
+    const uint64_t code = c.mer[seed_s];
+    const int i11 = find_in_slice(c.s_contig, v1.j0, lc, c.k, code);
+    const int i12 = find_in_slice(c.s_read, v1.i0, v1.prei, c.k, code);
+    const int i21 = find_in_slice(c.s_read, v2.j0, lr, c.k, code);
+    const int i22 = find_in_slice(c.s_contig, v2.i0, v2.prei, c.k, code);
+    const int d1 = i11 > i12 ? i11 - i12 : i12 - i11;
+    const int d2 = i21 > i22 ? i21 - i22 : i22 - i21;
+    if (i11 > -1 && i12 > -1) {
+      if ((i21 == -1 && i22 == -1) || d2 > d1) { contig_overlap_read(c, v1, u, lr, grow); return true; }
+    } else if (i21 > -1 && i22 > -1) {
+      if ((i11 == -1 && i12 == -1) || d2 < d1) { read_overlap_contig(c, v2, u, lr, grow); return true; }
+    }
+    return false;
+  }
+  if (s1 > s2) contig_overlap_read(c, v1, u, lr, grow);
+  else read_overlap_contig(c, v2, u, lr, grow);
+  return true;
+}
+
+// ---- contig.check_read (:552-566, Q30) ---------------------------------------------------------
+BK_DEV bool check_read(RegionCtx& c, int seed_s, int u, bool grow) {
+  if (lane() == 0) c.r_buf[u] = c.serial;                            // self.buffer.add(read.id)
+  const bool match = check_align(c, u, seed_s, grow);
+  if (match) {
+    if (lane() == 0) { c.r_used[u] = 1; c.r_inreads[u] = c.serial; }  // committed by the finalize that follows
+  } else if (c.cnt[seed_s] > 2 && !c.r_used[u]) {
+    if (lane() == 0) c.l_alt[c.n_alt] = u;
+    c.n_alt += 1;
+  } else {
+    if (lane() == 0) c.l_del[c.n_del] = u;
+    c.n_del += 1;
+  }
+  syncwarp();
+  return match;
+}
+
+// ---- buffer.add_contig (:337-340) ----------------------------------------------------------------
+BK_DEV bool add_contig(RegionCtx& c, int u, int seed_s) {
+  if (c.r_used[u]) return false;            // (a queued read is always used, so `id in contigs` is implied)
+  if (lane() == 0) {
+    c.q_read[c.q_tail] = u; c.q_seed[c.q_tail] = seed_s;
+    c.r_used[u] = 1; c.r_queued[u] = 1;
+  }
+  c.q_tail += 1;
+  syncwarp();
+  return true;
+}
+
+// ---- contig.check_alt_reads (:568-582, Q12, Q13) + finalize (:584-599) + rb.clean (:389-397, Q11) --
+BK_DEV void finalize(RegionCtx& c, bool setup) {
+  if (setup) set_kmers(c);
+  c.fin_serial += 1;
+  const int k = c.k;
+  for (int a = 0; a < c.n_alt; ++a) {
+    const int u = c.l_alt[a];
+    const int lr = stage_read(c, u);
+    const int nwin = lr - k;                                         // get_read_kmers skips the last window (Q8)
+    int best = 0x7fffffff;
+    for (int t = 0; t < nwin; t += WARP) {
+      const int x = t + lane();
+      if (x < nwin) {
+        uint64_t code;
+        if (window_code(c.s_read, x, k, code)) {
+          const int s = find_mer(c, code);
+          if (s >= 0 && c.alive[s] && !c.mused[s] && c.taken[s] != c.fin_serial && c.cnt[s] > 1 && s < best) best = s;
+        }
+      }
+    }
+    best = warp_min_i(best);
+    if (best != 0x7fffffff) {
+      // new contig seeded at the smallest candidate mer; the WHOLE candidate set joins mer_set (:580)
+      for (int t = 0; t < nwin; t += WARP) {
+        const int x = t + lane();
+        if (x < nwin) {
+          uint64_t code;
+          if (window_code(c.s_read, x, k, code)) {
+            const int s = find_mer(c, code);
+            if (s >= 0 && c.alive[s] && !c.mused[s]) c.taken[s] = c.fin_serial;
+          }
+        }
+      }
+      syncwarp();
+      add_contig(c, u, best);
+    }
+  }
+  if (!c.ct_finalized) {
+    if (lane() == 0) c.r_inreads[c.ct_init_read] = c.serial;         // batch_reads[0] is aligned=True
+    c.ct_finalized = true;
+  }
+  for (int d = lane(); d < c.n_del; d += WARP) c.r_deleted[c.l_del[d]] = 1;   // del fq_recs[read.seq]
+  c.n_alt = 0; c.n_del = 0;
+  syncwarp();
+}
+
+// ---- find_reads / read_search (:102-122; Q9, Q10, Q28) -------------------------------------------
+// result in hit_u / hit_pos, sorted by (pos, -len) or (-pos, -len), ties in read order
+BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
+  const int64_t a = c.P->post_off[c.gm0 + s], b = c.P->post_off[c.gm0 + s + 1];
+  const int32_t* pr = c.P->post_read + a;
+  const int32_t* pp = c.P->post_pos + a;
+  const int n0 = (int)(b - a);
+  const unsigned lt = lane_lt_mask();
+  int n = 0;
+  for (int t = 0; t < n0; t += WARP) {
+    const int i = t + lane();
+    bool keep = false;
+    int u = 0, pos = 0;
+    if (i < n0) {
+      u = pr[i]; pos = pp[i];
+      keep = !c.r_deleted[u] && !(filter_buffer && c.r_buf[u] == c.serial);
+    }
+    const unsigned mk = ballot(keep);
+    if (keep) {
+      const int dst = n + popc(mk & lt);
+      c.hit2_u[dst] = u;
+      // sort key: primary pos (or -pos), secondary -len; both < 4096
+      const int len = c.read_len_of(u);
+      c.hit2_pos[dst] = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - len);
+    }
+    n += popc(mk);
+  }
+  syncwarp();
+  // stable rank sort (lists are short: at most the reads that contain one k-mer)
+  for (int t = 0; t < n; t += WARP) {
+    const int i = t + lane();
+    if (i < n) {
+      const int key = c.hit2_pos[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const int kj = c.hit2_pos[j];
+        rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+      }
+      c.hit_u[rank] = c.hit2_u[i];
+      const int hi = key >> 12;
+      c.hit_pos[rank] = rev ? (ASM_CAP - 1 - hi) : hi;
+    }
+  }
+  syncwarp();
+  if (lane() == 0) atomic_add(&c.P->stats[2], 1ull);
+  return n;
+}
+
+// ---- setup_contigs (:11-26, Q20) ---------------------------------------------------------------------
+// returns true if the new contig was queued (it is then the FIFO head and is grown next)
+BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
+  const int n = find_reads(c, seed_s, false, false);
+  if (lane() == 0) c.mused[seed_s] = 1;                              // buff.add_used_mer
+  syncwarp();
+  if (n == 0) return false;
+  bool queued = false;
+  for (int h = 0; h < n && c.status == ST_OK; ++h) {
+    const int u = c.hit_u[h];
+    if (h == 0) {
+      contig_init(c, seed_s, u);
+      // buff.add_contig(read, ct): only if the read is not used yet (Q20)
+      if (!c.r_used[u]) {
+        if (lane() == 0) { c.r_used[u] = 1; }
+        queued = true;
+        syncwarp();
+      }
+    } else {
+      check_read(c, seed_s, u, false);
+    }
+  }
+  if (c.status == ST_OK) finalize(c, true);
+  return queued;
+}
+
+// ---- set_kmer_locs (:434-438, Q25) + emit the accepted contig -------------------------------------------
+BK_DEV void emit_contig(RegionCtx& c) {
+  const AsmParams& P = *c.P;
+  const int k = c.k, len = c.clen;
+  const int32_t* Ks = c.K; const int32_t* Kx = c.K + ASM_KCAP; const int32_t* Km = c.K + 2 * ASM_KCAP;
+  // window codes of the final contig, then for each tuple the first window with its mer (str.find)
+  const int nwin = len - k + 1;
+  for (int x = lane(); x < nwin; x += WARP) {
+    uint64_t code;
+    c.wcode[x] = window_code(c.s_contig, x, k, code) ? code : KEY_INVALID;
+  }
+  for (int x = lane(); x <= len; x += WARP) c.diff[x] = 0;
+  syncwarp();
+  for (int e = lane(); e < c.nK; e += WARP) {
+    const uint64_t code = c.mer[Ks[e]];
+    int p = -1;
+    for (int x = 0; x < nwin; ++x)
+      if (c.wcode[x] == code) { p = x; break; }
+    if (p >= 0) {                                                    // find() == -1 touches nothing (Q25)
+      atomic_add(&c.diff[p], 1);
+      atomic_add(&c.diff[(p + k) < len ? (p + k) : len], -1);
+    }
+  }
+  syncwarp();
+  // reads of the contig, ascending unique-read index
+  int n_reads = 0;
+  const unsigned lt = lane_lt_mask();
+  for (int t = 0; t < c.U; t += WARP) {
+    const int u = t + lane();
+    const bool in = (u < c.U) && (c.r_inreads[u] == c.serial);
+    const unsigned mk = ballot(in);
+    if (in) c.hit_u[n_reads + popc(mk & lt)] = u;
+    n_reads += popc(mk);
+  }
+  syncwarp();
+  // reserve output space
+  unsigned long long o_seq = 0, o_cnt = 0, o_rd = 0, o_km = 0, o_ct = 0;
+  if (lane() == 0) {
+    o_seq = atomic_add(&P.out_cursor[0], (unsigned long long)len);
+    o_cnt = atomic_add(&P.out_cursor[1], (unsigned long long)c.klen);
+    o_rd = atomic_add(&P.out_cursor[2], (unsigned long long)n_reads);
+    o_km = atomic_add(&P.out_cursor[3], (unsigned long long)c.nK);
+    o_ct = atomic_add(&P.out_cursor[4], 1ull);
+  }
+  o_seq = shfl(o_seq, 0); o_cnt = shfl(o_cnt, 0); o_rd = shfl(o_rd, 0); o_km = shfl(o_km, 0); o_ct = shfl(o_ct, 0);
+  if (o_seq + len > P.cap_seq || o_cnt + c.klen > P.cap_cnt || o_rd + n_reads > P.cap_reads || o_km + c.nK > P.cap_kmers ||
+      o_ct + 1 > P.cap_ctg) {
+    c.status = ST_CAPACITY;
+    return;
+  }
+  // kmer_locs = prefix sum of diff (sequential over chunks of a warp)
+  int carry = 0;
+  for (int t = 0; t < len; t += WARP) {
+    const int x = t + lane();
+    int v = x < len ? c.diff[x] : 0;
+#ifndef BK_SIM
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int w = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane() >= o) v += w;
+    }
+#endif
+    if (x < len) {
+      P.o_locs[o_seq + x] = carry + v;
+      P.o_seq[o_seq + x] = c.s_contig[x];
+    }
+    carry += shfl(v, WARP - 1);
+  }
+  const int32_t* vi = c.io_vec(c.cur) + c.k0;
+  const int32_t* vo = c.ot_vec(c.cur) + c.k0;
+  for (int x = lane(); x < c.klen; x += WARP) { P.o_io[o_cnt + x] = vi[x]; P.o_ot[o_cnt + x] = vo[x]; }
+  for (int x = lane(); x < n_reads; x += WARP) P.o_reads[o_rd + x] = c.u_rec[c.hit_u[x]];
+  for (int e = lane(); e < c.nK; e += WARP) {
+    P.o_kmer_mer[o_km + e] = c.mer[Ks[e]];
+    P.o_kmer_pos[o_km + e] = Kx[e];
+    P.o_kmer_meta[o_km + e] = Km[e];
+  }
+  if (lane() == 0) {
+    int64_t* d = P.o_desc + o_ct * 10;
+    d[0] = c.region; d[1] = c.n_out; d[2] = (int64_t)o_seq; d[3] = len; d[4] = (int64_t)o_cnt; d[5] = c.klen;
+    d[6] = (int64_t)o_rd; d[7] = n_reads; d[8] = (int64_t)o_km; d[9] = c.nK;
+  }
+  c.n_out += 1;
+  syncwarp();
+}
+
+// ---- contig.grow (:616-649) ------------------------------------------------------------------------------
+BK_DEV void grow(RegionCtx& c) {
+  if (!c.ct_setup) set_kmers(c);
+  const unsigned lt = lane_lt_mask();
+  int32_t* Ks = c.K; int32_t* Km = c.K + 2 * ASM_KCAP;
+  int32_t* Ns = c.NK; int32_t* Nm = c.NK + 2 * ASM_KCAP;
+  while (c.status == ST_OK) {
+    // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
+    int nn = 0;
+    for (int t = 0; t < c.nK; t += WARP) {
+      const int e = t + lane();
+      bool keep = false;
+      int s = 0, meta = 0;
+      if (e < c.nK) { s = Ks[e]; meta = Km[e]; keep = c.checked[s] != c.serial; }
+      const unsigned mk = ballot(keep);
+      if (keep) { const int dst = nn + popc(mk & lt); Ns[dst] = s; Nm[dst] = meta; }
+      nn += popc(mk);
+    }
+    c.nNK = nn;
+    syncwarp();
+    if (nn == 0) break;
+    for (int e = 0; e < nn && c.status == ST_OK; ++e) {
+      const int s = Ns[e], meta = Nm[e];
+      const int lth = meta & 1, order = (meta >> 1) & 3;
+      // get_mer_reads (:604-614)
+      bool rev;
+      if (order == ORDER_MID) rev = (lth == 0);
+      else rev = (order == ORDER_FOR);
+      const int n = find_reads(c, s, true, rev);
+      if (lane() == 0) c.mused[s] = 1;
+      syncwarp();
+      for (int h = 0; h < n && c.status == ST_OK; ++h) {
+        const int u = c.hit_u[h];
+        if (check_read(c, s, u, true)) {
+          if (c.r_queued[u] == 1) {                                    // buff.remove_contig(read.id) :639
+            if (lane() == 0) c.r_queued[u] = 2;
+            syncwarp();
+          }
+        }
+      }
+      if (c.status != ST_OK) break;
+      finalize(c, false);
+      if (lane() == 0) c.checked[s] = c.serial;
+      syncwarp();
+    }
+  }
+}
+
+BK_DEV int total_reads(const RegionCtx& c) {                         // :178-179
+  const int32_t* vi = c.io_vec(c.cur) + c.k0;
+  const int32_t* vo = c.ot_vec(c.cur) + c.k0;
+  int a = -0x7fffffff, b = -0x7fffffff;
+  for (int x = lane(); x < c.klen; x += WARP) { a = vi[x] > a ? vi[x] : a; b = vo[x] > b ? vo[x] : b; }
+  return warp_max_i(a) + warp_max_i(b);
+}
+
+// after grow: accept or drop (:53-59, Q21)
+BK_DEV void finish_contig(RegionCtx& c, int rc_thresh, int read_len) {
+  if (c.status != ST_OK) return;
+  if (total_reads(c) < rc_thresh || c.clen <= read_len) return;
+  emit_contig(c);
+}
+
+// ---- init_assembly (:30-63) for one region ------------------------------------------------------------------
+BK_DEV void assemble_region(RegionCtx& c) {
+  const AsmParams& P = *c.P;
+  const int read_len = P.read_len[c.region];
+  int cursor = 0;
+  c.serial = 0; c.fin_serial = 0; c.status = ST_OK; c.n_out = 0;
+  c.q_head = 0; c.q_tail = 0; c.n_alt = 0; c.n_del = 0;
+  if (c.S == 0) return;                                              // :33-34
+  while (c.status == ST_OK) {
+    // has_mers (:318-322): the first live mer in seed order carries the max count
+    while (cursor < c.S && !c.alive[c.seed_order[cursor]]) ++cursor;
+    if (cursor >= c.S) break;
+    const int seed = c.seed_order[cursor];
+    if (c.cnt[seed] <= 1) break;
+    if (lane() == 0) atomic_add(&P.stats[3], 1ull);
+    const bool queued = setup_contigs(c, seed);
+    if (queued && c.status == ST_OK) {                               // it is the FIFO head (the queue was empty)
+      grow(c);
+      finish_contig(c, P.rc_thresh, read_len);
+    }
+    while (c.status == ST_OK) {                                      // while len(buff.contigs) > 0 (:50)
+      while (c.q_head < c.q_tail && c.r_queued[c.q_read[c.q_head]] != 1) ++c.q_head;
+      if (c.q_head >= c.q_tail) break;
+      const int u = c.q_read[c.q_head], s = c.q_seed[c.q_head];
+      ++c.q_head;
+      if (lane() == 0) c.r_queued[u] = 2;
+      syncwarp();
+      contig_init(c, s, u);
+      grow(c);
+      finish_contig(c, P.rc_thresh, read_len);
+    }
+    // buff.remove_kmers (:358-360); remove_reads is a no-op (Q10)
+    for (int s = lane(); s < c.S; s += WARP)
+      if (c.mused[s]) { c.alive[s] = 0; c.mused[s] = 0; }
+    syncwarp();
+  }
+}
+
+BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_read, uint8_t* s_contig) {
+  c.P = &P; c.region = region; c.k = P.k;
+  c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
+  c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
+  c.alive = P.m_alive + c.gm0; c.mused = P.m_used + c.gm0; c.checked = P.m_checked + c.gm0; c.taken = P.m_taken + c.gm0;
+  c.gu0 = P.u_off[region]; c.U = (int)(P.u_off[region + 1] - c.gu0);
+  c.u_rec = P.u_rec + c.gu0; c.u_mult = P.u_mult + c.gu0; c.u_io = P.u_io + c.gu0;
+  c.r_used = P.r_used + c.gu0; c.r_deleted = P.r_deleted + c.gu0; c.r_queued = P.r_queued + c.gu0;
+  c.r_buf = P.r_buf + c.gu0; c.r_inreads = P.r_inreads + c.gu0;
+  c.q_read = P.q_read + c.gu0; c.q_seed = P.q_seed + c.gu0;
+  c.l_alt = P.l_alt + c.gu0; c.l_del = P.l_del + c.gu0;
+  c.hit_u = P.hit_u + c.gu0; c.hit_pos = P.hit_pos + c.gu0; c.hit2_u = P.hit2_u + c.gu0; c.hit2_pos = P.hit2_pos + c.gu0;
+  c.cseq = P.w_cseq + slot * ASM_BUF;
+  c.cnt_buf = P.w_cnt + slot * 4 * ASM_BUF;
+  c.K = P.w_K + slot * 3 * ASM_KCAP;
+  c.NK = P.w_NK + slot * 3 * ASM_KCAP;
+  c.wcode = P.w_wcode + slot * ASM_CAP;
+  c.diff = P.w_diff + slot * (ASM_CAP + 1);
+  c.edge = P.w_edge ? P.w_edge + slot * 2 * ASM_CAP : nullptr;
+  c.s_read = s_read; c.s_contig = s_contig;
+}
+
+#ifndef BK_SIM
+constexpr int ASM_WARPS_PER_CTA = 1;
+__global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA) assemble_kernel(AsmParams P) {
+  __shared__ __align__(16) uint8_t s_read[ASM_CAP];
+  __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
+  const int64_t slot = blockIdx.x;
+  RegionCtx c;
+  for (;;) {
+    int w = 0;
+    if (lane() == 0) w = atomicAdd(P.work_counter, 1);
+    w = shfl(w, 0);
+    if (w >= P.n_regions) break;
+    const int region = P.work_order[w];
+    bind_region(c, P, region, slot, s_read, s_contig);
+    assemble_region(c);
+    if (lane() == 0) { P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out; }
+    syncwarp();
+  }
+}
+#endif
+
+}  // namespace bk

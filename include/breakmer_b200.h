@@ -105,14 +105,17 @@ typedef struct bk_batch_input {
 
 /* All arrays are library-owned (valid until the next call on the handle).
  * Contig c of region r: c in [ctg_reg_off[r], ctg_reg_off[r+1]), acceptance order.
- *   sequence       ctg_seq[ctg_seq_off[c] .. ctg_seq_off[c+1])
- *   count vectors  ctg_indel_only / ctg_others [ctg_cnt_off[c] .. ctg_cnt_off[c+1])
- *                  (their length can differ from the sequence length)
- *   kmer_locs      ctg_kmer_locs[ctg_seq_off[c] .. ) one int per base
- *   reads          ctg_reads[ctg_reads_off[c] .. ) = record index (into the input
- *                  read arrays) of the representative (first) record of each
- *                  unique read in contig.reads
- *   k-mer tuples   ctg_kmer_mer/pos/lth/dist/order [ctg_kmers_off[c] .. ) ; order
+ * Each ctg_*_off table holds an (offset, length) PAIR per contig: X_off[2c] is the
+ * start in the payload array(s), X_off[2c+1] the element count (payload arrays are
+ * in device completion order, only these tables are ordered).
+ *   sequence       ctg_seq[off .. off+len)          via ctg_seq_off
+ *   kmer_locs      ctg_kmer_locs[off .. off+len)    via ctg_seq_off, one int per base
+ *   count vectors  ctg_indel_only / ctg_others      via ctg_cnt_off (their length can
+ *                  differ from the sequence length)
+ *   reads          ctg_reads                        via ctg_reads_off = record index
+ *                  (into the input read arrays) of the representative (first) record
+ *                  of each unique read in contig.reads
+ *   k-mer tuples   ctg_kmer_mer/pos/lth/dist/order  via ctg_kmers_off ; order
  *                  0='for' 1='rev' 2='mid' (sv_assembly.py:130,142)
  * Unique reads (fq_recs keys, insertion order): region r owns
  * [uniq_reg_off[r], uniq_reg_off[r+1]); uniq_rec = representative record index,

@@ -1,0 +1,108 @@
+// tests/sim: host-compiled, single-lane build of the device assembler's control
+// logic (breakmer_b200/csrc/assemble.cuh with BK_SIM).  TEST/DEBUG TOOL ONLY: it
+// lets the state machine be checked against the oracle in the build container,
+// which has no GPU.  It is not part of the product library, is never loaded by
+// breakmer_b200, and is not a fallback -- the product path runs the same source
+// compiled by nvcc for sm_100a with 32-lane warps and the warp DP kernel.
+#define BK_SIM 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../breakmer_b200/csrc/assemble.cuh"
+
+using namespace bk;
+
+extern "C" int sim_assemble_region(
+    const uint8_t* rbases, const int64_t* roff, int n_reads, const uint32_t* mult, const uint8_t* io,
+    const uint64_t* mers, const uint32_t* counts, int n_mers, int k, int rc_thresh, int read_len,
+    // outputs (caller allocated, capacities given)
+    int64_t cap, uint8_t* o_seq, int32_t* o_locs, int32_t* o_io, int32_t* o_ot, int32_t* o_reads,
+    uint64_t* o_kmer_mer, int32_t* o_kmer_pos, int32_t* o_kmer_meta, int64_t* o_desc, int64_t* n_contigs,
+    uint64_t* stats_out) {
+  AsmParams P;
+  memset(&P, 0, sizeof P);
+  P.n_regions = 1; P.k = k; P.rc_thresh = rc_thresh;
+  P.rbases = rbases; P.roff = roff;
+  int64_t u_off[2] = {0, n_reads};
+  std::vector<int32_t> u_rec(n_reads);
+  for (int i = 0; i < n_reads; ++i) u_rec[i] = i;
+  P.u_off = u_off; P.u_rec = u_rec.data(); P.u_mult = mult; P.u_io = io;
+  int32_t rl = read_len;
+  P.read_len = &rl;
+  int64_t so_off[2] = {0, n_mers};
+  P.so_off = so_off; P.so_mer = mers; P.so_cnt = counts;
+  // seed order: (count, mer) descending (kernel: prep); alive: not a homopolymer
+  std::vector<int32_t> order(n_mers);
+  for (int i = 0; i < n_mers; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (counts[a] != counts[b]) return counts[a] > counts[b];
+    return mers[a] > mers[b];
+  });
+  P.seed_order = order.data();
+  std::vector<uint8_t> alive(n_mers + 1), mused(n_mers + 1, 0);
+  for (int i = 0; i < n_mers; ++i) {
+    uint64_t m = mers[i];
+    bool homo = true;
+    for (int t = 1; t < k; ++t) homo = homo && (((m >> (2 * t)) & 3) == (m & 3));
+    alive[i] = homo ? 0 : 1;
+  }
+  // posting lists (kernel: index)
+  std::vector<std::vector<std::pair<int, int>>> post(n_mers);
+  for (int u = 0; u < n_reads; ++u) {
+    const uint8_t* s = rbases + roff[u];
+    int len = (int)(roff[u + 1] - roff[u]);
+    for (int x = 0; x + k <= len; ++x) {
+      uint64_t code;
+      if (!window_code(s, x, k, code)) continue;
+      const uint64_t* it = std::lower_bound(mers, mers + n_mers, code);
+      if (it == mers + n_mers || *it != code) continue;
+      int si = (int)(it - mers);
+      if (!post[si].empty() && post[si].back().first == u) continue;   // first position only
+      post[si].push_back({u, x});
+    }
+  }
+  std::vector<int64_t> post_off(n_mers + 1, 0);
+  std::vector<int32_t> post_read, post_pos;
+  for (int i = 0; i < n_mers; ++i) {
+    post_off[i] = (int64_t)post_read.size();
+    for (auto& pr : post[i]) { post_read.push_back(pr.first); post_pos.push_back(pr.second); }
+  }
+  post_off[n_mers] = (int64_t)post_read.size();
+  post_read.push_back(0); post_pos.push_back(0);
+  P.post_off = post_off.data(); P.post_read = post_read.data(); P.post_pos = post_pos.data();
+  std::vector<uint32_t> m_checked(n_mers + 1, 0), m_taken(n_mers + 1, 0);
+  P.m_alive = alive.data(); P.m_used = mused.data(); P.m_checked = m_checked.data(); P.m_taken = m_taken.data();
+  const int U = n_reads + 1;
+  std::vector<uint8_t> r_used(U, 0), r_deleted(U, 0), r_queued(U, 0);
+  std::vector<uint32_t> r_buf(U, 0), r_inreads(U, 0);
+  std::vector<int32_t> q_read(U), q_seed(U), l_alt(U), l_del(U), hit_u(U), hit_pos(U), hit2_u(U), hit2_pos(U);
+  P.r_used = r_used.data(); P.r_deleted = r_deleted.data(); P.r_queued = r_queued.data();
+  P.r_buf = r_buf.data(); P.r_inreads = r_inreads.data();
+  P.q_read = q_read.data(); P.q_seed = q_seed.data(); P.l_alt = l_alt.data(); P.l_del = l_del.data();
+  P.hit_u = hit_u.data(); P.hit_pos = hit_pos.data(); P.hit2_u = hit2_u.data(); P.hit2_pos = hit2_pos.data();
+  std::vector<uint8_t> w_cseq(ASM_BUF);
+  std::vector<int32_t> w_cnt(4 * ASM_BUF), w_K(3 * ASM_KCAP), w_NK(3 * ASM_KCAP), w_diff(ASM_CAP + 1);
+  std::vector<uint64_t> w_wcode(ASM_CAP);
+  P.w_cseq = w_cseq.data(); P.w_cnt = w_cnt.data(); P.w_K = w_K.data(); P.w_NK = w_NK.data();
+  P.w_wcode = w_wcode.data(); P.w_diff = w_diff.data(); P.w_edge = nullptr;
+  unsigned long long cursor[5] = {0, 0, 0, 0, 0};
+  P.out_cursor = cursor;
+  P.cap_seq = P.cap_cnt = P.cap_reads = P.cap_kmers = P.cap_ctg = (unsigned long long)cap;
+  P.o_seq = o_seq; P.o_locs = o_locs; P.o_io = o_io; P.o_ot = o_ot; P.o_reads = o_reads;
+  P.o_kmer_mer = o_kmer_mer; P.o_kmer_pos = o_kmer_pos; P.o_kmer_meta = o_kmer_meta; P.o_desc = o_desc;
+  int32_t status = 0, ncontigs = 0;
+  P.region_status = &status; P.region_ncontigs = &ncontigs;
+  unsigned long long stats[4] = {0, 0, 0, 0};
+  P.stats = stats;
+  std::vector<uint8_t> s_read(ASM_CAP), s_contig(ASM_CAP);
+  RegionCtx c;
+  bind_region(c, P, 0, 0, s_read.data(), s_contig.data());
+  assemble_region(c);
+  *n_contigs = (int64_t)cursor[4];
+  for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];
+  return c.status;
+}

@@ -1,0 +1,91 @@
+"""GPU parity of the whole hot path (bk_compare_kmers_batch) against the oracle and
+against the reference's own outputs (golden)."""
+import pytest
+
+from conftest import golden
+from breakmer_b200 import synth
+from oracle import assembler_py
+from oracle.make_golden import digest, oracle_sample_only, region_scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from breakmer_b200 import _lib
+    h = _lib.Handle(0)
+    yield h
+    h.close()
+
+
+def oracle_region(region):
+    _r, _c, _s, only = oracle_sample_only(region)
+    ctg = assembler_py.init_assembly(only, region.reads, region.k, region.rc_thresh, region.read_len)
+    return only, ctg
+
+
+def check_batch(handle, regions, with_mers=False):
+    from breakmer_b200 import batch
+    pk = batch.PackedBatch(regions)
+    exp = [oracle_region(r) for r in regions]
+    if with_mers:
+        pk.set_mers([e[0] for e in exp])
+    out = batch.run(handle, pk)
+    assert out.n_regions == len(regions)
+    assert all(s == 0 for s in out.region_status)
+    for i, r in enumerate(regions):
+        only, ctg = exp[i]
+        assert out.sample_only(i) == only, r.name
+        got = out.contig_records(i)
+        assert got == ctg, r.name
+    return out
+
+
+def test_golden_regions_by_k(handle):
+    cases = golden("assembly_golden.json")["cases"]
+    by_k = {}
+    for c in cases:
+        kw = dict(c["kwargs"]); kw["event"] = tuple(kw["event"])
+        by_k.setdefault(kw["k"], []).append((c, synth.make_region(c["name"], **kw)))
+    for k, items in by_k.items():
+        from breakmer_b200 import batch
+        regions = [it[1] for it in items]
+        out = batch.run(handle, batch.PackedBatch(regions))
+        for i, (c, region) in enumerate(items):
+            got = out.contig_records(i)
+            assert len(out.sample_only(i)) == c["n_sample_only"]
+            assert digest(got) == c["contigs_sha256"], c["name"]       # the reference's own output
+            if "contigs" in c:
+                assert got == c["contigs"]
+
+
+def test_init_assembly_shape_with_given_mers(handle):
+    regions = [synth.make_region(n, **kw) for n, kw in region_scenarios()[:20] if kw["k"] == 15]
+    check_batch(handle, regions, with_mers=True)
+
+
+def test_config_slices(handle):
+    check_batch(handle, [synth.config_region("C1", 0)])
+    check_batch(handle, list(synth.config_regions("C2", n=24)))
+    check_batch(handle, list(synth.config_regions("C3", n=12)))       # normal subtraction
+    check_batch(handle, list(synth.config_regions("C4", n=4)))
+    check_batch(handle, list(synth.config_regions("C5", n=200, start=0)))
+
+
+def test_empty_and_ragged_regions(handle):
+    r0 = synth.make_region("e0", seed=5, L=800, cov=0, k=15, e=0.0, event=("none",))
+    assert r0.reads == []
+    r1 = synth.make_region("e1", seed=6, L=900, cov=200, k=15, e=0.01, event=("del", 100, None))
+    r2 = synth.Region(name="e2", k=15, ref_fwd="ACGT" * 100, reads=[("@a:1:1:1:1/1_0", "ACGTN", "IIIII", False)],
+                      sc_records=[("a", "AC")])
+    out = check_batch(handle, [r0, r1, r2, r0])
+    assert out.ctg_reg_off[1] == 0 and out.sample_only(0) == {}
+    from breakmer_b200 import batch
+    empty = batch.run(handle, batch.PackedBatch([]))
+    assert empty.n_regions == 0 and empty.n_contigs == 0
+
+
+def test_long_reads_use_the_blocked_dp(handle):
+    regions = [synth.make_region("lr%d" % i, seed=700 + i, L=3000, cov=120, k=21, e=0.01,
+                                 event=("del", 200, None), rl=300, rl_jitter=40) for i in range(3)]
+    check_batch(handle, regions)
