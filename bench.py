@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the BreaKmer per-target k-mer assembly hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+A "step" is one pass of the whole hot path (target.compare_kmers: k-mer counting,
+sample-only selection, read grouping, init_assembly) over one batch of synthetic
+target regions.  At N=1 the workload is BASELINE.json configs[1]: the 500-target
+gene panel (k=15).  With N ranks every rank owns its own 500 regions of the same
+generator (weak scaling, regions sharded by rank, no data-path collective).
+
+One JSON line is printed by rank 0.  `value` is whole-job regions/s with the
+batch already resident in HBM; `e2e` is the same metric through the C-ABI entry
+point bk_compare_kmers_batch with HOST buffers (host->device copies and the
+result read-back inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": ("C1: single synthetic 20 kb target region, 100 bp reads at 200x, planted 1.5 kb deletion, k=15", 1),
+    "C2": ("C2: 500-target gene panel, synthetic tumor reads with planted indels/inversions/tandem dups, k=15", 500),
+    "C3": ("C3: tumor/normal pair, 500 targets with normal-k-mer subtraction, k=15", 500),
+    "C4": ("C4: 2000x amplicon-depth panel, 100 amplicons, k=21", 100),
+    "C5": ("C5: exome-scale 20,000 target regions with planted translocations, k=15 (2,500 per GPU)", 2500),
+}
+METRIC = "target_regions_assembled_per_sec"
+UNIT = "regions/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_regions(workload, n, rank):
+    from breakmer_b200 import synth
+    return list(synth.config_regions(workload, n=n, start=rank * n))
+
+
+# ---------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------
+# CPU side (the oracle; used only as the reported baseline / reference arm)
+# ---------------------------------------------------------------------------------
+def cpu_region(region):
+    """The reference's CPU path for one region, as restated by the oracle: pure-Python
+    k-mer counting + set algebra + init_assembly with the pure-Python olc.nw loop
+    (that loop is what the reference itself executes in CPython)."""
+    from oracle import assembler_py, kmers_py, nw_py
+    normal = [x[1] for x in region.normal_reads] if region.normal_reads else None
+    _r, _c, _s, only = kmers_py.sample_only(region.ref_fwd, [x[1] for x in region.reads],
+                                            [x[1] for x in region.sc_records], region.k, normal)
+    ctg = assembler_py.init_assembly(only, region.reads, region.k, region.rc_thresh, region.read_len, nw=nw_py.nw)
+    return len(only), len(ctg)
+
+
+def _cpu_region_by_index(args):
+    workload, idx = args
+    from breakmer_b200 import synth
+    t0 = time.time()
+    n_only, n_ctg = cpu_region(synth.config_region(workload, idx))
+    return n_only, n_ctg, time.time() - t0
+
+
+def cpu_baseline_single(workload, regions, budget_s=20.0, max_regions=8):
+    t0 = time.time()
+    done = 0
+    kmers = 0
+    for r in regions[:max_regions]:
+        n_only, _ = cpu_region(r)
+        kmers += n_only
+        done += 1
+        if time.time() - t0 >= budget_s:
+            break
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d regions of %s, single process, regions serial (as sv_processor.py:185), "
+                      "oracle port with the pure-Python olc.nw loop; jellyfish absent so the k-mer stage is the "
+                      "oracle's dict counter (under-states the reference)" % (done, workload),
+            "seconds": round(dt, 2), "sample_only_kmers_per_s": kmers / dt}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    desc, per_gpu = WORKLOADS[args.workload]
+    n_total = per_gpu * args.gpus
+    per_step = min(cores, n_total)
+    budget = float(os.environ.get("BK_REF_BUDGET_S", "170"))
+    ctx = mp.get_context("fork")
+    t_start = time.time()
+    timed_regions = 0
+    timed_s = 0.0
+    timed_kmers = 0
+    steps_done = 0
+    with ctx.Pool(cores) as pool:
+        nxt = 0
+        for step in range(args.warmup + args.steps):
+            idx = [(args.workload, (nxt + j) % n_total) for j in range(per_step)]
+            nxt += per_step
+            t0 = time.time()
+            res = pool.map(_cpu_region_by_index, idx, chunksize=1)
+            dt = time.time() - t0
+            if step >= args.warmup:
+                timed_regions += len(res)
+                timed_s += dt
+                timed_kmers += sum(r[0] for r in res)
+                steps_done += 1
+            if time.time() - t_start > budget and steps_done >= 1:
+                break
+    value = timed_regions / timed_s if timed_s > 0 else 0.0
+    sample = ("%d regions per step (one per host core) of %s, %d of %d timed steps completed within the %.0f s budget; "
+              "oracle port of the reference's CPython path over multiprocessing" %
+              (per_step, args.workload, steps_done, args.steps, budget))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * timed_s / max(1, steps_done), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": 21 if args.workload == "C4" else 15},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sample_only_kmers_per_s": timed_kmers / timed_s if timed_s > 0 else 0.0,
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    from breakmer_b200 import _lib, batch
+    desc, per_gpu = WORKLOADS[args.workload]
+    if args.regions:
+        per_gpu = args.regions
+    regions = make_regions(args.workload, per_gpu, rank)
+    pk = batch.PackedBatch(regions)
+    h = _lib.Handle(local_rank)
+    hbm_peak, peak_src = load_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident-input run: `value` -----------------------------------------------------
+    batch.upload(h, pk)
+    for _ in range(args.warmup):
+        batch.run(h, pk, resident=True, decode=False)
+    h.kernel_times_reset(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.time()
+    step_ms = []
+    last = None
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (the write itself is not in step_ms)
+        torch.cuda.synchronize()
+        res = batch.run(h, pk, resident=True, decode=False)
+        step_ms.append(float(res.gpu_ms))   # CUDA events on the library's stream, around the whole step
+        last = (int(res.n_contigs), int(res.n_check_align), int(res.n_dp_cells), int(res.n_kmer_occurrences),
+                int(res.so_off[res.n_regions]))
+    barrier()
+    wall_s = time.time() - t0
+    clocks = sampler.stop()
+    ktimes = h.kernel_times()
+    h.kernel_times_reset(False)
+    dev_s = max_over_ranks(sum(step_ms) / 1000.0)
+    n_regions_total = per_gpu * world
+    value = n_regions_total * args.steps / dev_s
+    n_contigs, n_check, n_cells, n_occ, n_only = last
+    kmers_per_s = sum_over_ranks(float(n_only)) * args.steps / dev_s
+    gpu_launches = int(sum(v[1] for v in ktimes.values()))
+
+    # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------------------
+    for _ in range(max(1, min(args.warmup, 3))):
+        batch.run(h, pk, decode=False)
+    barrier()
+    t0 = time.time()
+    d2h = 0
+    for _ in range(args.steps):
+        res = batch.run(h, pk, decode=False)
+    torch.cuda.synchronize()
+    e2e_local = time.time() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_local)
+    e2e_value = n_regions_total * args.steps / e2e_s
+    h2d = pk.input_bytes + 8 * (len(pk.read_off) + len(pk.sc_off) + len(pk.ref_off)) + len(pk.read_flags)
+    out = batch.BatchOutput(res, pk)
+    d2h = int(out.seq.nbytes + out.kmer_locs.nbytes + out.indel_only.nbytes + out.others.nbytes + out.reads.nbytes +
+              out.kmer_mer.nbytes + 2 * out.kmer_pos.nbytes + out.so_mers.nbytes + out.so_counts.nbytes +
+              out.uniq_rec.nbytes + out.uniq_mult.nbytes)
+
+    # ---- roofline of the dominant kernel (the assembler) and of the dominant k-mer stage kernel -----
+    asm_ms, asm_n = ktimes["assemble"]
+    asm_ms_per_launch = asm_ms / max(1, asm_n)
+    # algorithmic bytes of one assemble launch (DESIGN.md "A-stage"): every unique read once, the sample-only
+    # table (12 B/mer), the posting lists (8 B/entry), and the contigs written
+    NU = int(out.uniq_reg_off[-1])
+    read_lens = pk.read_off[1:] - pk.read_off[:-1]
+    uniq_bases = int(read_lens[out.uniq_rec].sum()) if NU else 0
+    asm_bytes = uniq_bases + 12 * n_only + d2h
+    asm_gbs = asm_bytes / (asm_ms_per_launch * 1e-3) / 1e9 if asm_ms_per_launch > 0 else 0.0
+    sc_ms, sc_n = ktimes["sort_scatter"]
+    sort_bytes = 2 * 12 * n_occ          # one pass: keys+values read once, written once
+    sort_gbs = sort_bytes / (sc_ms / max(1, sc_n) * 1e-3) / 1e9 if sc_ms > 0 else 0.0
+    cells_per_s = n_cells * args.steps / (asm_ms * 1e-3) if asm_ms > 0 else 0.0
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    int_peak_cells = 148 * 4 * 32 * sm_mhz * 1e6 / 10.0     # 10 integer issue slots per DP cell (nw.cuh), 1 warp-instr/clk/SMSP
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": pk.k, "rc_thresh": pk.rc_thresh,
+                   "input_bytes_per_gpu": pk.input_bytes, "l2": "256 MB buffer written between timed steps (flush)",
+                   "timing": "CUDA events on the library stream around each step, max over ranks",
+                   "wall_ms_per_step_incl_flush": 1000.0 * wall_s / args.steps},
+        "sample_only_kmers_per_s": kmers_per_s,
+        "per_step": {"contigs": n_contigs, "check_align_calls": n_check, "dp_cells": n_cells,
+                     "kmer_occurrences": n_occ, "sample_only_kmers": n_only},
+        "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": asm_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": asm_ms_per_launch,
+                     "share_of_step": asm_ms / sum(step_ms) if step_ms else None,
+                     "note": "the dominant kernel is an integer-issue/latency bound DP state machine that moves "
+                             "O(m+n) bytes per O(m*n) cell updates; its HBM fraction is small by construction, "
+                             "see roofline_alu and roofline_kstage"},
+        "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": int_peak_cells,
+                         "unit": "DP cell updates/s", "frac": cells_per_s / int_peak_cells if int_peak_cells else None,
+                         "peak_source": "nominal: 148 SM x 4 SMSP x 32 lanes x sm clock / 10 issue slots per cell"},
+        "roofline_kstage": {"kernel": "rs_scatter_kernel", "bound": "hbm", "achieved": sort_gbs, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": None,
+                            "algorithmic_bytes_per_launch": sort_bytes, "launches": sc_n},
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in ktimes.items() if v[1]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1000.0 * e2e_s / args.steps},
+        "gpu_launches": gpu_launches,
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(args.workload, regions)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--regions", type=int, default=0, help="override regions per GPU (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int3
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbreakmer_b200.so")
+LIB_PATH = os.environ.get("BK_LIB") or os.path.join(_HERE, "lib", "libbreakmer_b200.so")
 
 BK_OK = 0
 BK_ERR_CUDA = -1

@@ -29,6 +29,16 @@ constexpr int ASM_BUF = 3 * ASM_CAP;   // gap buffers: data starts at ASM_CAP, m
 constexpr int ASM_KCAP = 2 * ASM_CAP;  // contig k-mer tuple list capacity
 constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 
+// optional phase timing (-DBK_PHASE_PROF, experiments only): cycles per phase, summed over regions
+enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_STAGE, PH_TOTAL, PH_MAXREGION, PH_COUNT_ };
+#if defined(BK_PHASE_PROF) && !defined(BK_SIM)
+#define BK_PH_BEGIN long long _ph_t0 = clock64();
+#define BK_PH_END(c, ph) (c).ph_cycles[ph] += clock64() - _ph_t0;
+#else
+#define BK_PH_BEGIN
+#define BK_PH_END(c, ph)
+#endif
+
 // ---- batch-wide inputs / state (device pointers) -----------------------------
 struct AsmParams {
   int n_regions;
@@ -87,7 +97,7 @@ struct AsmParams {
                                    //                        reads_off, n_reads, kmers_off, n_kmers
   int32_t* region_status;
   int32_t* region_ncontigs;
-  unsigned long long* stats;       // [0] check_align calls, [1] DP cells, [2] find_reads, [3] seeds
+  unsigned long long* stats;       // [0] check_align calls, [1] DP cells, [2] find_reads, [3] seeds, [8..] phase cycles
 };
 
 // ---- small warp helpers -----------------------------------------------------------------
@@ -145,6 +155,9 @@ struct RegionCtx {
   int ct_init_read;
   int status;
   int n_out;
+#if defined(BK_PHASE_PROF) && !defined(BK_SIM)
+  long long ph_cycles[PH_COUNT_];
+#endif
   // staging (shared memory on the device)
   uint8_t* s_read; uint8_t* s_contig;
 
@@ -169,11 +182,13 @@ BK_DEV int find_mer(const RegionCtx& c, uint64_t code) {
 }
 
 BK_DEV int stage_read(RegionCtx& c, int u) {
+  BK_PH_BEGIN
   const int n = c.read_len_of(u);
   const uint8_t* src = c.read_ptr(u);
   syncwarp();
   for (int x = lane(); x < n; x += WARP) c.s_read[x] = src[x];
   syncwarp();
+  BK_PH_END(c, PH_STAGE)
   return n;
 }
 BK_DEV void sync_contig_to_smem(RegionCtx& c) {
@@ -189,6 +204,7 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
   const int k = c.k;
   const int nwin = nlen - k;              // range(0, len - l)
   if (nwin <= 0) return;
+  BK_PH_BEGIN
   const int m = nlen / 2;
   const unsigned lt = lane_lt_mask();
   int32_t* Ks = c.K; int32_t* Kx = c.K + ASM_KCAP; int32_t* Km = c.K + 2 * ASM_KCAP;
@@ -224,6 +240,7 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
   }
   if (c.nK > ASM_KCAP) { c.nK = ASM_KCAP; c.status = ST_CAPACITY; }
   syncwarp();
+  BK_PH_END(c, PH_KMERS)
 }
 
 BK_DEV void set_kmers(RegionCtx& c) {                               // :548-550
@@ -358,10 +375,12 @@ BK_DEV bool check_align(RegionCtx& c, int u, int seed_s, bool grow) {
   const int lr = stage_read(c, u);
   const int lc = c.clen;
   NwDual r;
+  BK_PH_BEGIN
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  if (lr <= 128) nw_dual_warp<4, false>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, nullptr, r);
-  else nw_dual_warp<8, false>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, nullptr, r);
+  if (lr <= 128) nw_dual_warp_fast<4>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, r);
+  else nw_dual_warp_fast<8>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, r);
   const NwOut v1 = r.b, v2 = r.a;
+  BK_PH_END(c, PH_NW)
   if (lane() == 0) {
     atomic_add(&c.P->stats[0], 1ull);
     atomic_add(&c.P->stats[1], (unsigned long long)lc * (unsigned long long)lr);
@@ -437,6 +456,7 @@ BK_DEV bool add_contig(RegionCtx& c, int u, int seed_s) {
 // ---- contig.check_alt_reads (:568-582, Q12, Q13) + finalize (:584-599) + rb.clean (:389-397, Q11) --
 BK_DEV void finalize(RegionCtx& c, bool setup) {
   if (setup) set_kmers(c);
+  BK_PH_BEGIN
   c.fin_serial += 1;
   const int k = c.k;
   for (int a = 0; a < c.n_alt; ++a) {
@@ -478,11 +498,13 @@ BK_DEV void finalize(RegionCtx& c, bool setup) {
   for (int d = lane(); d < c.n_del; d += WARP) c.r_deleted[c.l_del[d]] = 1;   // del fq_recs[read.seq]
   c.n_alt = 0; c.n_del = 0;
   syncwarp();
+  BK_PH_END(c, PH_FINALIZE)
 }
 
 // ---- find_reads / read_search (:102-122; Q9, Q10, Q28) -------------------------------------------
 // result in hit_u / hit_pos, sorted by (pos, -len) or (-pos, -len), ties in read order
 BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
+  BK_PH_BEGIN
   const int64_t a = c.P->post_off[c.gm0 + s], b = c.P->post_off[c.gm0 + s + 1];
   const int32_t* pr = c.P->post_read + a;
   const int32_t* pp = c.P->post_pos + a;
@@ -525,6 +547,7 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
   }
   syncwarp();
   if (lane() == 0) atomic_add(&c.P->stats[2], 1ull);
+  BK_PH_END(c, PH_FIND)
   return n;
 }
 
@@ -556,6 +579,7 @@ BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
 
 // ---- set_kmer_locs (:434-438, Q25) + emit the accepted contig -------------------------------------------
 BK_DEV void emit_contig(RegionCtx& c) {
+  BK_PH_BEGIN
   const AsmParams& P = *c.P;
   const int k = c.k, len = c.clen;
   const int32_t* Ks = c.K; const int32_t* Kx = c.K + ASM_KCAP; const int32_t* Km = c.K + 2 * ASM_KCAP;
@@ -638,6 +662,7 @@ BK_DEV void emit_contig(RegionCtx& c) {
   }
   c.n_out += 1;
   syncwarp();
+  BK_PH_END(c, PH_EMIT)
 }
 
 // ---- contig.grow (:616-649) ------------------------------------------------------------------------------
@@ -765,7 +790,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 
 #ifndef BK_SIM
 constexpr int ASM_WARPS_PER_CTA = 1;
-__global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA) assemble_kernel(AsmParams P) {
+__global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA, 8) assemble_kernel(AsmParams P) {
   __shared__ __align__(16) uint8_t s_read[ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
   const int64_t slot = blockIdx.x;
@@ -777,7 +802,18 @@ __global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA) assemble_kernel(AsmPar
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
     bind_region(c, P, region, slot, s_read, s_contig);
+#if defined(BK_PHASE_PROF)
+    for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
+    const long long t_reg0 = clock64();
+#endif
     assemble_region(c);
+#if defined(BK_PHASE_PROF)
+    c.ph_cycles[PH_TOTAL] = clock64() - t_reg0;
+    if (lane() == 0) {
+      for (int i = 0; i < PH_MAXREGION; ++i) atomicAdd(&P.stats[8 + i], (unsigned long long)c.ph_cycles[i]);
+      atomicMax(&P.stats[8 + PH_MAXREGION], (unsigned long long)c.ph_cycles[PH_TOTAL]);
+    }
+#endif
     if (lane() == 0) { P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out; }
     syncwarp();
   }

@@ -121,6 +121,10 @@ inline void nw_dual_warp(const uint8_t* cs, int m, const uint8_t* rs, int n, int
   nw_decode_a(best_a, best_ai, m, out.a);
   nw_decode_b(best_b, best_bj, n, out.b);
 }
+template <int C>
+inline void nw_dual_warp_fast(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, NwDual& out) {
+  nw_dual_warp<C, false>(cs, m, rs, n, e0, e1, nullptr, out);
+}
 #else
 // ---------------------------------------------------------------------------
 // The product kernel.
@@ -218,6 +222,150 @@ __device__ __forceinline__ void nw_dual_warp(const uint8_t* __restrict__ cs, int
     best_ai = __shfl_sync(FULL, best_ai, own_lane);
   }
   // B: max score over the last row, largest column on ties (olc.py:81 uses >=)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int oq = __shfl_xor_sync(FULL, best_b, off);
+    const int oj = __shfl_xor_sync(FULL, best_bj, off);
+    const int s0 = best_b >> NW_SHIFT, s1 = oq >> NW_SHIFT;
+    if (s1 > s0 || (s1 == s0 && oj > best_bj)) { best_b = oq; best_bj = oj; }
+  }
+  nw_decode_a(best_a, best_ai, m, out.a);
+  nw_decode_b(best_b, best_bj, n, out.b);
+}
+
+// Fast path (no pointer table): TWO rows per systolic step.  Lane L works on rows
+// (2(t-L)+1, 2(t-L)+2) at step t; within the lane's C-column strip the 2 x C tile is
+// evaluated as straight-line code, so the four independent dependency chains (two
+// rows x two directions) overlap in the pipeline, and the step count is halved.
+// Row characters are fetched one step ahead.  `rs` must be 2-byte aligned and
+// readable up to index n (one byte past the sequence).
+template <int C>
+__device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs, int m,
+                                                  const uint8_t* __restrict__ rs, int n,
+                                                  int2* edge0, int2* edge1, NwDual& out) {
+  const unsigned FULL = 0xffffffffu;
+  const int L = lane();
+  constexpr int W = 32 * C;
+  const int nblk = (m + W - 1) / W;
+  int best_a = NW_BIAS + m, best_ai = 0;        // score[0][m] = 0 (olc.py:79-83 starts at row 0)
+  int best_b = NW_BIAS, best_bj = 0;            // score[n][0] = 0
+  const int steps = ((n + 1) >> 1) + 31;
+  for (int b = 0; b < nblk; ++b) {
+    const int jb = b * W;
+    const int jfirst = jb + L * C + 1;          // 1-based column held in slot 0
+    int colA[C], colB[C], ch[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = jfirst + c;
+      colA[c] = colB[c] = NW_BIAS + j;          // row 0: score 0, origin (0, j)
+      ch[c] = (j <= m) ? (int)cs[j - 1] : 0x100;
+    }
+    int diagA = NW_BIAS + (jfirst - 1), diagB = diagA;
+    int lastA0 = 0, lastB0 = 0, lastA1 = colA[C - 1], lastB1 = colB[C - 1];
+    const int2* ein = (b & 1) ? edge1 : edge0;
+    int2* eout = (b & 1) ? edge0 : edge1;
+    const bool more = (b + 1 < nblk);
+    const bool own = (m > jb) && (m <= jb + W) && (L == (m - 1 - jb) / C);
+    const int own_c = (m - 1 - jb) % C;
+    // row characters of the first step this lane is active in (t == L): rows 1 and 2
+    unsigned rc_next = *reinterpret_cast<const unsigned short*>(rs);
+    for (int t = 0; t < steps; ++t) {
+      int hA0 = __shfl_up_sync(FULL, lastA0, 1);
+      int hB0 = __shfl_up_sync(FULL, lastB0, 1);
+      int hA1 = __shfl_up_sync(FULL, lastA1, 1);
+      int hB1 = __shfl_up_sync(FULL, lastB1, 1);
+      const int i0 = 2 * (t - L) + 1, i1 = i0 + 1;
+      const bool active = (t >= L) && (i0 <= n);
+      if (L == 0) {
+        if (b == 0) {
+          hA0 = hB0 = NW_BIAS - i0;             // column 0: score 0, origin (i, 0)
+          hA1 = hB1 = NW_BIAS - i1;
+        } else if (active) {
+          const int2 e0 = ein[i0];
+          hA0 = e0.x; hB0 = e0.y;
+          if (i1 <= n) { const int2 e1 = ein[i1]; hA1 = e1.x; hB1 = e1.y; }
+        }
+      }
+      if (active) {
+        const unsigned rc = rc_next;
+        {   // prefetch the two row characters of the next step (clamped, always in bounds)
+          int nx = i0 + 1;                      // index of row i0+2 in rs
+          nx = nx > NW_MAX_LEN - 1 ? NW_MAX_LEN - 1 : nx;
+          rc_next = *reinterpret_cast<const unsigned short*>(rs + nx);
+        }
+        const int rc0 = (int)(rc & 0xffu), rc1 = (int)(rc >> 8);
+        int r0A[C], r0B[C];
+        // ---- row i0 ----
+        {
+          int dA = diagA, dB = diagB, hA = hA0, hB = hB0;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int vA = colA[c], vB = colB[c];
+            const int s = (ch[c] == rc0) ? NW_D_MATCH : NW_D_MISM;
+            int tA = dA + s;
+            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
+            tA = __viaddmax_s32(vA, NW_GAP_LO, tA);
+            int tB = dB + s;
+            tB = __viaddmax_s32(vB, NW_GAP_HI, tB);
+            tB = __viaddmax_s32(hB, NW_GAP_LO, tB);
+            dA = vA; dB = vB;
+            hA = tA & NW_TAG_CLEAR; hB = tB & NW_TAG_CLEAR;
+            r0A[c] = hA; r0B[c] = hB;
+          }
+        }
+        // ---- row i1 (garbage when i1 == n + 1; never observed) ----
+        {
+          int dA = hA0, dB = hB0, hA = hA1, hB = hB1;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int vA = r0A[c], vB = r0B[c];
+            const int s = (ch[c] == rc1) ? NW_D_MATCH : NW_D_MISM;
+            int tA = dA + s;
+            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
+            tA = __viaddmax_s32(vA, NW_GAP_LO, tA);
+            int tB = dB + s;
+            tB = __viaddmax_s32(vB, NW_GAP_HI, tB);
+            tB = __viaddmax_s32(hB, NW_GAP_LO, tB);
+            dA = vA; dB = vB;
+            hA = tA & NW_TAG_CLEAR; hB = tB & NW_TAG_CLEAR;
+            colA[c] = hA; colB[c] = hB;
+          }
+        }
+        diagA = hA1; diagB = hB1;               // Q(i1, jfirst-1): diagonal input of the next step's first row
+        lastA0 = r0A[C - 1]; lastB0 = r0B[C - 1];
+        lastA1 = colA[C - 1]; lastB1 = colB[C - 1];
+        if (more && L == 31) {
+          eout[i0] = make_int2(lastA0, lastB0);
+          if (i1 <= n) eout[i1] = make_int2(lastA1, lastB1);
+        }
+        {   // last column (direction A): rows in increasing order, >= keeps the largest row
+          int c0 = r0A[0], c1 = colA[0];
+#pragma unroll
+          for (int c = 1; c < C; ++c) { c0 = (c == own_c) ? r0A[c] : c0; c1 = (c == own_c) ? colA[c] : c1; }
+          const bool u0 = own && ((c0 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
+          best_a = u0 ? c0 : best_a; best_ai = u0 ? i0 : best_ai;
+          const bool u1 = own && (i1 <= n) && ((c1 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
+          best_a = u1 ? c1 : best_a; best_ai = u1 ? i1 : best_ai;
+        }
+        if (i0 == n) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if (jfirst + c <= m && (r0B[c] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = r0B[c]; best_bj = jfirst + c; }
+        } else if (i1 == n) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if (jfirst + c <= m && (colB[c] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = colB[c]; best_bj = jfirst + c; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  {
+    const int jb = (nblk - 1) * W;
+    const int own_lane = (m - 1 - jb) / C;
+    best_a = __shfl_sync(FULL, best_a, own_lane);
+    best_ai = __shfl_sync(FULL, best_ai, own_lane);
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     const int oq = __shfl_xor_sync(FULL, best_b, off);

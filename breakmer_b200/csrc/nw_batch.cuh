@@ -33,8 +33,13 @@ struct NwBatchParams {
 template <bool PTR>
 __device__ __forceinline__ void nw_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1,
                                             uint8_t* ptrmat, NwDual& out) {
-  if (m <= 128) nw_dual_warp<4, PTR>(cs, m, rs, n, e0, e1, ptrmat, out);
-  else nw_dual_warp<8, PTR>(cs, m, rs, n, e0, e1, ptrmat, out);
+  if (PTR) {
+    if (m <= 128) nw_dual_warp<4, true>(cs, m, rs, n, e0, e1, ptrmat, out);
+    else nw_dual_warp<8, true>(cs, m, rs, n, e0, e1, ptrmat, out);
+  } else {
+    if (m <= 128) nw_dual_warp_fast<4>(cs, m, rs, n, e0, e1, out);
+    else nw_dual_warp_fast<8>(cs, m, rs, n, e0, e1, out);
+  }
 }
 
 __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams p) {

@@ -383,7 +383,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   auto zalloc = [&](size_t bytes) { bytes = (bytes + 255) & ~size_t(255); size_t o = zero_bytes; zero_bytes += bytes; return o; };
   const size_t o_mused = zalloc(S_total), o_checked = zalloc(S_total * 4), o_taken = zalloc(S_total * 4);
   const size_t o_rused = zalloc(NU), o_rdel = zalloc(NU), o_rq = zalloc(NU), o_rbuf = zalloc(NU * 4), o_rin = zalloc(NU * 4);
-  const size_t o_work = zalloc(sizeof(int)), o_cursor = zalloc(5 * sizeof(unsigned long long)), o_stats = zalloc(4 * sizeof(unsigned long long));
+  const size_t o_work = zalloc(sizeof(int)), o_cursor = zalloc(5 * sizeof(unsigned long long)), o_stats = zalloc(16 * sizeof(unsigned long long));
   zero_lo = h->dev.get<uint8_t>(zero_bytes);
   A.m_used = zero_lo + o_mused; A.m_checked = (uint32_t*)(zero_lo + o_checked); A.m_taken = (uint32_t*)(zero_lo + o_taken);
   A.r_used = zero_lo + o_rused; A.r_deleted = zero_lo + o_rdel; A.r_queued = zero_lo + o_rq;
@@ -417,7 +417,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     }
     BK_CUDA(cudaGetLastError());
     h_cursor = to_host(h, A.out_cursor, 5);
-    h_stats = to_host(h, A.stats, 4);
+    h_stats = to_host(h, A.stats, 16);
     h_status = to_host(h, A.region_status, (size_t)(R ? R : 1));
     BK_CUDA(cudaStreamSynchronize(st));
     const bool overflow = h_cursor[0] > A.cap_seq || h_cursor[1] > A.cap_cnt || h_cursor[2] > A.cap_reads ||
@@ -432,6 +432,11 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   out->n_contigs = n_ctg;
   out->n_check_align = (int64_t)h_stats[0];
   out->n_dp_cells = (int64_t)h_stats[1];
+  if (getenv("BK_PHASE_PRINT")) {
+    static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "stage", "total", "max_region"};
+    for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
+    fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu\n", h_stats[2], h_stats[3], h_stats[0]);
+  }
   out->so_off = h_so_off;
   out->so_mers = to_host(h, so_mer, (size_t)S_total);
   out->so_counts = to_host(h, so_cnt, (size_t)S_total);

@@ -96,7 +96,7 @@ extern "C" int sim_assemble_region(
   P.o_kmer_mer = o_kmer_mer; P.o_kmer_pos = o_kmer_pos; P.o_kmer_meta = o_kmer_meta; P.o_desc = o_desc;
   int32_t status = 0, ncontigs = 0;
   P.region_status = &status; P.region_ncontigs = &ncontigs;
-  unsigned long long stats[4] = {0, 0, 0, 0};
+  unsigned long long stats[16] = {0};
   P.stats = stats;
   std::vector<uint8_t> s_read(ASM_CAP), s_contig(ASM_CAP);
   RegionCtx c;
