@@ -1,0 +1,85 @@
+"""Drop-in for `target.compare_kmers()` (sv_processor.py:609-645) and a batched
+form for the region loop (sv_processor.py:185-201).
+
+`compare_kmers(target)` takes the reference's own `target` object (or anything
+shaped like it) after `set_ref_data`, `extract_bam_reads` and `clean_reads` have
+run, and leaves it in the state the reference method leaves it in:
+
+    target.kmers['clusters']   list of contigs (breakmer_b200.sv_assembly.contig)
+    target.kmers['ref'|'case'|'case_sc'|'case_only'] = {}       (:634-636, :644)
+    target.files['sample_kmers']  "<kmers path>/<name>_sample_kmers.out" written
+                                  as "<mer>\\t<case count>" lines (:625-632)
+    target.files['kmer_clusters'] set (:639)
+    target.cleaned_read_recs = None                              (:643)
+
+What it reads from the target: files['target_ref_fn'][0] (forward reference
+FASTA; the reverse-complement file the reference also counts is by construction
+its reverse complement, utils.py:367-371, and is derived on the device),
+files['cleaned_fq'], files['sv_sc_unmapped_fa'], cleaned_read_recs, read_len,
+paths['kmers'], name, params.get_kmer_size(), params.get_sr_thresh('min').
+An optional files['normal_fq'] enables normal-sample subtraction (K4).
+
+`compare_kmers_batch(targets)` does the same for many targets in ONE device
+pass; the reference loop becomes: extract+clean all targets, one batched call,
+then resolve_sv per target.
+"""
+import os
+
+from . import batch, get_handle, utils
+from .sv_assembly import contig
+
+
+class _TargetInput:
+    def __init__(self, trgt):
+        self.name = trgt.name
+        self.k = int(trgt.params.get_kmer_size())
+        self.rc_thresh = int(trgt.params.get_sr_thresh('min'))
+        refs = utils.read_sequences(trgt.files['target_ref_fn'][0])
+        self.ref_fwd = refs[0] if refs else ""
+        self.reads = []
+        self.objs = []
+        for seq, group in trgt.cleaned_read_recs.items():
+            for fr in group:
+                self.reads.append((fr.id, fr.seq, fr.qual, bool(fr.indel_only)))
+                self.objs.append(fr)
+        self.sc_records = [("sc", s) for s in utils.read_sequences(trgt.files['sv_sc_unmapped_fa'])]
+        nfq = trgt.files.get('normal_fq') if hasattr(trgt.files, "get") else None
+        self.normal_reads = [("n", s) for s in utils.read_sequences(nfq)] if nfq else []
+        self.read_len = int(trgt.read_len)
+
+
+def compare_kmers_batch(targets, device=0):
+    import numpy as np
+    if not targets:
+        return
+    inputs = [_TargetInput(t) for t in targets]
+    pk = batch.PackedBatch(inputs, rc_thresh=inputs[0].rc_thresh)
+    pk.read_len = np.array([inp.read_len for inp in inputs] + [0], dtype=np.int32)
+    out = batch.run(get_handle(device), pk)
+    objs = [o for inp in inputs for o in inp.objs]
+    for i, trgt in enumerate(targets):
+        if out.region_status[i] != 0:
+            raise RuntimeError("compare_kmers: device capacity exceeded for target %s" % trgt.name)
+        only = out.sample_only(i)
+        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
+        with open(trgt.files['sample_kmers'], 'w') as f:
+            for mer, cnt in only.items():
+                f.write("\t".join([mer, str(cnt)]) + "\n")
+        for key in ('ref', 'case', 'case_sc'):
+            trgt.kmers[key] = {}
+        logger = getattr(trgt, "logger", None)
+        if logger is not None:
+            logger.info('Writing %d sample-only kmers to file %s' % (len(only), trgt.files['sample_kmers']))
+        trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
+        ctgs = []
+        for j, rec in enumerate(out.contig_records(i)):
+            cidx = int(out.ctg_reg_off[i]) + j
+            ro, nr = out.reads_off[cidx]
+            ctgs.append(contig(rec, [objs[int(r)] for r in out.reads[ro:ro + nr]], inputs[i].k))
+        trgt.kmers['clusters'] = ctgs
+        trgt.cleaned_read_recs = None
+        trgt.kmers['case_only'] = {}
+
+
+def compare_kmers(target, device=0):
+    compare_kmers_batch([target], device=device)

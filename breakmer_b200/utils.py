@@ -1,0 +1,110 @@
+"""Drop-ins for the hot-path pieces of the reference's utils.py.
+
+  fq_read, FastqFile        utils.py:681-720  (record model, T1)
+  run_jellyfish             utils.py:151-179  k-mer counting, on the GPU instead of
+                                              `jellyfish count` + `jellyfish dump -c`
+  load_kmers                utils.py:287-297  dump file(s) -> {mer: count}
+  get_marker_fn             utils.py:146
+
+`run_jellyfish` keeps the reference's signature, file naming and marker-file
+cache: it writes "<fa_fn>_<k>mers_dump" ("<MER> <count>" per line, the format
+`dump -c` produces) next to the input and touches ".<dump name>".  The
+`jellyfish` argument (path of the binary) is accepted and ignored.
+"""
+import logging
+import os
+
+from . import _lib, get_handle
+
+
+class fq_read:
+    def __init__(self, header, seq, qual, indel_only):
+        self.id = header
+        self.seq = str(seq)
+        self.qual = str(qual)
+        self.used = False
+        self.dup = False
+        self.indel_only = indel_only
+
+
+class FastqFile(object):
+    """Iterator over (header, seq, qual); like the reference it insists on the
+    five ':'-separated header fields (utils.py:704-712)."""
+
+    def __init__(self, f):
+        if isinstance(f, str):
+            f = open(f)
+        self._f = f
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        header, seq, _qh, qual = [next(self._f) for _ in range(4)]
+        header = header.strip()
+        inst, lane, tile, x, y_end = header.split(':')
+        return (header, seq.strip(), qual.strip())
+
+    next = __next__
+
+
+def get_marker_fn(fn):
+    return os.path.join(os.path.split(fn)[0], "." + os.path.basename(fn))
+
+
+def read_sequences(fn):
+    """Record sequences of a FASTA or FASTQ file (format sniffed from the first
+    byte, as jellyfish does); multi-line FASTA records are joined."""
+    seqs = []
+    with open(fn) as f:
+        first = f.read(1)
+        f.seek(0)
+        if first == "@":
+            lines = f.read().splitlines()
+            for i in range(1, len(lines), 4):
+                seqs.append(lines[i].strip())
+        else:
+            cur = None
+            for line in f:
+                line = line.strip()
+                if line.startswith(">"):
+                    if cur is not None:
+                        seqs.append("".join(cur))
+                    cur = []
+                elif cur is not None:
+                    cur.append(line)
+            if cur is not None:
+                seqs.append("".join(cur))
+    return seqs
+
+
+def run_jellyfish(fa_fn, jellyfish, kmer_size):
+    logger = logging.getLogger('root')
+    file_path = os.path.split(fa_fn)[0]
+    file_base = os.path.basename(fa_fn)
+    dump_fn = os.path.join(file_path, file_base + "_" + str(kmer_size) + "mers_dump")
+    dump_marker_fn = get_marker_fn(dump_fn)
+    if not os.path.isfile(dump_marker_fn):
+        logger.info('Counting %d-mers of %s on the GPU' % (kmer_size, fa_fn))
+        mers, counts = get_handle().count_kmers(read_sequences(fa_fn), int(kmer_size))
+        with open(dump_fn, "w") as out:
+            for m, c in zip(mers, counts):
+                out.write("%s %d\n" % (_lib.code_to_mer(m, int(kmer_size)), int(c)))
+        open(dump_marker_fn, "a").close()
+        logger.info('Completed k-mer dump %s, touching marker file %s' % (dump_fn, dump_marker_fn))
+    else:
+        logger.info('Kmers already generated for target.')
+    return dump_fn
+
+
+def load_kmers(fns, kmers):
+    fns = fns.split(",")
+    for fn in fns:
+        with open(fn) as f:
+            for line in f.readlines():
+                line = line.strip()
+                mer, count = line.split()
+                if mer not in kmers:
+                    kmers[mer] = 0
+                kmers[mer] += int(count)
+    return kmers

@@ -1,0 +1,145 @@
+"""GPU tests of the reference-shaped Python API (the drop-in boundary): olc.nw,
+utils.run_jellyfish/load_kmers, sv_assembly.init_assembly, target.compare_kmers."""
+import logging
+import os
+
+import pytest
+
+from conftest import golden
+from breakmer_b200 import synth
+from oracle import assembler_py, kmers_py
+from oracle.make_golden import oracle_sample_only, region_scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def test_olc_nw_signature_and_values():
+    from breakmer_b200 import olc
+    cases = golden("nw_golden.json")["cases"][:40]
+    for c in cases[:6]:
+        assert list(olc.nw(c["seq1"], c["seq2"])) == c["out"]
+    got = olc.nw_batch([(c["seq1"], c["seq2"]) for c in cases])
+    assert [list(g) for g in got] == [c["out"] for c in cases]
+    with pytest.raises(NameError):
+        olc.nw("", "ACGT")
+    assert (olc.match_award, olc.mismatch_penalty, olc.gap_penalty) == (1, -2, -2)
+
+
+def _write_region_files(region, d):
+    ref_f = os.path.join(d, region.name + "_forward_refseq.fa")
+    ref_r = os.path.join(d, region.name + "_reverse_refseq.fa")
+    with open(ref_f, "w") as f:
+        f.write(">%s\n%s\n" % (region.name, region.ref_fwd))
+    with open(ref_r, "w") as f:
+        f.write(">%s\n%s\n" % (region.name, kmers_py.revcomp(region.ref_fwd)))
+    fq = os.path.join(d, region.name + "_sv_reads_cleaned_filtered.fastq")
+    with open(fq, "w") as f:
+        for rid, seq, qual, _io in region.reads:
+            f.write("%s\n%s\n+\n%s\n" % (rid, seq, qual))
+    sc = os.path.join(d, region.name + "_sv_sc_seqs.fa")
+    with open(sc, "w") as f:
+        for name, seq in region.sc_records:
+            f.write(">%s\n%s\n" % (name, seq))
+    return ref_f, ref_r, fq, sc
+
+
+def test_run_jellyfish_and_load_kmers_like_the_reference(tmp_path):
+    from breakmer_b200 import utils
+    name, kw = region_scenarios()[4]
+    region = synth.make_region(name, **kw)
+    ref_f, ref_r, fq, sc = _write_region_files(region, str(tmp_path))
+    k = region.k
+    # sv_processor.py:613-620, verbatim shape
+    ref = {}
+    for fn in (ref_f, ref_r):
+        ref = utils.load_kmers(utils.run_jellyfish(fn, "/no/such/jellyfish", k), ref)
+    case = utils.load_kmers(utils.run_jellyfish(fq, "jellyfish", k), {})
+    case_sc = utils.load_kmers(utils.run_jellyfish(sc, "jellyfish", k), {})
+    oref, ocase, osc, only = oracle_sample_only(region)
+    assert ref == oref and case == ocase and case_sc == osc
+    sample_only = list((set(case) & set(case_sc)).difference(set(ref)))
+    assert {m: case[m] for m in sample_only} == only
+    # marker-file cache (utils.py:157): a second call must not recount
+    dump = fq + "_%dmers_dump" % k
+    assert os.path.isfile(utils.get_marker_fn(dump))
+    os.remove(dump)
+    assert utils.run_jellyfish(fq, "jellyfish", k) == dump and not os.path.isfile(dump)
+    # comma separated list accumulates (utils.py:288-295)
+    both = utils.load_kmers(",".join([ref_f + "_%dmers_dump" % k, ref_r + "_%dmers_dump" % k]), {})
+    assert both == oref
+
+
+def _fq_recs(region):
+    from breakmer_b200.utils import fq_read
+    fq_recs = {}
+    for rid, seq, qual, io in region.reads:
+        fr = fq_read(rid, seq, qual, io)
+        fq_recs.setdefault(fr.seq, []).append(fr)
+    return fq_recs
+
+
+def test_init_assembly_drop_in():
+    from breakmer_b200 import sv_assembly
+    cases = [c for c in golden("assembly_golden.json")["cases"] if "contigs" in c][:12]
+    for c in cases:
+        kw = dict(c["kwargs"]); kw["event"] = tuple(kw["event"])
+        region = synth.make_region(c["name"], **kw)
+        _r, _c, _s, only = oracle_sample_only(region)
+        ctgs = sv_assembly.init_assembly(only, _fq_recs(region), region.k, region.rc_thresh, region.read_len)
+        got = [{"seq": ct.get_contig_seq(), "indel_only": ct.get_contig_counts().indel_only,
+                "others": ct.get_contig_counts().others, "reads": sorted(r.id for r in ct.reads),
+                "kmers": [list(t) for t in ct.kmers], "kmer_locs": ct.get_kmer_locs()} for ct in ctgs]
+        assert got == c["contigs"], c["name"]               # the reference's own output
+        for ct in ctgs:
+            assert ct.get_contig_len() == len(ct.aseq.seq)
+            assert ct.get_total_read_support() == max(ct.aseq.counts.indel_only) + max(ct.aseq.counts.others)
+            n = len(ct.aseq.counts.others)
+            assert ct.aseq.counts.get_counts(0, min(5, n), 'indel') == \
+                [a + b for a, b in zip(ct.aseq.counts.indel_only[:5], ct.aseq.counts.others[:5])]
+    assert sv_assembly.init_assembly({}, {}, 15, 2, 100) == []
+
+
+class _Params:
+    def __init__(self, k):
+        self.k = k
+        self.opts = {"jellyfish": "jellyfish"}
+
+    def get_kmer_size(self):
+        return self.k
+
+    def get_sr_thresh(self, kind):
+        assert kind == 'min'
+        return 2
+
+
+class _Target:
+    """The slice of sv_processor.target that compare_kmers touches."""
+
+    def __init__(self, region, d):
+        ref_f, ref_r, fq, sc = _write_region_files(region, d)
+        self.name = region.name
+        self.params = _Params(region.k)
+        self.files = {"target_ref_fn": [ref_f, ref_r], "cleaned_fq": fq, "sv_sc_unmapped_fa": sc}
+        self.paths = {"kmers": d}
+        self.kmers = {}
+        self.cleaned_read_recs = _fq_recs(region)
+        self.read_len = region.read_len
+        self.logger = logging.getLogger("root")
+
+
+def test_compare_kmers_single_and_batched(tmp_path):
+    from breakmer_b200 import sv_processor
+    regions = [synth.make_region(n, **kw) for n, kw in region_scenarios()[:8] if kw["k"] == 15]
+    targets = [_Target(r, str(tmp_path)) for r in regions]
+    sv_processor.compare_kmers(targets[0])
+    sv_processor.compare_kmers_batch(targets[1:])
+    for r, t in zip(regions, targets):
+        _a, _b, _c, only = oracle_sample_only(r)
+        exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
+        with open(t.files["sample_kmers"]) as f:
+            lines = dict(l.split("\t") for l in f.read().splitlines())
+        assert {m: int(c) for m, c in lines.items()} == only
+        assert [ct.get_contig_seq() for ct in t.kmers["clusters"]] == [e["seq"] for e in exp]
+        assert [sorted(x.id for x in ct.reads) for ct in t.kmers["clusters"]] == [e["reads"] for e in exp]
+        assert t.cleaned_read_recs is None and t.kmers["case_only"] == {} and t.kmers["ref"] == {}
+        assert t.files["kmer_clusters"].endswith("_sample_kmers_merged.out")
