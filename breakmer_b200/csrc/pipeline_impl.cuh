@@ -214,7 +214,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     sc.table = h->dev.get<uint32_t>(256 * tiles);
     sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
     uint64_t* sk; uint32_t* sv;
-    radix_sort_pairs(hk, hv, n_rec, 64, sc, st, &sk, &sv, h->timers);
+    radix_sort_pairs(hk, hv, n_rec, 64, sc, st, &sk, &sv, h->timers, true);
     int32_t* leader_of = h->dev.get<int32_t>(n_rec);
     uint32_t* mult_by_rec = dev_zero<uint32_t>(h, n_rec);
     uint32_t* flag = h->dev.get<uint32_t>(n_rec);
@@ -298,7 +298,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     sc.table = h->dev.get<uint32_t>(256 * tiles);
     sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
     uint64_t* sk; uint32_t* sv;
-    radix_sort_pairs(sk0, sv0, S_total, 64, sc, st, &sk, &sv, h->timers);
+    radix_sort_pairs(sk0, sv0, S_total, 64, sc, st, &sk, &sv, h->timers, true);
     TimedLaunch t(h->timers, st, KF_PREP);
     unpack_u32_to_i32_kernel<<<nblk(S_total, 256), 256, 0, st>>>(sv, S_total, seed_order);
   }
@@ -331,7 +331,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       sc.vals_alt = h->dev.get<uint32_t>(n_post);
       sc.table = h->dev.get<uint32_t>(256 * tiles);
       sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
-      radix_sort_pairs(ik, iv, n_post, 24 + bits_for((uint64_t)S_total + 1), sc, st, &sk, &sv, h->timers);
+      radix_sort_pairs(ik, iv, n_post, 24 + bits_for((uint64_t)S_total + 1), sc, st, &sk, &sv, h->timers, true);
     }
     TimedLaunch t(h->timers, st, KF_INDEX, 2);
     post_off_kernel<<<nblk(S_total + 1, 256), 256, 0, st>>>(sk, n_post, S_total, post_off);

@@ -107,7 +107,8 @@ inline int64_t rs_num_tiles(int64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 // last pass wrote, returned through *keys_sorted / *vals_sorted.  Returns the
 // number of passes run.
 inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, const RadixSortScratch& s,
-                            cudaStream_t st, uint64_t** keys_sorted, uint32_t** vals_sorted, KernelTimers& kt) {
+                            cudaStream_t st, uint64_t** keys_sorted, uint32_t** vals_sorted, KernelTimers& kt,
+                            bool aux = false) {
   uint64_t* ka = keys; uint64_t* kb = s.keys_alt;
   uint32_t* va = vals; uint32_t* vb = s.vals_alt;
   int passes = 0;
@@ -118,15 +119,15 @@ inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int key_b
     for (int p = 0; p < passes; ++p) {
       const int shift = 8 * p;
       {
-        TimedLaunch t(kt, st, KF_SORT_COUNT);
+        TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_COUNT);
         rs_count_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, n, shift, s.table, tiles);
       }
       {
-        TimedLaunch t(kt, st, KF_SORT_SCAN, 3);
+        TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_SCAN, 3);
         exclusive_scan_u32(s.table, s.table, 256 * tiles, s.scan_tmp, nullptr, st);
       }
       {
-        TimedLaunch t(kt, st, KF_SORT_SCATTER);
+        TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_SCATTER);
         rs_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, shift, s.table, tiles);
       }
       uint64_t* tk = ka; ka = kb; kb = tk;
