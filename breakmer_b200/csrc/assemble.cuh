@@ -29,6 +29,25 @@ constexpr int ASM_BUF = 3 * ASM_CAP;   // gap buffers: data starts at ASM_CAP, m
 constexpr int ASM_KCAP = 2 * ASM_CAP;  // contig k-mer tuple list capacity
 constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 
+// Speculation width: the next ASM_SPEC_W reads of a contig's read stream are aligned
+// against the current contig concurrently, one warp each (the CTA has ASM_SPEC_W
+// warps per region; warp 0 also runs the state machine).  Results are committed
+// in stream order and discarded from the first read that changes the contig
+// sequence, so the outcome is identical to checking the reads one by one.
+#ifndef ASM_SPEC_W
+#define ASM_SPEC_W 4
+#endif
+
+struct SpecShared {               // command + results of one speculation round (shared memory)
+  int n;                          // reads in this round, -1 = workers exit
+  int lc;                         // contig length
+  int region;
+  int u[ASM_SPEC_W];              // local unique-read indices
+  int lr[ASM_SPEC_W];
+  NwOut v1[ASM_SPEC_W];           // nw(contig, read)
+  NwOut v2[ASM_SPEC_W];           // nw(read, contig)
+};
+
 // optional phase timing (-DBK_PHASE_PROF, experiments only): cycles per phase, summed over regions
 enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_STAGE, PH_TOTAL, PH_MAXREGION, PH_COUNT_ };
 #if defined(BK_PHASE_PROF) && !defined(BK_SIM)
@@ -98,6 +117,7 @@ struct AsmParams {
   int32_t* region_status;
   int32_t* region_ncontigs;
   unsigned long long* stats;       // [0] check_align calls, [1] DP cells, [2] find_reads, [3] seeds, [8..] phase cycles
+  unsigned long long* prof_regions; // BK_PHASE_PROF: n_regions x 8 phase cycles (or null)
 };
 
 // ---- small warp helpers -----------------------------------------------------------------
@@ -144,6 +164,13 @@ struct RegionCtx {
   int32_t* q_read; int32_t* q_seed; int q_head, q_tail;
   int32_t* l_alt; int32_t* l_del; int n_alt, n_del;
   int32_t* hit_u; int32_t* hit_pos; int32_t* hit2_u; int32_t* hit2_pos;
+  // read stream of the current snapshot (st_u aliases hit_u) and speculation state
+  int st_n;
+  int rnd_base, rnd_cnt;          // stream range the last round covers
+  unsigned seq_ver;               // bumped whenever the contig SEQUENCE changes
+  SpecShared* sp;
+  uint8_t* s_reads;               // ASM_SPEC_W staging buffers of ASM_CAP bytes; [0] doubles as s_read
+  int2* edge_all;                 // ASM_SPEC_W x (2 * ASM_CAP) int2 or null
   // contig under construction
   uint8_t* cseq; int c0, clen;
   int32_t* cnt_buf; int cur, k0, klen;
@@ -267,7 +294,7 @@ BK_DEV void extend_counts(RegionCtx& c, int l, int n, bool io, bool post) {     
 }
 // contig replaced by read u; old counts re-added at [start, end) with python's
 // zip-truncate / slice-assign semantics (:181-193, Q17).  s_read holds read u.
-BK_DEV void set_superseq(RegionCtx& c, int u, int lr, int start, int end) {
+BK_DEV void set_superseq(RegionCtx& c, int u, const uint8_t* rd, int lr, int start, int end) {
   const int n = (int)c.u_mult[u];
   const bool io = c.u_io[u] != 0;
   const int bio = io ? n : 0, bot = io ? 0 : n;
@@ -286,7 +313,8 @@ BK_DEV void set_superseq(RegionCtx& c, int u, int lr, int start, int end) {
   }
   c.cur ^= 1; c.k0 = ASM_CAP; c.klen = nl;
   c.c0 = ASM_CAP; c.clen = lr;
-  for (int x = lane(); x < lr; x += WARP) { const uint8_t ch = c.s_read[x]; c.cseq[ASM_CAP + x] = ch; c.s_contig[x] = ch; }
+  for (int x = lane(); x < lr; x += WARP) { const uint8_t ch = rd[x]; c.cseq[ASM_CAP + x] = ch; c.s_contig[x] = ch; }
+  c.seq_ver += 1;
   syncwarp();
 }
 
@@ -330,20 +358,21 @@ BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
 }
 
 // ---- contig.check_align (:449-504) and the two overlap cases (:506-546) ------------------
-BK_DEV void contig_overlap_read(RegionCtx& c, const NwOut& v1, int u, int lr, bool grow) {
+BK_DEV void contig_overlap_read(RegionCtx& c, const NwOut& v1, int u, const uint8_t* rd, int lr, bool grow) {
   const int lc = c.clen;
   if (v1.j0 == 0) {                                                 // :508 (prej == len always, Q15)
-    set_superseq(c, u, lr, v1.i0, v1.prei);
+    set_superseq(c, u, rd, lr, v1.i0, v1.prei);
     if (grow) set_kmers(c);
     return;
   }
   const int plen = lr - v1.prei;                                    // post_seq = read[aln[4]:]
   if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
   for (int x = lane(); x < plen; x += WARP) {
-    const uint8_t ch = c.s_read[v1.prei + x];
+    const uint8_t ch = rd[v1.prei + x];
     c.cseq[c.c0 + lc + x] = ch; c.s_contig[lc + x] = ch;
   }
   c.clen = lc + plen;
+  if (plen > 0) c.seq_ver += 1;
   syncwarp();
   const int n = (int)c.u_mult[u];
   const bool io = c.u_io[u] != 0;
@@ -352,7 +381,7 @@ BK_DEV void contig_overlap_read(RegionCtx& c, const NwOut& v1, int u, int lr, bo
   if (grow) append_kmers(c, c.s_contig, lc - (c.k - 1), (c.k - 1) + plen, ORDER_FOR);   // :521,525-527
 }
 
-BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, int lr, bool grow) {
+BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, const uint8_t* rd, int lr, bool grow) {
   const int n = (int)c.u_mult[u];
   const bool io = c.u_io[u] != 0;
   if (v2.j0 == 0) {                                                 // :531
@@ -362,8 +391,9 @@ BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, int lr, bo
   const int plen = v2.j0;                                           // pre_seq = read[0:aln[3]]
   const int lc = c.clen;
   if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
-  for (int x = lane(); x < plen; x += WARP) c.cseq[c.c0 - plen + x] = c.s_read[x];
+  for (int x = lane(); x < plen; x += WARP) c.cseq[c.c0 - plen + x] = rd[x];
   c.c0 -= plen; c.clen = lc + plen;
+  c.seq_ver += 1;
   sync_contig_to_smem(c);
   set_counts(c, v2.i0, v2.prei, n, io);                             // add_preseq :255-262 (old coordinates)
   extend_counts(c, plen, n, io, false);
@@ -371,16 +401,51 @@ BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, int lr, bo
   if (grow) append_kmers(c, c.s_contig, 0, plen + head, ORDER_REV);  // :539,543-545
 }
 
-BK_DEV bool check_align(RegionCtx& c, int u, int seed_s, bool grow) {
-  const int lr = stage_read(c, u);
-  const int lc = c.clen;
+// ---- the two olc.nw calls of check_align (:451-452), one warp per read ------------------------------
+// Executed by every warp of the CTA (warp w takes stream slot w of the round).
+BK_DEV void spec_work(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, const uint8_t* s_contig, int w, int2* edge) {
+  const int64_t gu0 = P.u_off[sp->region];
+  const int u = sp->u[w];
+  const int rec = P.u_rec[gu0 + u];
+  const int64_t a = P.roff[rec];
+  const int lr = (int)(P.roff[rec + 1] - a);
+  uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
+  const uint8_t* src = P.rbases + a;
+  for (int x = lane(); x < lr; x += WARP) rd[x] = src[x];
+  syncwarp();
   NwDual r;
-  BK_PH_BEGIN
+  const int lc = sp->lc;
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  if (lr <= 128) nw_dual_warp_fast<4>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, r);
-  else nw_dual_warp_fast<8>(c.s_read, lr, c.s_contig, lc, c.edge, c.edge ? c.edge + ASM_CAP : nullptr, r);
-  const NwOut v1 = r.b, v2 = r.a;
+  if (lr <= 128) nw_dual_warp_fast<4>(rd, lr, s_contig, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  else nw_dual_warp_fast<8>(rd, lr, s_contig, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  if (lane() == 0) { sp->lr[w] = lr; sp->v1[w] = r.b; sp->v2[w] = r.a; }
+  syncwarp();
+}
+
+// one speculation round over stream slots [pos, pos + cnt)
+BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
+  BK_PH_BEGIN
+  SpecShared* sp = c.sp;
+  syncwarp();
+  if (lane() == 0) {
+    sp->n = cnt; sp->lc = c.clen; sp->region = c.region;
+    for (int w = 0; w < cnt; ++w) sp->u[w] = c.hit_u[pos + w];
+  }
+  syncwarp();
+#ifdef BK_SIM
+  for (int w = 0; w < cnt; ++w) spec_work(*c.P, sp, c.s_reads, c.s_contig, w, nullptr);
+#else
+  __syncthreads();                                   // release the worker warps
+  spec_work(*c.P, sp, c.s_reads, c.s_contig, 0, c.edge_all);
+  __syncthreads();                                   // all results are in shared memory
+#endif
+  c.rnd_base = pos; c.rnd_cnt = cnt;
   BK_PH_END(c, PH_NW)
+}
+
+// ---- contig.check_align (:449-504), decision part: v1/v2 come from the round -------------------------------
+BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2) {
+  const int lc = c.clen;
   if (lane() == 0) {
     atomic_add(&c.P->stats[0], 1ull);
     atomic_add(&c.P->stats[1], (unsigned long long)lc * (unsigned long long)lr);
@@ -396,7 +461,7 @@ BK_DEV bool check_align(RegionCtx& c, int u, int seed_s, bool grow) {
   const bool io = c.u_io[u] != 0;
   if (s1 == s2) {
     if (lc < lr || v1.j0 == 0) {                                     // :471
-      set_superseq(c, u, lr, v1.i0, v1.prei);
+      set_superseq(c, u, rd, lr, v1.i0, v1.prei);
       if (grow) set_kmers(c);
       return true;
     }
@@ -407,27 +472,38 @@ BK_DEV bool check_align(RegionCtx& c, int u, int seed_s, bool grow) {
     // :485-496 -- alignment strings minus '-' are the aligned spans themselves
     const uint64_t code = c.mer[seed_s];
     const int i11 = find_in_slice(c.s_contig, v1.j0, lc, c.k, code);
-    const int i12 = find_in_slice(c.s_read, v1.i0, v1.prei, c.k, code);
-    const int i21 = find_in_slice(c.s_read, v2.j0, lr, c.k, code);
+    const int i12 = find_in_slice(rd, v1.i0, v1.prei, c.k, code);
+    const int i21 = find_in_slice(rd, v2.j0, lr, c.k, code);
     const int i22 = find_in_slice(c.s_contig, v2.i0, v2.prei, c.k, code);
     const int d1 = i11 > i12 ? i11 - i12 : i12 - i11;
     const int d2 = i21 > i22 ? i21 - i22 : i22 - i21;
     if (i11 > -1 && i12 > -1) {
-      if ((i21 == -1 && i22 == -1) || d2 > d1) { contig_overlap_read(c, v1, u, lr, grow); return true; }
+      if ((i21 == -1 && i22 == -1) || d2 > d1) { contig_overlap_read(c, v1, u, rd, lr, grow); return true; }
     } else if (i21 > -1 && i22 > -1) {
-      if ((i11 == -1 && i12 == -1) || d2 < d1) { read_overlap_contig(c, v2, u, lr, grow); return true; }
+      if ((i11 == -1 && i12 == -1) || d2 < d1) { read_overlap_contig(c, v2, u, rd, lr, grow); return true; }
     }
     return false;
   }
-  if (s1 > s2) contig_overlap_read(c, v1, u, lr, grow);
-  else read_overlap_contig(c, v2, u, lr, grow);
+  if (s1 > s2) contig_overlap_read(c, v1, u, rd, lr, grow);
+  else read_overlap_contig(c, v2, u, rd, lr, grow);
   return true;
 }
 
-// ---- contig.check_read (:552-566, Q30) ---------------------------------------------------------
-BK_DEV bool check_read(RegionCtx& c, int seed_s, int u, bool grow) {
-  if (lane() == 0) c.r_buf[u] = c.serial;                            // self.buffer.add(read.id)
-  const bool match = check_align(c, u, seed_s, grow);
+// ---- contig.check_read (:552-566, Q30) for stream slot `pos` -----------------------------------------------
+// Runs a new speculation round when `pos` is past the reads the last round
+// covered (or the contig sequence changed since).  Returns the match flag.
+BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
+  if (pos >= c.rnd_base + c.rnd_cnt) {
+    int cnt = c.st_n - pos;
+    if (cnt > ASM_SPEC_W) cnt = ASM_SPEC_W;
+    nw_round(c, pos, cnt);
+  }
+  const int w = pos - c.rnd_base;
+  const int u = c.hit_u[pos];
+  const unsigned ver = c.seq_ver;
+  const NwOut v1 = c.sp->v1[w], v2 = c.sp->v2[w];
+  const bool match = apply_align(c, u, seed_s, grow, c.s_reads + (size_t)w * ASM_CAP, c.sp->lr[w], v1, v2);
+  if (c.seq_ver != ver) c.rnd_cnt = w + 1;                            // later results of the round are stale
   if (match) {
     if (lane() == 0) { c.r_used[u] = 1; c.r_inreads[u] = c.serial; }  // committed by the finalize that follows
   } else if (c.cnt[seed_s] > 2 && !c.r_used[u]) {
@@ -502,8 +578,13 @@ BK_DEV void finalize(RegionCtx& c, bool setup) {
 }
 
 // ---- find_reads / read_search (:102-122; Q9, Q10, Q28) -------------------------------------------
-// result in hit_u / hit_pos, sorted by (pos, -len) or (-pos, -len), ties in read order
-BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
+// Appends the matching reads to the stream at [at, at + n), sorted by (pos, -len)
+// or (-pos, -len) with ties in read order.  With filter_buffer the reads already in
+// contig.buffer are skipped and the appended ones join it right away: they are
+// all going to be checked by this contig, in this order, whatever the outcomes
+// (the k-mer snapshot loop of grow has no early exit), so adding them early is
+// unobservable.
+BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at) {
   BK_PH_BEGIN
   const int64_t a = c.P->post_off[c.gm0 + s], b = c.P->post_off[c.gm0 + s + 1];
   const int32_t* pr = c.P->post_read + a;
@@ -526,23 +607,26 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
       // sort key: primary pos (or -pos), secondary -len; both < 4096
       const int len = c.read_len_of(u);
       c.hit2_pos[dst] = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - len);
+      if (filter_buffer) c.r_buf[u] = c.serial;
     }
     n += popc(mk);
   }
   syncwarp();
-  // stable rank sort (lists are short: at most the reads that contain one k-mer)
-  for (int t = 0; t < n; t += WARP) {
-    const int i = t + lane();
-    if (i < n) {
-      const int key = c.hit2_pos[i];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        const int kj = c.hit2_pos[j];
-        rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+  if (n == 1) {
+    if (lane() == 0) c.hit_u[at] = c.hit2_u[0];
+  } else {
+    // stable rank sort (lists are short: at most the reads that contain one k-mer)
+    for (int t = 0; t < n; t += WARP) {
+      const int i = t + lane();
+      if (i < n) {
+        const int key = c.hit2_pos[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const int kj = c.hit2_pos[j];
+          rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+        }
+        c.hit_u[at + rank] = c.hit2_u[i];
       }
-      c.hit_u[rank] = c.hit2_u[i];
-      const int hi = key >> 12;
-      c.hit_pos[rank] = rev ? (ASM_CAP - 1 - hi) : hi;
     }
   }
   syncwarp();
@@ -554,24 +638,23 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev) {
 // ---- setup_contigs (:11-26, Q20) ---------------------------------------------------------------------
 // returns true if the new contig was queued (it is then the FIFO head and is grown next)
 BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
-  const int n = find_reads(c, seed_s, false, false);
+  const int n = find_reads(c, seed_s, false, false, 0);
   if (lane() == 0) c.mused[seed_s] = 1;                              // buff.add_used_mer
   syncwarp();
   if (n == 0) return false;
+  c.st_n = n;
+  c.rnd_base = 0; c.rnd_cnt = 1;                                     // slot 0 is the contig's own read: nothing to align
+  const int u0 = c.hit_u[0];
+  contig_init(c, seed_s, u0);
   bool queued = false;
-  for (int h = 0; h < n && c.status == ST_OK; ++h) {
-    const int u = c.hit_u[h];
-    if (h == 0) {
-      contig_init(c, seed_s, u);
-      // buff.add_contig(read, ct): only if the read is not used yet (Q20)
-      if (!c.r_used[u]) {
-        if (lane() == 0) { c.r_used[u] = 1; }
-        queued = true;
-        syncwarp();
-      }
-    } else {
-      check_read(c, seed_s, u, false);
-    }
+  if (!c.r_used[u0]) {                                               // buff.add_contig(read, ct) (Q20)
+    if (lane() == 0) c.r_used[u0] = 1;
+    queued = true;
+    syncwarp();
+  }
+  for (int h = 1; h < n && c.status == ST_OK; ++h) {
+    if (lane() == 0) c.r_buf[c.hit_u[h]] = c.serial;                 // self.buffer.add(read.id)
+    check_read(c, seed_s, h, false);
   }
   if (c.status == ST_OK) finalize(c, true);
   return queued;
@@ -670,7 +753,7 @@ BK_DEV void grow(RegionCtx& c) {
   if (!c.ct_setup) set_kmers(c);
   const unsigned lt = lane_lt_mask();
   int32_t* Ks = c.K; int32_t* Km = c.K + 2 * ASM_KCAP;
-  int32_t* Ns = c.NK; int32_t* Nm = c.NK + 2 * ASM_KCAP;
+  int32_t* Ns = c.NK; int32_t* Nend = c.NK + ASM_KCAP; int32_t* Nm = c.NK + 2 * ASM_KCAP;
   while (c.status == ST_OK) {
     // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
     int nn = 0;
@@ -686,19 +769,28 @@ BK_DEV void grow(RegionCtx& c) {
     c.nNK = nn;
     syncwarp();
     if (nn == 0) break;
-    for (int e = 0; e < nn && c.status == ST_OK; ++e) {
-      const int s = Ns[e], meta = Nm[e];
+    // The read stream of this snapshot: get_mer_reads (:604-614) for every tuple, in
+    // order.  It does not depend on how the alignments turn out (see find_reads).
+    int st = 0;
+    for (int e = 0; e < nn; ++e) {
+      const int meta = Nm[e];
       const int lth = meta & 1, order = (meta >> 1) & 3;
-      // get_mer_reads (:604-614)
-      bool rev;
-      if (order == ORDER_MID) rev = (lth == 0);
-      else rev = (order == ORDER_FOR);
-      const int n = find_reads(c, s, true, rev);
-      if (lane() == 0) c.mused[s] = 1;
+      const bool rev = (order == ORDER_MID) ? (lth == 0) : (order == ORDER_FOR);
+      st += find_reads(c, Ns[e], true, rev, st);
+      if (lane() == 0) Nend[e] = st;
+    }
+    c.st_n = st;
+    c.rnd_base = 0; c.rnd_cnt = 0;
+    syncwarp();
+    int pos = 0;
+    for (int e = 0; e < nn && c.status == ST_OK; ++e) {
+      const int s = Ns[e];
+      const int end = Nend[e];
+      if (lane() == 0) c.mused[s] = 1;                                 // buff.add_used_mer (:632)
       syncwarp();
-      for (int h = 0; h < n && c.status == ST_OK; ++h) {
-        const int u = c.hit_u[h];
-        if (check_read(c, s, u, true)) {
+      for (; pos < end && c.status == ST_OK; ++pos) {
+        const int u = c.hit_u[pos];
+        if (check_read(c, s, pos, true)) {
           if (c.r_queued[u] == 1) {                                    // buff.remove_contig(read.id) :639
             if (lane() == 0) c.r_queued[u] = 2;
             syncwarp();
@@ -766,7 +858,8 @@ BK_DEV void assemble_region(RegionCtx& c) {
   }
 }
 
-BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_read, uint8_t* s_contig) {
+BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_reads, uint8_t* s_contig,
+                        SpecShared* sp) {
   c.P = &P; c.region = region; c.k = P.k;
   c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
   c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
@@ -784,16 +877,31 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.NK = P.w_NK + slot * 3 * ASM_KCAP;
   c.wcode = P.w_wcode + slot * ASM_CAP;
   c.diff = P.w_diff + slot * (ASM_CAP + 1);
-  c.edge = P.w_edge ? P.w_edge + slot * 2 * ASM_CAP : nullptr;
-  c.s_read = s_read; c.s_contig = s_contig;
+  c.edge_all = P.w_edge ? P.w_edge + slot * ASM_SPEC_W * 2 * ASM_CAP : nullptr;
+  c.edge = c.edge_all;
+  c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
+  c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
 }
 
 #ifndef BK_SIM
-constexpr int ASM_WARPS_PER_CTA = 1;
-__global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA, 8) assemble_kernel(AsmParams P) {
-  __shared__ __align__(16) uint8_t s_read[ASM_CAP];
+// One CTA per region slot: warp 0 runs the state machine and is worker 0 of every
+// speculation round; warps 1..ASM_SPEC_W-1 only align.
+__global__ void __launch_bounds__(32 * ASM_SPEC_W, 3) assemble_kernel(AsmParams P) {
+  __shared__ __align__(16) uint8_t s_reads[ASM_SPEC_W * ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
+  __shared__ SpecShared sp;
   const int64_t slot = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  if (warp > 0) {
+    int2* edge = P.w_edge ? P.w_edge + (slot * ASM_SPEC_W + warp) * 2 * ASM_CAP : nullptr;
+    for (;;) {
+      __syncthreads();
+      const int n = sp.n;
+      if (n < 0) return;
+      if (warp < n) spec_work(P, &sp, s_reads, s_contig, warp, edge);
+      __syncthreads();
+    }
+  }
   RegionCtx c;
   for (;;) {
     int w = 0;
@@ -801,7 +909,7 @@ __global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA, 8) assemble_kernel(Asm
     w = shfl(w, 0);
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
-    bind_region(c, P, region, slot, s_read, s_contig);
+    bind_region(c, P, region, slot, s_reads, s_contig, &sp);
 #if defined(BK_PHASE_PROF)
     for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
     const long long t_reg0 = clock64();
@@ -812,11 +920,14 @@ __global__ void __launch_bounds__(32 * ASM_WARPS_PER_CTA, 8) assemble_kernel(Asm
     if (lane() == 0) {
       for (int i = 0; i < PH_MAXREGION; ++i) atomicAdd(&P.stats[8 + i], (unsigned long long)c.ph_cycles[i]);
       atomicMax(&P.stats[8 + PH_MAXREGION], (unsigned long long)c.ph_cycles[PH_TOTAL]);
+      if (P.prof_regions) for (int i = 0; i < 8; ++i) P.prof_regions[(size_t)region * 8 + i] = (unsigned long long)c.ph_cycles[i];
     }
 #endif
     if (lane() == 0) { P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out; }
     syncwarp();
   }
+  if (lane() == 0) sp.n = -1;                          // dismiss the workers
+  __syncthreads();
 }
 #endif
 

@@ -364,7 +364,9 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.so_off = so_off; A.so_mer = so_mer; A.so_cnt = so_cnt; A.seed_order = seed_order;
   A.post_off = post_off; A.post_read = post_read; A.post_pos = post_pos;
   A.work_order = to_device(h, h->dev, order.data(), (size_t)R);
-  int grid = std::min<int64_t>(R, (int64_t)h->sm_count * 16);
+  int ctas_per_sm = 3;                                         // 3 CTAs of ASM_SPEC_W warps per SM
+  if (const char* e = getenv("BK_ASM_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(e));
+  int grid = std::min<int64_t>(R, (int64_t)h->sm_count * ctas_per_sm);
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
@@ -372,7 +374,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.w_NK = h->dev.get<int32_t>((size_t)grid * 3 * ASM_KCAP);
   A.w_wcode = h->dev.get<uint64_t>((size_t)grid * ASM_CAP);
   A.w_diff = h->dev.get<int32_t>((size_t)grid * (ASM_CAP + 1));
-  A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * 2 * ASM_CAP) : nullptr;
+  A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * ASM_SPEC_W * 2 * ASM_CAP) : nullptr;
   A.region_status = h->dev.get<int32_t>(R ? R : 1);
   A.region_ncontigs = h->dev.get<int32_t>(R ? R : 1);
   // a mutable copy of the liveness flags per attempt, everything else zeroed
@@ -396,6 +398,8 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.hit_u = h->dev.get<int32_t>(NU); A.hit_pos = h->dev.get<int32_t>(NU);
   A.hit2_u = h->dev.get<int32_t>(NU); A.hit2_pos = h->dev.get<int32_t>(NU);
 
+  const bool want_prof = getenv("BK_PHASE_PRINT") != nullptr;
+  A.prof_regions = want_prof ? dev_zero<unsigned long long>(h, (size_t)R * 8 + 8) : nullptr;
   unsigned long long cap_seq = (unsigned long long)std::max<int64_t>(1 << 20, 8 * p.total_read_bytes);
   const unsigned long long* h_cursor = nullptr;
   const unsigned long long* h_stats = nullptr;
@@ -413,7 +417,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     if (S_total) BK_CUDA(cudaMemcpyAsync(alive_run, m_alive, S_total, cudaMemcpyDeviceToDevice, st));
     if (R > 0) {
       TimedLaunch t(h->timers, st, KF_ASSEMBLE);
-      assemble_kernel<<<grid, 32 * ASM_WARPS_PER_CTA, 0, st>>>(A);
+      assemble_kernel<<<grid, 32 * ASM_SPEC_W, 0, st>>>(A);
     }
     BK_CUDA(cudaGetLastError());
     h_cursor = to_host(h, A.out_cursor, 5);
@@ -436,6 +440,19 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "stage", "total", "max_region"};
     for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
     fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu\n", h_stats[2], h_stats[3], h_stats[0]);
+    if (A.prof_regions) {
+      std::vector<unsigned long long> pr((size_t)R * 8);
+      BK_CUDA(cudaMemcpy(pr.data(), A.prof_regions, pr.size() * 8, cudaMemcpyDeviceToHost));
+      std::vector<int> ids(R);
+      std::iota(ids.begin(), ids.end(), 0);
+      std::sort(ids.begin(), ids.end(), [&](int a, int b) { return pr[(size_t)a * 8 + 6] > pr[(size_t)b * 8 + 6]; });
+      for (int t = 0; t < 4 && t < R; ++t) {
+        const unsigned long long* q = &pr[(size_t)ids[t] * 8];
+        fprintf(stderr, "region %d (U=%lld S=%lld): total %llu nw %llu find %llu kmers %llu finalize %llu emit %llu stage %llu\n", ids[t],
+                (long long)(h_u_off[ids[t] + 1] - h_u_off[ids[t]]), (long long)(h_so_off[ids[t] + 1] - h_so_off[ids[t]]), q[6], q[0], q[1],
+                q[2], q[3], q[4], q[5]);
+      }
+    }
   }
   out->so_off = h_so_off;
   out->so_mers = to_host(h, so_mer, (size_t)S_total);

@@ -98,9 +98,11 @@ extern "C" int sim_assemble_region(
   P.region_status = &status; P.region_ncontigs = &ncontigs;
   unsigned long long stats[16] = {0};
   P.stats = stats;
-  std::vector<uint8_t> s_read(ASM_CAP), s_contig(ASM_CAP);
+  std::vector<uint8_t> s_reads((size_t)ASM_SPEC_W * ASM_CAP), s_contig(ASM_CAP);
+  SpecShared sp;
+  memset(&sp, 0, sizeof sp);
   RegionCtx c;
-  bind_region(c, P, 0, 0, s_read.data(), s_contig.data());
+  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), &sp);
   assemble_region(c);
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];

@@ -59,7 +59,7 @@ def decode_contigs(n_ctg, desc, o_seq, o_locs, o_io, o_ot, o_reads, o_mer, o_pos
     return out
 
 
-def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 20):
+def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 23):
     lib = ctypes.CDLL(build(asan))
     uniq = assembler_py.group_reads(records)
     seqs = [u.seq.encode() for u in uniq]
