@@ -150,7 +150,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     desc, per_gpu = WORKLOADS[args.workload]
     n_total = per_gpu * args.gpus
-    per_step = min(cores, n_total)
+    per_step = min(2 * cores, n_total)        # two regions per core per step keeps the pool busy past the stragglers
     budget = float(os.environ.get("BK_REF_BUDGET_S", "170"))
     ctx = mp.get_context("fork")
     t_start = time.time()
@@ -174,7 +174,7 @@ def reference_arm(args):
             if time.time() - t_start > budget and steps_done >= 1:
                 break
     value = timed_regions / timed_s if timed_s > 0 else 0.0
-    sample = ("%d regions per step (one per host core) of %s, %d of %d timed steps completed within the %.0f s budget; "
+    sample = ("%d regions per step (two per host core, dynamic pool) of %s, %d of %d timed steps completed within the %.0f s budget; "
               "oracle port of the reference's CPython path over multiprocessing" %
               (per_step, args.workload, steps_done, args.steps, budget))
     line = {
@@ -302,7 +302,11 @@ def gpu_arm(args):
     sort_gbs = sort_bytes / (sc_ms / max(1, sc_n) * 1e-3) / 1e9 if sc_ms > 0 else 0.0
     cells_per_s = n_cells * args.steps / (asm_ms * 1e-3) if asm_ms > 0 else 0.0
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    int_peak_cells = 148 * 4 * 32 * sm_mhz * 1e6 / 10.0     # 10 integer issue slots per DP cell (nw.cuh), 1 warp-instr/clk/SMSP
+    # INT32 ALU-pipe ceiling of the DP: 8 alu-pipe instructions per cell (nw.cuh), 16 lanes/clk/SMSP (B300_MICROARCH.md)
+    int_peak_cells = 148 * 4 * 16 * sm_mhz * 1e6 / 8.0
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_*.md); only valid for the default workload
+    asm_traffic = 29835008 if (args.workload == "C2" and per_gpu == 500) else None
+    sort_traffic = 501317120 if (args.workload == "C2" and per_gpu == 500) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,7 +319,7 @@ def gpu_arm(args):
         "per_step": {"contigs": n_contigs, "check_align_calls": n_check, "dp_cells": n_cells,
                      "kmer_occurrences": n_occ, "sample_only_kmers": n_only},
         "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": asm_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": asm_gbs / hbm_peak, "traffic": asm_traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": asm_ms_per_launch,
                      "share_of_step": asm_ms / sum(step_ms) if step_ms else None,
                      "note": "the dominant kernel is an integer-issue/latency bound DP state machine that moves "
@@ -323,9 +327,10 @@ def gpu_arm(args):
                              "see roofline_alu and roofline_kstage"},
         "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": int_peak_cells,
                          "unit": "DP cell updates/s", "frac": cells_per_s / int_peak_cells if int_peak_cells else None,
-                         "peak_source": "nominal: 148 SM x 4 SMSP x 32 lanes x sm clock / 10 issue slots per cell"},
+                         "peak_source": "148 SM x 4 SMSP x 16 alu lanes/clk x measured sm clock / 8 alu-pipe instructions per cell; "
+                                        "ncu: pipe_alu 65% busy on active SMs (profiles/r1_assemble_kernel.md)"},
         "roofline_kstage": {"kernel": "rs_scatter_kernel", "bound": "hbm", "achieved": sort_gbs, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": None,
+                            "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": sort_traffic,
                             "algorithmic_bytes_per_launch": sort_bytes, "launches": sc_n},
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in ktimes.items() if v[1]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
