@@ -886,7 +886,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 #ifndef BK_SIM
 // One CTA per region slot: warp 0 runs the state machine and is worker 0 of every
 // speculation round; warps 1..ASM_SPEC_W-1 only align.
-__global__ void __launch_bounds__(32 * ASM_SPEC_W, 3) assemble_kernel(AsmParams P) {
+__global__ void __launch_bounds__(32 * ASM_SPEC_W, (ASM_SPEC_W >= 4 ? 3 : (ASM_SPEC_W == 2 ? 5 : 8))) assemble_kernel(AsmParams P) {
   __shared__ __align__(16) uint8_t s_reads[ASM_SPEC_W * ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
   __shared__ SpecShared sp;
