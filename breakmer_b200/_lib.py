@@ -90,9 +90,10 @@ def load():
     lib.bk_kernel_times.argtypes = [H, POINTER(c_char_p), POINTER(POINTER(c_double)), POINTER(POINTER(c_int64)),
                                     POINTER(c_int32)]
     lib.bk_kernel_times_reset.argtypes = [H, c_int]
+    lib.bk_set_option.argtypes = [H, c_char_p, c_int64]
     for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_count_kmers", "bk_sample_only",
                  "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
-                 "bk_kernel_times_reset"):
+                 "bk_kernel_times_reset", "bk_set_option"):
         getattr(lib, name).restype = c_int
     _lib = lib
     return lib
@@ -101,7 +102,7 @@ def load():
 EXPORTED_SYMBOLS = (
     "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_count_kmers",
     "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
-    "bk_kernel_times_reset")
+    "bk_kernel_times_reset", "bk_set_option")
 
 
 def _ptr(a):
@@ -193,6 +194,9 @@ class Handle:
         if n.value == 0:
             return np.zeros(0, np.uint64), np.zeros(0, np.uint32)
         return (np.ctypeslib.as_array(pm, shape=(n.value,)).copy(), np.ctypeslib.as_array(pc, shape=(n.value,)).copy())
+
+    def set_option(self, name, value):
+        self._check(self.lib.bk_set_option(self.h, name.encode(), int(value)))
 
     # ---- timers -------------------------------------------------------------------------
     def kernel_times_reset(self, enable=True):

@@ -168,6 +168,7 @@ struct RegionCtx {
   int st_n;
   int rnd_base, rnd_cnt;          // stream range the last round covers
   unsigned seq_ver;               // bumped whenever the contig SEQUENCE changes
+  int spec_w;                     // speculation width of this launch (1..ASM_SPEC_W)
   SpecShared* sp;
   uint8_t* s_reads;               // ASM_SPEC_W staging buffers of ASM_CAP bytes; [0] doubles as s_read
   int2* edge_all;                 // ASM_SPEC_W x (2 * ASM_CAP) int2 or null
@@ -435,9 +436,9 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
 #ifdef BK_SIM
   for (int w = 0; w < cnt; ++w) spec_work(*c.P, sp, c.s_reads, c.s_contig, w, nullptr);
 #else
-  __syncthreads();                                   // release the worker warps
+  if (c.spec_w > 1) __syncthreads();                 // release the worker warps
   spec_work(*c.P, sp, c.s_reads, c.s_contig, 0, c.edge_all);
-  __syncthreads();                                   // all results are in shared memory
+  if (c.spec_w > 1) __syncthreads();                 // all results are in shared memory
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
   BK_PH_END(c, PH_NW)
@@ -495,7 +496,7 @@ BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_
 BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
   if (pos >= c.rnd_base + c.rnd_cnt) {
     int cnt = c.st_n - pos;
-    if (cnt > ASM_SPEC_W) cnt = ASM_SPEC_W;
+    if (cnt > c.spec_w) cnt = c.spec_w;
     nw_round(c, pos, cnt);
   }
   const int w = pos - c.rnd_base;
@@ -859,7 +860,8 @@ BK_DEV void assemble_region(RegionCtx& c) {
 }
 
 BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_reads, uint8_t* s_contig,
-                        SpecShared* sp) {
+                        SpecShared* sp, int spec_w) {
+  c.spec_w = spec_w;
   c.P = &P; c.region = region; c.k = P.k;
   c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
   c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
@@ -877,23 +879,29 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.NK = P.w_NK + slot * 3 * ASM_KCAP;
   c.wcode = P.w_wcode + slot * ASM_CAP;
   c.diff = P.w_diff + slot * (ASM_CAP + 1);
-  c.edge_all = P.w_edge ? P.w_edge + slot * ASM_SPEC_W * 2 * ASM_CAP : nullptr;
+  c.edge_all = P.w_edge ? P.w_edge + slot * spec_w * 2 * ASM_CAP : nullptr;
   c.edge = c.edge_all;
   c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
   c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
 }
 
 #ifndef BK_SIM
-// One CTA per region slot: warp 0 runs the state machine and is worker 0 of every
-// speculation round; warps 1..ASM_SPEC_W-1 only align.
-__global__ void __launch_bounds__(32 * ASM_SPEC_W, (ASM_SPEC_W >= 4 ? 3 : (ASM_SPEC_W == 2 ? 5 : 8))) assemble_kernel(AsmParams P) {
-  __shared__ __align__(16) uint8_t s_reads[ASM_SPEC_W * ASM_CAP];
+// One CTA of W warps per region slot: warp 0 runs the state machine and is worker 0 of
+// every speculation round; warps 1..W-1 only align.  W = 4 minimises the latency of a
+// region (used when a batch runs alone on the device), W = 1 spends no work on
+// speculation and packs more regions per SM (used when several batches are in flight).
+// `pad_smem` bytes of dynamic shared memory do nothing but bound the CTAs resident per
+// SM, so that the short k-mer stage kernels of other in-flight batches can still get
+// registers while long assemblies occupy the machine.
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assemble_kernel(AsmParams P) {
+  __shared__ __align__(16) uint8_t s_reads[W * ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
   __shared__ SpecShared sp;
   const int64_t slot = blockIdx.x;
   const int warp = threadIdx.x >> 5;
-  if (warp > 0) {
-    int2* edge = P.w_edge ? P.w_edge + (slot * ASM_SPEC_W + warp) * 2 * ASM_CAP : nullptr;
+  if (W > 1 && warp > 0) {
+    int2* edge = P.w_edge ? P.w_edge + (slot * W + warp) * 2 * ASM_CAP : nullptr;
     for (;;) {
       __syncthreads();
       const int n = sp.n;
@@ -909,10 +917,12 @@ __global__ void __launch_bounds__(32 * ASM_SPEC_W, (ASM_SPEC_W >= 4 ? 3 : (ASM_S
     w = shfl(w, 0);
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
-    bind_region(c, P, region, slot, s_reads, s_contig, &sp);
+    bind_region(c, P, region, slot, s_reads, s_contig, &sp, W);
 #if defined(BK_PHASE_PROF)
     for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
     const long long t_reg0 = clock64();
+    unsigned long long gt0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
 #endif
     assemble_region(c);
 #if defined(BK_PHASE_PROF)
@@ -920,14 +930,23 @@ __global__ void __launch_bounds__(32 * ASM_SPEC_W, (ASM_SPEC_W >= 4 ? 3 : (ASM_S
     if (lane() == 0) {
       for (int i = 0; i < PH_MAXREGION; ++i) atomicAdd(&P.stats[8 + i], (unsigned long long)c.ph_cycles[i]);
       atomicMax(&P.stats[8 + PH_MAXREGION], (unsigned long long)c.ph_cycles[PH_TOTAL]);
-      if (P.prof_regions) for (int i = 0; i < 8; ++i) P.prof_regions[(size_t)region * 8 + i] = (unsigned long long)c.ph_cycles[i];
+      if (P.prof_regions) {
+        for (int i = 0; i < 8; ++i) P.prof_regions[(size_t)region * 12 + i] = (unsigned long long)c.ph_cycles[i];
+        unsigned long long gt1; unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt1));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        P.prof_regions[(size_t)region * 12 + 8] = gt0; P.prof_regions[(size_t)region * 12 + 9] = gt1;
+        P.prof_regions[(size_t)region * 12 + 10] = smid;
+      }
     }
 #endif
     if (lane() == 0) { P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out; }
     syncwarp();
   }
-  if (lane() == 0) sp.n = -1;                          // dismiss the workers
-  __syncthreads();
+  if (W > 1) {
+    if (lane() == 0) sp.n = -1;                        // dismiss the workers
+    __syncthreads();
+  }
 }
 #endif
 

@@ -364,9 +364,17 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.so_off = so_off; A.so_mer = so_mer; A.so_cnt = so_cnt; A.seed_order = seed_order;
   A.post_off = post_off; A.post_read = post_read; A.post_pos = post_pos;
   A.work_order = to_device(h, h->dev, order.data(), (size_t)R);
-  int ctas_per_sm = 3;                                         // 3 CTAs of ASM_SPEC_W warps per SM
+  // speculation width and residency of the assembler (see assemble_kernel)
+  int spec_w = h->spec_width;
+  if (const char* e = getenv("BK_SPEC_W")) spec_w = atoi(e);
+  spec_w = spec_w >= 4 ? 4 : (spec_w >= 2 ? 2 : 1);
+  int ctas_per_sm = spec_w == 4 ? 2 : (spec_w == 2 ? 4 : 6);
   if (const char* e = getenv("BK_ASM_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(e));
   int grid = std::min<int64_t>(R, (int64_t)h->sm_count * ctas_per_sm);
+  // static shared memory of the kernel + padding = 1/ctas_per_sm of the SM's shared memory
+  const int static_smem = spec_w * ASM_CAP + ASM_CAP + 256;
+  int pad_smem = (int)((227 * 1024) / ctas_per_sm) - static_smem - 1024;
+  if (pad_smem < 0) pad_smem = 0;
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
@@ -374,7 +382,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.w_NK = h->dev.get<int32_t>((size_t)grid * 3 * ASM_KCAP);
   A.w_wcode = h->dev.get<uint64_t>((size_t)grid * ASM_CAP);
   A.w_diff = h->dev.get<int32_t>((size_t)grid * (ASM_CAP + 1));
-  A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * ASM_SPEC_W * 2 * ASM_CAP) : nullptr;
+  A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * spec_w * 2 * ASM_CAP) : nullptr;
   A.region_status = h->dev.get<int32_t>(R ? R : 1);
   A.region_ncontigs = h->dev.get<int32_t>(R ? R : 1);
   // a mutable copy of the liveness flags per attempt, everything else zeroed
@@ -399,7 +407,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.hit2_u = h->dev.get<int32_t>(NU); A.hit2_pos = h->dev.get<int32_t>(NU);
 
   const bool want_prof = getenv("BK_PHASE_PRINT") != nullptr;
-  A.prof_regions = want_prof ? dev_zero<unsigned long long>(h, (size_t)R * 8 + 8) : nullptr;
+  A.prof_regions = want_prof ? dev_zero<unsigned long long>(h, (size_t)R * 12 + 12) : nullptr;
   unsigned long long cap_seq = (unsigned long long)std::max<int64_t>(1 << 20, 8 * p.total_read_bytes);
   const unsigned long long* h_cursor = nullptr;
   const unsigned long long* h_stats = nullptr;
@@ -417,7 +425,16 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     if (S_total) BK_CUDA(cudaMemcpyAsync(alive_run, m_alive, S_total, cudaMemcpyDeviceToDevice, st));
     if (R > 0) {
       TimedLaunch t(h->timers, st, KF_ASSEMBLE);
-      assemble_kernel<<<grid, 32 * ASM_SPEC_W, 0, st>>>(A);
+      if (spec_w == 4) {
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
+        assemble_kernel<4><<<grid, 128, pad_smem, st>>>(A);
+      } else if (spec_w == 2) {
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
+        assemble_kernel<2><<<grid, 64, pad_smem, st>>>(A);
+      } else {
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
+        assemble_kernel<1><<<grid, 32, pad_smem, st>>>(A);
+      }
     }
     BK_CUDA(cudaGetLastError());
     h_cursor = to_host(h, A.out_cursor, 5);
@@ -441,13 +458,41 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
     fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu\n", h_stats[2], h_stats[3], h_stats[0]);
     if (A.prof_regions) {
-      std::vector<unsigned long long> pr((size_t)R * 8);
+      std::vector<unsigned long long> pr((size_t)R * 12);
       BK_CUDA(cudaMemcpy(pr.data(), A.prof_regions, pr.size() * 8, cudaMemcpyDeviceToHost));
       std::vector<int> ids(R);
       std::iota(ids.begin(), ids.end(), 0);
-      std::sort(ids.begin(), ids.end(), [&](int a, int b) { return pr[(size_t)a * 8 + 6] > pr[(size_t)b * 8 + 6]; });
+      std::sort(ids.begin(), ids.end(), [&](int a, int b) { return pr[(size_t)a * 12 + 6] > pr[(size_t)b * 12 + 6]; });
+      {
+        unsigned long long t0 = ~0ull, t1 = 0, sum = 0;
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long a = pr[(size_t)r * 12 + 8], b = pr[(size_t)r * 12 + 9];
+          if (a < t0) t0 = a;
+          if (b > t1) t1 = b;
+          sum += b - a;
+        }
+        fprintf(stderr, "TIMELINE handle %p regions_start_ns %llu end_ns %llu span_ms %.3f sum_region_ms %.3f avg_concurrency %.1f\n", (void*)h,
+                t0, t1, (t1 - t0) / 1e6, sum / 1e6, (double)sum / (double)(t1 - t0 + 1));
+        if (getenv("BK_REGION_DUMP")) {
+          FILE* f = fopen(getenv("BK_REGION_DUMP"), "w");
+          if (f) {
+            for (int r = 0; r < R; ++r)
+              fprintf(f, "%d %lld %lld %llu %llu %llu\n", r, (long long)(h_u_off[r + 1] - h_u_off[r]), (long long)(h_so_off[r + 1] - h_so_off[r]),
+                      pr[(size_t)r * 12 + 6], pr[(size_t)r * 12 + 0], pr[(size_t)r * 12 + 8] - t0);
+            fclose(f);
+          }
+        }
+        if (getenv("BK_TIMELINE_DUMP")) {
+          FILE* f = fopen(getenv("BK_TIMELINE_DUMP"), "a");
+          if (f) {
+            for (int r = 0; r < R; ++r)
+              fprintf(f, "%p %d %llu %llu %llu\n", (void*)h, r, pr[(size_t)r * 12 + 8], pr[(size_t)r * 12 + 9], pr[(size_t)r * 12 + 10]);
+            fclose(f);
+          }
+        }
+      }
       for (int t = 0; t < 4 && t < R; ++t) {
-        const unsigned long long* q = &pr[(size_t)ids[t] * 8];
+        const unsigned long long* q = &pr[(size_t)ids[t] * 12];
         fprintf(stderr, "region %d (U=%lld S=%lld): total %llu nw %llu find %llu kmers %llu finalize %llu emit %llu stage %llu\n", ids[t],
                 (long long)(h_u_off[ids[t] + 1] - h_u_off[ids[t]]), (long long)(h_so_off[ids[t] + 1] - h_so_off[ids[t]]), q[6], q[0], q[1],
                 q[2], q[3], q[4], q[5]);

@@ -20,7 +20,7 @@ extern "C" int sim_assemble_region(
     const uint8_t* rbases, const int64_t* roff, int n_reads, const uint32_t* mult, const uint8_t* io,
     const uint64_t* mers, const uint32_t* counts, int n_mers, int k, int rc_thresh, int read_len,
     // outputs (caller allocated, capacities given)
-    int64_t cap, uint8_t* o_seq, int32_t* o_locs, int32_t* o_io, int32_t* o_ot, int32_t* o_reads,
+    int spec_w, int64_t cap, uint8_t* o_seq, int32_t* o_locs, int32_t* o_io, int32_t* o_ot, int32_t* o_reads,
     uint64_t* o_kmer_mer, int32_t* o_kmer_pos, int32_t* o_kmer_meta, int64_t* o_desc, int64_t* n_contigs,
     uint64_t* stats_out) {
   AsmParams P;
@@ -102,7 +102,7 @@ extern "C" int sim_assemble_region(
   SpecShared sp;
   memset(&sp, 0, sizeof sp);
   RegionCtx c;
-  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), &sp);
+  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), &sp, spec_w);
   assemble_region(c);
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];

@@ -59,7 +59,7 @@ def decode_contigs(n_ctg, desc, o_seq, o_locs, o_io, o_ot, o_reads, o_mer, o_pos
     return out
 
 
-def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 23):
+def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 23, spec_w=4):
     lib = ctypes.CDLL(build(asan))
     uniq = assembler_py.group_reads(records)
     seqs = [u.seq.encode() for u in uniq]
@@ -82,7 +82,7 @@ def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 <
     lib.sim_assemble_region.restype = ctypes.c_int
     rc = lib.sim_assemble_region(p(rb), p(roff), ctypes.c_int(len(uniq)), p(mult), p(io), p(mc), p(cc),
                                  ctypes.c_int(len(items)), ctypes.c_int(k), ctypes.c_int(rc_thresh), ctypes.c_int(read_len),
-                                 ctypes.c_int64(cap // 10), p(o_seq), p(o_locs), p(o_io), p(o_ot), p(o_reads),
+                                 ctypes.c_int(spec_w), ctypes.c_int64(cap // 10), p(o_seq), p(o_locs), p(o_io), p(o_ot), p(o_reads),
                                  p(o_mer), p(o_pos), p(o_meta), p(desc), ctypes.byref(n_ctg), p(stats))
     if rc != 0:
         raise RuntimeError("sim status %d" % rc)
