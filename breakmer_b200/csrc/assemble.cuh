@@ -30,20 +30,26 @@ constexpr int ASM_KCAP = 2 * ASM_CAP;  // contig k-mer tuple list capacity
 constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 
 // Speculation width: the next ASM_SPEC_W reads of a contig's read stream are aligned
-// against the current contig concurrently, one warp each (the CTA has ASM_SPEC_W
-// warps per region; warp 0 also runs the state machine).  Results are committed
-// in stream order and discarded from the first read that changes the contig
-// sequence, so the outcome is identical to checking the reads one by one.
+// concurrently, one warp each (the CTA has up to ASM_SPEC_W warps per region; warp 0
+// also runs the state machine).  Slot 0 aligns against the current contig; slot w > 0
+// aligns against a PREDICTED contig -- the current one with the predicted effects of
+// slots 0..w-1 applied (gapless overlap at the shared k-mer: prepend / append /
+// replace / no change).  Results are committed in stream order, and a slot's result
+// is used only if the actual contig at that moment is byte-identical to the contig
+// the slot was aligned against; otherwise a new round starts there.  The outcome is
+// therefore identical to checking the reads one by one (the prediction is a hint).
 #ifndef ASM_SPEC_W
 #define ASM_SPEC_W 4
 #endif
 
 struct SpecShared {               // command + results of one speculation round (shared memory)
   int n;                          // reads in this round, -1 = workers exit
-  int lc;                         // contig length
   int region;
   int u[ASM_SPEC_W];              // local unique-read indices
-  int lr[ASM_SPEC_W];
+  int lr[ASM_SPEC_W];             // their lengths
+  int abuf[ASM_SPEC_W];           // which contig buffer slot w aligns against: 0 = the current contig,
+                                  // b > 0 = predicted contig buffer b - 1
+  int la[ASM_SPEC_W];             // length of that contig
   NwOut v1[ASM_SPEC_W];           // nw(contig, read)
   NwOut v2[ASM_SPEC_W];           // nw(read, contig)
 };
@@ -97,8 +103,8 @@ struct AsmParams {
   // per-warp scratch, slot = global warp index
   uint8_t* w_cseq;                 // ASM_BUF bytes
   int32_t* w_cnt;                  // 4 * ASM_BUF ints: io[2], ot[2]
-  int32_t* w_K;                    // 3 * ASM_KCAP ints: s, x, meta
-  int32_t* w_NK;                   // 3 * ASM_KCAP
+  int32_t* w_K;                    // 4 * ASM_KCAP ints: s, x, meta, buffer coordinate of the window
+  int32_t* w_NK;                   // 4 * ASM_KCAP ints: s, stream end, meta, buffer coordinate
   uint64_t* w_wcode;               // ASM_CAP
   int32_t* w_diff;                 // ASM_CAP + 1
   int2* w_edge;                    // 2 * ASM_CAP int2, or null if no read is longer than 256
@@ -168,9 +174,14 @@ struct RegionCtx {
   int st_n;
   int rnd_base, rnd_cnt;          // stream range the last round covers
   unsigned seq_ver;               // bumped whenever the contig SEQUENCE changes
+  unsigned rnd_ver;               // seq_ver when the last round started
   int spec_w;                     // speculation width of this launch (1..ASM_SPEC_W)
   SpecShared* sp;
   uint8_t* s_reads;               // ASM_SPEC_W staging buffers of ASM_CAP bytes; [0] doubles as s_read
+  uint8_t* s_pred;                // ASM_SPEC_W - 1 predicted-contig buffers of ASM_CAP bytes
+  int round_seed;                 // >= 0: every slot of the stream belongs to this mer (setup); -1: look up the entry
+  int seed_anchor;                // setup: gap-buffer coordinate of the seed mer in the contig
+  int cur_e;                      // grow: entry of the snapshot being committed
   int2* edge_all;                 // ASM_SPEC_W x (2 * ASM_CAP) int2 or null
   // contig under construction
   uint8_t* cseq; int c0, clen;
@@ -235,7 +246,7 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
   BK_PH_BEGIN
   const int m = nlen / 2;
   const unsigned lt = lane_lt_mask();
-  int32_t* Ks = c.K; int32_t* Kx = c.K + ASM_KCAP; int32_t* Km = c.K + 2 * ASM_KCAP;
+  int32_t* Ks = c.K; int32_t* Kx = c.K + ASM_KCAP; int32_t* Km = c.K + 2 * ASM_KCAP; int32_t* Kb = c.K + 3 * ASM_KCAP;
   // pass 0: ascending x over [lo0, hi0) ; pass 1: descending x over [lo1, hi1)
   int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
   if (order == ORDER_FOR) { lo0 = 0; hi0 = nwin; }
@@ -261,6 +272,7 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
           Ks[dst] = s; Kx[dst] = x;
           const int lth = x < m ? 1 : 0, dist = x < m ? m - x : x - m;
           Km[dst] = lth | (order << 1) | (dist << 3);
+          Kb[dst] = c.c0 + base + x;         // where the window sits in the gap buffer (stable under prepend/append)
         }
       }
       c.nK += popc(mk);
@@ -404,23 +416,93 @@ BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, const uint
 
 // ---- the two olc.nw calls of check_align (:451-452), one warp per read ------------------------------
 // Executed by every warp of the CTA (warp w takes stream slot w of the round).
-BK_DEV void spec_work(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, const uint8_t* s_contig, int w, int2* edge) {
+BK_DEV void spec_stage(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, int w) {
   const int64_t gu0 = P.u_off[sp->region];
-  const int u = sp->u[w];
-  const int rec = P.u_rec[gu0 + u];
+  const int rec = P.u_rec[gu0 + sp->u[w]];
   const int64_t a = P.roff[rec];
   const int lr = (int)(P.roff[rec + 1] - a);
   uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
   const uint8_t* src = P.rbases + a;
   for (int x = lane(); x < lr; x += WARP) rd[x] = src[x];
+  if (lane() == 0) sp->lr[w] = lr;
   syncwarp();
+}
+BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_contig, const uint8_t* s_pred, int w, int2* edge) {
+  const uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
+  const int lr = sp->lr[w];
+  const int b = sp->abuf[w];
+  const uint8_t* ct = b == 0 ? s_contig : s_pred + (size_t)(b - 1) * ASM_CAP;
+  const int lc = sp->la[w];
   NwDual r;
-  const int lc = sp->lc;
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  if (lr <= 128) nw_dual_warp_fast<4>(rd, lr, s_contig, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
-  else nw_dual_warp_fast<8>(rd, lr, s_contig, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
-  if (lane() == 0) { sp->lr[w] = lr; sp->v1[w] = r.b; sp->v2[w] = r.a; }
+  if (lr <= 128) nw_dual_warp_fast<4>(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  else nw_dual_warp_fast<8>(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  if (lane() == 0) { sp->v1[w] = r.b; sp->v2[w] = r.a; }
   syncwarp();
+}
+
+
+// mer (local index) that stream slot `pos` belongs to, and where that mer sits in the
+// contig's gap buffer (a hint for the predictor; may be stale after a replacement)
+BK_DEV int slot_mer(const RegionCtx& c, int pos, int* anchor_buf) {
+  if (c.round_seed >= 0) { *anchor_buf = c.seed_anchor; return c.round_seed; }
+  const int32_t* Ns = c.NK; const int32_t* Nend = c.NK + ASM_KCAP; const int32_t* Nb = c.NK + 3 * ASM_KCAP;
+  int e = c.cur_e;
+  while (pos >= Nend[e]) ++e;
+  *anchor_buf = Nb[e];
+  return Ns[e];
+}
+
+// Predicted contig after read slot w-1 is committed against contig buffer (src, la):
+// gapless overlap anchored at the shared k-mer.  Writes the prediction to dst (if it
+// differs) and returns its length; *same is set when the prediction is "unchanged".
+BK_DEV int predict_contig(const RegionCtx& c, const uint8_t* src, int la, const uint8_t* rd, int lr, int pos_r, int mer_s,
+                          int xc_hint, uint8_t* dst, bool* same, int* shift) {
+  *same = true;
+  const int k = c.k;
+  if (pos_r < 0 || pos_r + k > lr) return la;
+  // anchor: the hinted position if the k-mer really is there, else the first occurrence
+  int xc = xc_hint;
+  bool ok = xc >= 0 && xc + k <= la;
+  if (ok) {
+    bool diff = false;
+    for (int t = lane(); t < k; t += WARP) diff = diff || (src[xc + t] != rd[pos_r + t]);
+    ok = ballot(diff) == 0u;
+  }
+  if (!ok) xc = find_in_slice(src, 0, la, k, c.mer[mer_s]);
+  if (xc < 0) return la;
+  const int oL = pos_r - xc, oR = (lr - pos_r) - (la - xc);
+  const int r0 = oL > 0 ? oL : 0, r1 = lr - (oR > 0 ? oR : 0), c0 = oL < 0 ? -oL : 0;
+  const int ov = r1 - r0;
+  if (ov <= 0) return la;
+  int mm = 0;
+  for (int t = lane(); t < ov; t += WARP) mm += (rd[r0 + t] != src[c0 + t]) ? 1 : 0;
+#ifndef BK_SIM
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+#endif
+  const int sc = ov - 3 * mm;
+  const int mn = la < lr ? la : lr;
+  if (200 * sc < 179 * ov || 4 * sc < mn) return la;            // predicted: no match
+  if (oL <= 0 && oR <= 0) return la;                            // contained: only the counts change
+  int nl;
+  if (oL > 0 && oR > 0) {                                       // the read replaces the contig
+    nl = lr;
+    for (int x = lane(); x < lr; x += WARP) dst[x] = rd[x];
+    *shift = 0x40000000;                                        // coordinates of the old contig are void
+  } else if (oL > 0) {                                          // prepend read[0:oL]
+    nl = la + oL;
+    if (nl > NW_MAX_LEN) return la;
+    for (int x = lane(); x < nl; x += WARP) dst[x] = x < oL ? rd[x] : src[x - oL];
+    *shift += oL;
+  } else {                                                      // append read[lr-oR:]
+    nl = la + oR;
+    if (nl > NW_MAX_LEN) return la;
+    for (int x = lane(); x < nl; x += WARP) dst[x] = x < la ? src[x] : rd[lr - oR + (x - la)];
+  }
+  *same = false;
+  syncwarp();
+  return nl;
 }
 
 // one speculation round over stream slots [pos, pos + cnt)
@@ -429,16 +511,48 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
   SpecShared* sp = c.sp;
   syncwarp();
   if (lane() == 0) {
-    sp->n = cnt; sp->lc = c.clen; sp->region = c.region;
+    sp->n = cnt; sp->region = c.region;
     for (int w = 0; w < cnt; ++w) sp->u[w] = c.hit_u[pos + w];
   }
   syncwarp();
+  const bool multi = c.spec_w > 1;
+  // 1. every warp stages its read
 #ifdef BK_SIM
-  for (int w = 0; w < cnt; ++w) spec_work(*c.P, sp, c.s_reads, c.s_contig, w, nullptr);
+  for (int w = 0; w < cnt; ++w) spec_stage(*c.P, sp, c.s_reads, w);
 #else
-  if (c.spec_w > 1) __syncthreads();                 // release the worker warps
-  spec_work(*c.P, sp, c.s_reads, c.s_contig, 0, c.edge_all);
-  if (c.spec_w > 1) __syncthreads();                 // all results are in shared memory
+  if (multi) __syncthreads();
+  spec_stage(*c.P, sp, c.s_reads, 0);
+  if (multi) __syncthreads();
+#endif
+  // 2. warp 0 predicts the contig each later slot will see
+  if (lane() == 0) { atomic_add(&c.P->stats[4], 1ull); atomic_add(&c.P->stats[5], (unsigned long long)cnt); }
+  {
+    BK_PH_BEGIN
+    int buf = 0, la = c.clen;                                    // buffer 0 = the current contig
+    const uint8_t* src = c.s_contig;
+    if (lane() == 0) { sp->abuf[0] = 0; sp->la[0] = la; }
+    int shift = 0;                                               // bases the predictions have prepended so far
+    for (int w = 1; w < cnt; ++w) {
+      uint8_t* dst = c.s_pred + (size_t)(w - 1) * ASM_CAP;
+      bool same;
+      int anchor_buf;
+      const int mer_s = slot_mer(c, pos + w - 1, &anchor_buf);
+      const int hint = shift >= 0x40000000 ? -1 : anchor_buf - c.c0 + shift;
+      const int nl = predict_contig(c, src, la, c.s_reads + (size_t)(w - 1) * ASM_CAP, sp->lr[w - 1], c.hit_pos[pos + w - 1],
+                                    mer_s, hint, dst, &same, &shift);
+      if (!same) { buf = w; la = nl; src = dst; }
+      if (lane() == 0) { sp->abuf[w] = buf; sp->la[w] = la; }
+    }
+    syncwarp();
+    BK_PH_END(c, PH_STAGE)
+  }
+  // 3. every warp aligns its read against its contig
+#ifdef BK_SIM
+  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, w, nullptr);
+#else
+  if (multi) __syncthreads();
+  spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, 0, c.edge_all);
+  if (multi) __syncthreads();
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
   BK_PH_END(c, PH_NW)
@@ -491,20 +605,32 @@ BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_
 }
 
 // ---- contig.check_read (:552-566, Q30) for stream slot `pos` -----------------------------------------------
-// Runs a new speculation round when `pos` is past the reads the last round
-// covered (or the contig sequence changed since).  Returns the match flag.
+// Uses the slot's result from the last round if the contig it was aligned against
+// is byte-identical to the contig now; otherwise runs a new round starting here.
+BK_DEV bool round_slot_valid(const RegionCtx& c, int w) {
+  const SpecShared* sp = c.sp;
+  const int b = sp->abuf[w];
+  if (sp->la[w] != c.clen) return false;
+  if (b == 0) return c.seq_ver == c.rnd_ver;                          // aligned against the contig of the round start
+  const uint8_t* pr = c.s_pred + (size_t)(b - 1) * ASM_CAP;
+  bool diff = false;
+  for (int x = lane(); x < c.clen; x += WARP) diff = diff || (pr[x] != c.s_contig[x]);
+  return ballot(diff) == 0u;
+}
+
 BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
-  if (pos >= c.rnd_base + c.rnd_cnt) {
+  bool have = pos < c.rnd_base + c.rnd_cnt;
+  if (have) have = round_slot_valid(c, pos - c.rnd_base);
+  if (!have) {
     int cnt = c.st_n - pos;
     if (cnt > c.spec_w) cnt = c.spec_w;
+    c.rnd_ver = c.seq_ver;
     nw_round(c, pos, cnt);
   }
   const int w = pos - c.rnd_base;
   const int u = c.hit_u[pos];
-  const unsigned ver = c.seq_ver;
   const NwOut v1 = c.sp->v1[w], v2 = c.sp->v2[w];
   const bool match = apply_align(c, u, seed_s, grow, c.s_reads + (size_t)w * ASM_CAP, c.sp->lr[w], v1, v2);
-  if (c.seq_ver != ver) c.rnd_cnt = w + 1;                            // later results of the round are stale
   if (match) {
     if (lane() == 0) { c.r_used[u] = 1; c.r_inreads[u] = c.serial; }  // committed by the finalize that follows
   } else if (c.cnt[seed_s] > 2 && !c.r_used[u]) {
@@ -614,7 +740,11 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
   }
   syncwarp();
   if (n == 1) {
-    if (lane() == 0) c.hit_u[at] = c.hit2_u[0];
+    if (lane() == 0) {
+      c.hit_u[at] = c.hit2_u[0];
+      const int hi = c.hit2_pos[0] >> 12;
+      c.hit_pos[at] = rev ? (ASM_CAP - 1 - hi) : hi;
+    }
   } else {
     // stable rank sort (lists are short: at most the reads that contain one k-mer)
     for (int t = 0; t < n; t += WARP) {
@@ -627,6 +757,8 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
           rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
         }
         c.hit_u[at + rank] = c.hit2_u[i];
+        const int hi = key >> 12;
+        c.hit_pos[at + rank] = rev ? (ASM_CAP - 1 - hi) : hi;
       }
     }
   }
@@ -644,6 +776,8 @@ BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
   syncwarp();
   if (n == 0) return false;
   c.st_n = n;
+  c.round_seed = seed_s;
+  c.seed_anchor = ASM_CAP + c.hit_pos[0];                            // contig_init puts the first read at ASM_CAP
   c.rnd_base = 0; c.rnd_cnt = 1;                                     // slot 0 is the contig's own read: nothing to align
   const int u0 = c.hit_u[0];
   contig_init(c, seed_s, u0);
@@ -753,18 +887,18 @@ BK_DEV void emit_contig(RegionCtx& c) {
 BK_DEV void grow(RegionCtx& c) {
   if (!c.ct_setup) set_kmers(c);
   const unsigned lt = lane_lt_mask();
-  int32_t* Ks = c.K; int32_t* Km = c.K + 2 * ASM_KCAP;
-  int32_t* Ns = c.NK; int32_t* Nend = c.NK + ASM_KCAP; int32_t* Nm = c.NK + 2 * ASM_KCAP;
+  int32_t* Ks = c.K; int32_t* Km = c.K + 2 * ASM_KCAP; int32_t* Kb = c.K + 3 * ASM_KCAP;
+  int32_t* Ns = c.NK; int32_t* Nend = c.NK + ASM_KCAP; int32_t* Nm = c.NK + 2 * ASM_KCAP; int32_t* Nb = c.NK + 3 * ASM_KCAP;
   while (c.status == ST_OK) {
     // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
     int nn = 0;
     for (int t = 0; t < c.nK; t += WARP) {
       const int e = t + lane();
       bool keep = false;
-      int s = 0, meta = 0;
-      if (e < c.nK) { s = Ks[e]; meta = Km[e]; keep = c.checked[s] != c.serial; }
+      int s = 0, meta = 0, xb = 0;
+      if (e < c.nK) { s = Ks[e]; meta = Km[e]; xb = Kb[e]; keep = c.checked[s] != c.serial; }
       const unsigned mk = ballot(keep);
-      if (keep) { const int dst = nn + popc(mk & lt); Ns[dst] = s; Nm[dst] = meta; }
+      if (keep) { const int dst = nn + popc(mk & lt); Ns[dst] = s; Nm[dst] = meta; Nb[dst] = xb; }
       nn += popc(mk);
     }
     c.nNK = nn;
@@ -781,10 +915,12 @@ BK_DEV void grow(RegionCtx& c) {
       if (lane() == 0) Nend[e] = st;
     }
     c.st_n = st;
+    c.round_seed = -1;
     c.rnd_base = 0; c.rnd_cnt = 0;
     syncwarp();
     int pos = 0;
     for (int e = 0; e < nn && c.status == ST_OK; ++e) {
+      c.cur_e = e;
       const int s = Ns[e];
       const int end = Nend[e];
       if (lane() == 0) c.mused[s] = 1;                                 // buff.add_used_mer (:632)
@@ -860,8 +996,8 @@ BK_DEV void assemble_region(RegionCtx& c) {
 }
 
 BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_reads, uint8_t* s_contig,
-                        SpecShared* sp, int spec_w) {
-  c.spec_w = spec_w;
+                        uint8_t* s_pred, SpecShared* sp, int spec_w) {
+  c.spec_w = spec_w; c.s_pred = s_pred; c.round_seed = -1; c.cur_e = 0; c.rnd_ver = 0;
   c.P = &P; c.region = region; c.k = P.k;
   c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
   c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
@@ -875,8 +1011,8 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.hit_u = P.hit_u + c.gu0; c.hit_pos = P.hit_pos + c.gu0; c.hit2_u = P.hit2_u + c.gu0; c.hit2_pos = P.hit2_pos + c.gu0;
   c.cseq = P.w_cseq + slot * ASM_BUF;
   c.cnt_buf = P.w_cnt + slot * 4 * ASM_BUF;
-  c.K = P.w_K + slot * 3 * ASM_KCAP;
-  c.NK = P.w_NK + slot * 3 * ASM_KCAP;
+  c.K = P.w_K + slot * 4 * ASM_KCAP;
+  c.NK = P.w_NK + slot * 4 * ASM_KCAP;
   c.wcode = P.w_wcode + slot * ASM_CAP;
   c.diff = P.w_diff + slot * (ASM_CAP + 1);
   c.edge_all = P.w_edge ? P.w_edge + slot * spec_w * 2 * ASM_CAP : nullptr;
@@ -897,17 +1033,21 @@ template <int W>
 __global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assemble_kernel(AsmParams P) {
   __shared__ __align__(16) uint8_t s_reads[W * ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
+  __shared__ __align__(16) uint8_t s_pred[(W > 1 ? W - 1 : 1) * ASM_CAP];
   __shared__ SpecShared sp;
   const int64_t slot = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   if (W > 1 && warp > 0) {
     int2* edge = P.w_edge ? P.w_edge + (slot * W + warp) * 2 * ASM_CAP : nullptr;
     for (;;) {
-      __syncthreads();
+      __syncthreads();                                 // command published
       const int n = sp.n;
       if (n < 0) return;
-      if (warp < n) spec_work(P, &sp, s_reads, s_contig, warp, edge);
-      __syncthreads();
+      if (warp < n) spec_stage(P, &sp, s_reads, warp);
+      __syncthreads();                                 // reads staged; warp 0 predicts
+      __syncthreads();                                 // predictions published
+      if (warp < n) spec_dp(&sp, s_reads, s_contig, s_pred, warp, edge);
+      __syncthreads();                                 // results published
     }
   }
   RegionCtx c;
@@ -917,7 +1057,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assem
     w = shfl(w, 0);
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
-    bind_region(c, P, region, slot, s_reads, s_contig, &sp, W);
+    bind_region(c, P, region, slot, s_reads, s_contig, s_pred, &sp, W);
 #if defined(BK_PHASE_PROF)
     for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
     const long long t_reg0 = clock64();

@@ -378,8 +378,8 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
-  A.w_K = h->dev.get<int32_t>((size_t)grid * 3 * ASM_KCAP);
-  A.w_NK = h->dev.get<int32_t>((size_t)grid * 3 * ASM_KCAP);
+  A.w_K = h->dev.get<int32_t>((size_t)grid * 4 * ASM_KCAP);
+  A.w_NK = h->dev.get<int32_t>((size_t)grid * 4 * ASM_KCAP);
   A.w_wcode = h->dev.get<uint64_t>((size_t)grid * ASM_CAP);
   A.w_diff = h->dev.get<int32_t>((size_t)grid * (ASM_CAP + 1));
   A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * spec_w * 2 * ASM_CAP) : nullptr;
@@ -456,7 +456,8 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   if (getenv("BK_PHASE_PRINT")) {
     static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "stage", "total", "max_region"};
     for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
-    fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu\n", h_stats[2], h_stats[3], h_stats[0]);
+    fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu rounds %llu slots %llu\n", h_stats[2], h_stats[3], h_stats[0],
+            h_stats[4], h_stats[5]);
     if (A.prof_regions) {
       std::vector<unsigned long long> pr((size_t)R * 12);
       BK_CUDA(cudaMemcpy(pr.data(), A.prof_regions, pr.size() * 8, cudaMemcpyDeviceToHost));

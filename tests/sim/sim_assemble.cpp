@@ -85,7 +85,7 @@ extern "C" int sim_assemble_region(
   P.q_read = q_read.data(); P.q_seed = q_seed.data(); P.l_alt = l_alt.data(); P.l_del = l_del.data();
   P.hit_u = hit_u.data(); P.hit_pos = hit_pos.data(); P.hit2_u = hit2_u.data(); P.hit2_pos = hit2_pos.data();
   std::vector<uint8_t> w_cseq(ASM_BUF);
-  std::vector<int32_t> w_cnt(4 * ASM_BUF), w_K(3 * ASM_KCAP), w_NK(3 * ASM_KCAP), w_diff(ASM_CAP + 1);
+  std::vector<int32_t> w_cnt(4 * ASM_BUF), w_K(4 * ASM_KCAP), w_NK(4 * ASM_KCAP), w_diff(ASM_CAP + 1);
   std::vector<uint64_t> w_wcode(ASM_CAP);
   P.w_cseq = w_cseq.data(); P.w_cnt = w_cnt.data(); P.w_K = w_K.data(); P.w_NK = w_NK.data();
   P.w_wcode = w_wcode.data(); P.w_diff = w_diff.data(); P.w_edge = nullptr;
@@ -98,11 +98,11 @@ extern "C" int sim_assemble_region(
   P.region_status = &status; P.region_ncontigs = &ncontigs;
   unsigned long long stats[16] = {0};
   P.stats = stats;
-  std::vector<uint8_t> s_reads((size_t)ASM_SPEC_W * ASM_CAP), s_contig(ASM_CAP);
+  std::vector<uint8_t> s_reads((size_t)ASM_SPEC_W * ASM_CAP), s_contig(ASM_CAP), s_pred((size_t)ASM_SPEC_W * ASM_CAP);
   SpecShared sp;
   memset(&sp, 0, sizeof sp);
   RegionCtx c;
-  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), &sp, spec_w);
+  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), s_pred.data(), &sp, spec_w);
   assemble_region(c);
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];
