@@ -76,6 +76,7 @@ struct AsmParams {
   const int32_t* u_rec;            // representative (first) record of each unique read
   const uint32_t* u_mult;          // len(fq_recs[seq])
   const uint8_t* u_io;             // reads[0].indel_only
+  const int32_t* u_len;            // length of each unique read
   const int32_t* read_len;         // per region: max record length (utils.py:236)
   // sample-only k-mers (ascending per region) and derived tables
   const int64_t* so_off;           // n_regions + 1
@@ -85,11 +86,15 @@ struct AsmParams {
   const int64_t* post_off;         // total mers + 1 : k-mer -> read posting lists
   const int32_t* post_read;        // local unique-read index, ascending within a list
   const int32_t* post_pos;         // first position of the mer in that read
+  const int64_t* rk_off;           // total unique reads + 1 : read -> sample-only k-mers it holds (ascending local index)
+  const int32_t* rk_s;
+  const int32_t* rk_pos;           // first position of that mer in the read
   // mutable per-mer / per-read state (zero-initialised except m_alive)
   uint8_t* m_alive;                // akmers.mers membership (homopolymers start dead, Q5)
   uint8_t* m_used;                 // buffer.used_mers
   uint32_t* m_checked;             // contig serial in whose checked_kmers the mer is
   uint32_t* m_taken;               // finalize serial (check_alt_reads' mer_set)
+  uint32_t* m_first;               // [contig serial : 20 | 4095 - first window : 12] of the mer in the contig being emitted
   uint8_t* r_used;                 // fq_read.used
   uint8_t* r_deleted;              // key removed from fq_recs
   uint8_t* r_queued;               // 1: contig pending in buffer.contigs, 2: left it
@@ -162,10 +167,11 @@ struct RegionCtx {
   // mers
   int S; int64_t gm0;
   const uint64_t* mer; const uint32_t* cnt; const int32_t* seed_order;
-  uint8_t* alive; uint8_t* mused; uint32_t* checked; uint32_t* taken;
+  uint8_t* alive; uint8_t* mused; uint32_t* checked; uint32_t* taken; uint32_t* first;
+  int32_t* s_hash; bool hash_on;   // shared-memory hash of the region's mer table (find_mer)
   // reads
   int U; int64_t gu0;
-  const int32_t* u_rec; const uint32_t* u_mult; const uint8_t* u_io;
+  const int32_t* u_rec; const uint32_t* u_mult; const uint8_t* u_io; const int32_t* u_len;
   uint8_t* r_used; uint8_t* r_deleted; uint8_t* r_queued; uint32_t* r_buf; uint32_t* r_inreads;
   int32_t* q_read; int32_t* q_seed; int q_head, q_tail;
   int32_t* l_alt; int32_t* l_del; int n_alt, n_del;
@@ -202,15 +208,47 @@ struct RegionCtx {
 
   BK_DEV int32_t* io_vec(int which) const { return cnt_buf + (size_t)which * ASM_BUF; }
   BK_DEV int32_t* ot_vec(int which) const { return cnt_buf + (size_t)(2 + which) * ASM_BUF; }
-  BK_DEV int read_len_of(int u) const {
-    const int rec = u_rec[u];
-    return (int)(P->roff[rec + 1] - P->roff[rec]);
-  }
+  BK_DEV int read_len_of(int u) const { return u_len[u]; }
   BK_DEV const uint8_t* read_ptr(int u) const { return P->rbases + P->roff[u_rec[u]]; }
 };
 
-// binary search of a code in the region's ascending mer table; -1 if absent
+// lookup of a code in the region's ascending mer table; -1 if absent.  Regions with up
+// to MER_HASH_MAX mers use an open-addressed table in shared memory (entry =
+// [tag:15 | index:16]); larger ones fall back to a binary search.
+constexpr int MER_HASH_SIZE = 2048;
+constexpr int MER_HASH_MAX = 1400;
+BK_DEV unsigned mer_hash(uint64_t code) { return (unsigned)((code * 0x9E3779B97F4A7C15ull) >> 53); }        // 11 bits
+BK_DEV int mer_tag(uint64_t code) { return (int)((code * 0xC2B2AE3D27D4EB4Full) >> 49); }                 // 15 bits
+
+BK_DEV void build_mer_hash(RegionCtx& c) {
+  c.hash_on = c.S > 0 && c.S <= MER_HASH_MAX;
+  if (!c.hash_on) return;
+  syncwarp();
+  for (int i = lane(); i < MER_HASH_SIZE; i += WARP) c.s_hash[i] = -1;
+  syncwarp();
+  for (int s = lane(); s < c.S; s += WARP) {
+    const uint64_t code = c.mer[s];
+    const int entry = (mer_tag(code) << 16) | s;
+    unsigned slot = mer_hash(code);
+    while (atomic_cas(&c.s_hash[slot], -1, entry) != -1) slot = (slot + 1) & (MER_HASH_SIZE - 1);
+  }
+  syncwarp();
+}
+
 BK_DEV int find_mer(const RegionCtx& c, uint64_t code) {
+  if (c.hash_on) {
+    const int tag = mer_tag(code);
+    unsigned slot = mer_hash(code);
+    for (;;) {
+      const int e = c.s_hash[slot];
+      if (e < 0) return -1;
+      if ((e >> 16) == tag) {
+        const int idx = e & 0xffff;
+        if (c.mer[idx] == code) return idx;
+      }
+      slot = (slot + 1) & (MER_HASH_SIZE - 1);
+    }
+  }
   int lo = 0, hi = c.S;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -351,6 +389,7 @@ BK_DEV int find_in_slice(const uint8_t* seq, int a, int b, int k, uint64_t code)
 // ---- contig.__init__ (:417-426) ---------------------------------------------------------
 BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
   c.serial += 1;
+  if (c.serial >= (1u << 20)) { c.status = ST_CAPACITY; return; }   // tag width of m_first
   const int lr = stage_read(c, u);
   c.c0 = ASM_CAP; c.clen = lr;
   c.cur = 0; c.k0 = ASM_CAP; c.klen = lr;
@@ -664,30 +703,30 @@ BK_DEV void finalize(RegionCtx& c, bool setup) {
   const int k = c.k;
   for (int a = 0; a < c.n_alt; ++a) {
     const int u = c.l_alt[a];
-    const int lr = stage_read(c, u);
-    const int nwin = lr - k;                                         // get_read_kmers skips the last window (Q8)
-    int best = 0x7fffffff;
-    for (int t = 0; t < nwin; t += WARP) {
-      const int x = t + lane();
-      if (x < nwin) {
-        uint64_t code;
-        if (window_code(c.s_read, x, k, code)) {
-          const int s = find_mer(c, code);
-          if (s >= 0 && c.alive[s] && !c.mused[s] && c.taken[s] != c.fin_serial && c.cnt[s] > 1 && s < best) best = s;
-        }
+    // the read's sample-only mers (ascending) with their first positions; get_read_kmers
+    // skips the last window (Q8), i.e. keeps the mers whose first window starts before len-k
+    const int64_t e0 = c.P->rk_off[c.gu0 + u], e1 = c.P->rk_off[c.gu0 + u + 1];
+    const int32_t* ks = c.P->rk_s + e0;
+    const int32_t* kp = c.P->rk_pos + e0;
+    const int ne = (int)(e1 - e0);
+    const int lim = c.u_len[u] - k;
+    int best = -1;
+    for (int t = 0; t < ne && best < 0; t += WARP) {
+      const int i = t + lane();
+      bool cand = false;
+      if (i < ne && kp[i] < lim) {
+        const int s = ks[i];
+        cand = c.alive[s] && !c.mused[s] && c.taken[s] != c.fin_serial && c.cnt[s] > 1;
       }
+      const unsigned mk = ballot(cand);
+      if (mk) best = shfl(i < ne ? ks[i] : 0, ffs(mk) - 1);        // smallest candidate mer (order policy Q13)
     }
-    best = warp_min_i(best);
-    if (best != 0x7fffffff) {
-      // new contig seeded at the smallest candidate mer; the WHOLE candidate set joins mer_set (:580)
-      for (int t = 0; t < nwin; t += WARP) {
-        const int x = t + lane();
-        if (x < nwin) {
-          uint64_t code;
-          if (window_code(c.s_read, x, k, code)) {
-            const int s = find_mer(c, code);
-            if (s >= 0 && c.alive[s] && !c.mused[s]) c.taken[s] = c.fin_serial;
-          }
+    if (best >= 0) {
+      // new contig seeded there; the WHOLE candidate set joins mer_set (:580)
+      for (int i = lane(); i < ne; i += WARP) {
+        if (kp[i] < lim) {
+          const int s = ks[i];
+          if (c.alive[s] && !c.mused[s]) c.taken[s] = c.fin_serial;
         }
       }
       syncwarp();
@@ -801,20 +840,22 @@ BK_DEV void emit_contig(RegionCtx& c) {
   const AsmParams& P = *c.P;
   const int k = c.k, len = c.clen;
   const int32_t* Ks = c.K; const int32_t* Kx = c.K + ASM_KCAP; const int32_t* Km = c.K + 2 * ASM_KCAP;
-  // window codes of the final contig, then for each tuple the first window with its mer (str.find)
+  // first window of every sample-only mer in the final contig (str.find), via a tagged
+  // per-mer table: [serial | 4095 - x] under atomicMax keeps the smallest x of this contig
   const int nwin = len - k + 1;
+  for (int x = lane(); x <= len; x += WARP) c.diff[x] = 0;
   for (int x = lane(); x < nwin; x += WARP) {
     uint64_t code;
-    c.wcode[x] = window_code(c.s_contig, x, k, code) ? code : KEY_INVALID;
+    if (window_code(c.s_contig, x, k, code)) {
+      const int s = find_mer(c, code);
+      if (s >= 0) atomic_max(&c.first[s], (c.serial << 12) | (unsigned)(4095 - x));
+    }
   }
-  for (int x = lane(); x <= len; x += WARP) c.diff[x] = 0;
   syncwarp();
   for (int e = lane(); e < c.nK; e += WARP) {
-    const uint64_t code = c.mer[Ks[e]];
-    int p = -1;
-    for (int x = 0; x < nwin; ++x)
-      if (c.wcode[x] == code) { p = x; break; }
-    if (p >= 0) {                                                    // find() == -1 touches nothing (Q25)
+    const unsigned v = c.first[Ks[e]];
+    if ((v >> 12) == c.serial) {                                     // find() == -1 touches nothing (Q25)
+      const int p = 4095 - (int)(v & 4095u);
       atomic_add(&c.diff[p], 1);
       atomic_add(&c.diff[(p + k) < len ? (p + k) : len], -1);
     }
@@ -996,14 +1037,16 @@ BK_DEV void assemble_region(RegionCtx& c) {
 }
 
 BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_reads, uint8_t* s_contig,
-                        uint8_t* s_pred, SpecShared* sp, int spec_w) {
+                        uint8_t* s_pred, int32_t* s_hash, SpecShared* sp, int spec_w) {
+  c.s_hash = s_hash;
   c.spec_w = spec_w; c.s_pred = s_pred; c.round_seed = -1; c.cur_e = 0; c.rnd_ver = 0;
   c.P = &P; c.region = region; c.k = P.k;
   c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
   c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
   c.alive = P.m_alive + c.gm0; c.mused = P.m_used + c.gm0; c.checked = P.m_checked + c.gm0; c.taken = P.m_taken + c.gm0;
+  c.first = P.m_first + c.gm0;
   c.gu0 = P.u_off[region]; c.U = (int)(P.u_off[region + 1] - c.gu0);
-  c.u_rec = P.u_rec + c.gu0; c.u_mult = P.u_mult + c.gu0; c.u_io = P.u_io + c.gu0;
+  c.u_rec = P.u_rec + c.gu0; c.u_mult = P.u_mult + c.gu0; c.u_io = P.u_io + c.gu0; c.u_len = P.u_len + c.gu0;
   c.r_used = P.r_used + c.gu0; c.r_deleted = P.r_deleted + c.gu0; c.r_queued = P.r_queued + c.gu0;
   c.r_buf = P.r_buf + c.gu0; c.r_inreads = P.r_inreads + c.gu0;
   c.q_read = P.q_read + c.gu0; c.q_seed = P.q_seed + c.gu0;
@@ -1019,6 +1062,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.edge = c.edge_all;
   c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
   c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
+  build_mer_hash(c);
 }
 
 #ifndef BK_SIM
@@ -1034,6 +1078,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assem
   __shared__ __align__(16) uint8_t s_reads[W * ASM_CAP];
   __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
   __shared__ __align__(16) uint8_t s_pred[(W > 1 ? W - 1 : 1) * ASM_CAP];
+  __shared__ int32_t s_hash[MER_HASH_SIZE];
   __shared__ SpecShared sp;
   const int64_t slot = blockIdx.x;
   const int warp = threadIdx.x >> 5;
@@ -1057,7 +1102,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assem
     w = shfl(w, 0);
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
-    bind_region(c, P, region, slot, s_reads, s_contig, s_pred, &sp, W);
+    bind_region(c, P, region, slot, s_reads, s_contig, s_pred, s_hash, &sp, W);
 #if defined(BK_PHASE_PROF)
     for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
     const long long t_reg0 = clock64();

@@ -24,6 +24,8 @@ inline int ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline void threadfence() {}
+inline int atomic_cas(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p = val; return o; }
+inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 }  // namespace bk
 #else
 #include <cuda_runtime.h>
@@ -40,6 +42,8 @@ BK_DEV int ffs(unsigned x) { return __ffs((int)x); }
 BK_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
 BK_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 BK_DEV void threadfence() { __threadfence(); }
+BK_DEV int atomic_cas(int* p, int cmp, int val) { return atomicCAS(p, cmp, val); }
+BK_DEV unsigned atomic_max(unsigned* p, unsigned v) { return atomicMax(p, v); }
 }  // namespace bk
 #endif
 

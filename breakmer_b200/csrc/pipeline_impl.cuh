@@ -198,7 +198,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   // ---- 1. group identical reads -------------------------------------------------------
   const int64_t n_rec = p.reads.n_rec;
   int64_t NU = 0;
-  int32_t* u_rec = nullptr; uint32_t* u_mult = nullptr; uint8_t* u_io = nullptr;
+  int32_t* u_rec = nullptr; uint32_t* u_mult = nullptr; uint8_t* u_io = nullptr; int32_t* u_len = nullptr;
   int64_t* u_off = h->dev.get<int64_t>(R + 1);
   if (n_rec > 0) {
     uint64_t* hk = h->dev.get<uint64_t>(n_rec);
@@ -237,15 +237,16 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     u_rec = h->dev.get<int32_t>(NU);
     u_mult = h->dev.get<uint32_t>(NU);
     u_io = h->dev.get<uint8_t>(NU);
+    u_len = h->dev.get<int32_t>(NU);
     {
       TimedLaunch t(h->timers, st, KF_GROUP, 2);
-      unique_scatter_kernel<<<nblk(n_rec, 256), 256, 0, st>>>(leader_of, u_index, n_rec, mult_by_rec, p.read_flags, u_rec, u_mult,
-                                                              u_io);
+      unique_scatter_kernel<<<nblk(n_rec, 256), 256, 0, st>>>(leader_of, u_index, n_rec, mult_by_rec, p.read_flags, p.reads.off, u_rec,
+                                                              u_mult, u_io, u_len);
       region_uoff_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(p.read_reg_off, R, u_index, n_rec, d_total, u_off);
     }
   } else {
     BK_CUDA(cudaMemsetAsync(u_off, 0, (R + 1) * sizeof(int64_t), st));
-    u_rec = h->dev.get<int32_t>(1); u_mult = h->dev.get<uint32_t>(1); u_io = h->dev.get<uint8_t>(1);
+    u_rec = h->dev.get<int32_t>(1); u_mult = h->dev.get<uint32_t>(1); u_io = h->dev.get<uint8_t>(1); u_len = h->dev.get<int32_t>(1);
   }
 
   // ---- 2. k-mer stage ---------------------------------------------------------------------
@@ -307,15 +308,18 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   int64_t n_post = 0;
   int64_t* post_off = h->dev.get<int64_t>(S_total + 1);
   int32_t* post_read = nullptr; int32_t* post_pos = nullptr;
+  int64_t* rk_off = h->dev.get<int64_t>(NU + 1);
+  int32_t* rk_s = nullptr; int32_t* rk_pos = nullptr;
   if (S_total > 0 && NU > 0) {
     const int64_t cap = p.reads.n_bases;               // at most one entry per window
     uint64_t* ik = h->dev.get<uint64_t>(cap);
     uint32_t* iv = h->dev.get<uint32_t>(cap);
+    uint64_t* ik2 = h->dev.get<uint64_t>(cap);
     unsigned long long* d_n = dev_zero<unsigned long long>(h, 1);
     {
       TimedLaunch t(h->timers, st, KF_INDEX);
       index_emit_kernel<<<nblk(NU, IDX_WARPS), 32 * IDX_WARPS, 0, st>>>(p.reads.bases, p.reads.off, u_off, u_rec, R, NU, so_off,
-                                                                        so_mer, k, ik, iv, d_n, (unsigned long long)cap);
+                                                                        so_mer, k, ik, iv, ik2, d_n, (unsigned long long)cap);
     }
     const unsigned long long* h_n = to_host(h, d_n, 1);
     BK_CUDA(cudaStreamSynchronize(st));
@@ -323,8 +327,15 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     if (n_post > cap) fail(BK_ERR_CAPACITY, "index: posting overflow");
     post_read = h->dev.get<int32_t>(n_post);
     post_pos = h->dev.get<int32_t>(n_post);
+    rk_s = h->dev.get<int32_t>(n_post);
+    rk_pos = h->dev.get<int32_t>(n_post);
     uint64_t* sk = ik; uint32_t* sv = iv;
+    uint64_t* sk2 = ik2; uint32_t* sv2 = nullptr;
     if (n_post > 0) {
+      // the read -> k-mers copy gets its own value array (same positions) before either sort permutes it
+      uint32_t* iv2 = h->dev.get<uint32_t>(n_post);
+      BK_CUDA(cudaMemcpyAsync(iv2, iv, n_post * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      sv2 = iv2;
       const int64_t tiles = rs_num_tiles(n_post);
       RadixSortScratch sc;
       sc.keys_alt = h->dev.get<uint64_t>(n_post);
@@ -332,13 +343,23 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       sc.table = h->dev.get<uint32_t>(256 * tiles);
       sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
       radix_sort_pairs(ik, iv, n_post, 24 + bits_for((uint64_t)S_total + 1), sc, st, &sk, &sv, h->timers, true);
+      RadixSortScratch sc2 = sc;
+      sc2.keys_alt = h->dev.get<uint64_t>(n_post);
+      sc2.vals_alt = h->dev.get<uint32_t>(n_post);
+      radix_sort_pairs(ik2, iv2, n_post, 24 + bits_for((uint64_t)NU + 1), sc2, st, &sk2, &sv2, h->timers, true);
     }
-    TimedLaunch t(h->timers, st, KF_INDEX, 2);
+    TimedLaunch t(h->timers, st, KF_INDEX, 4);
     post_off_kernel<<<nblk(S_total + 1, 256), 256, 0, st>>>(sk, n_post, S_total, post_off);
-    if (n_post > 0) post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk, sv, n_post, post_read, post_pos);
+    post_off_kernel<<<nblk(NU + 1, 256), 256, 0, st>>>(sk2, n_post, NU, rk_off);
+    if (n_post > 0) {
+      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk, sv, n_post, post_read, post_pos);
+      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk2, sv2, n_post, rk_s, rk_pos);
+    }
   } else {
     BK_CUDA(cudaMemsetAsync(post_off, 0, (S_total + 1) * sizeof(int64_t), st));
+    BK_CUDA(cudaMemsetAsync(rk_off, 0, (NU + 1) * sizeof(int64_t), st));
     post_read = h->dev.get<int32_t>(1); post_pos = h->dev.get<int32_t>(1);
+    rk_s = h->dev.get<int32_t>(1); rk_pos = h->dev.get<int32_t>(1);
   }
 
   // region tables to the host: sizes, work order
@@ -360,7 +381,8 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   memset(&A, 0, sizeof A);
   A.n_regions = R; A.k = k; A.rc_thresh = p.rc_thresh;
   A.rbases = p.reads.bases; A.roff = p.reads.off;
-  A.u_off = u_off; A.u_rec = u_rec; A.u_mult = u_mult; A.u_io = u_io; A.read_len = p.read_len;
+  A.u_off = u_off; A.u_rec = u_rec; A.u_mult = u_mult; A.u_io = u_io; A.u_len = u_len; A.read_len = p.read_len;
+  A.rk_off = rk_off; A.rk_s = rk_s; A.rk_pos = rk_pos;
   A.so_off = so_off; A.so_mer = so_mer; A.so_cnt = so_cnt; A.seed_order = seed_order;
   A.post_off = post_off; A.post_read = post_read; A.post_pos = post_pos;
   A.work_order = to_device(h, h->dev, order.data(), (size_t)R);
@@ -391,11 +413,11 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   uint8_t* zero_lo = nullptr;
   size_t zero_bytes = 0;
   auto zalloc = [&](size_t bytes) { bytes = (bytes + 255) & ~size_t(255); size_t o = zero_bytes; zero_bytes += bytes; return o; };
-  const size_t o_mused = zalloc(S_total), o_checked = zalloc(S_total * 4), o_taken = zalloc(S_total * 4);
+  const size_t o_mused = zalloc(S_total), o_checked = zalloc(S_total * 4), o_taken = zalloc(S_total * 4), o_first = zalloc(S_total * 4);
   const size_t o_rused = zalloc(NU), o_rdel = zalloc(NU), o_rq = zalloc(NU), o_rbuf = zalloc(NU * 4), o_rin = zalloc(NU * 4);
   const size_t o_work = zalloc(sizeof(int)), o_cursor = zalloc(5 * sizeof(unsigned long long)), o_stats = zalloc(16 * sizeof(unsigned long long));
   zero_lo = h->dev.get<uint8_t>(zero_bytes);
-  A.m_used = zero_lo + o_mused; A.m_checked = (uint32_t*)(zero_lo + o_checked); A.m_taken = (uint32_t*)(zero_lo + o_taken);
+  A.m_used = zero_lo + o_mused; A.m_checked = (uint32_t*)(zero_lo + o_checked); A.m_taken = (uint32_t*)(zero_lo + o_taken); A.m_first = (uint32_t*)(zero_lo + o_first);
   A.r_used = zero_lo + o_rused; A.r_deleted = zero_lo + o_rdel; A.r_queued = zero_lo + o_rq;
   A.r_buf = (uint32_t*)(zero_lo + o_rbuf); A.r_inreads = (uint32_t*)(zero_lo + o_rin);
   A.work_counter = (int*)(zero_lo + o_work);

@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(256) leader_flag_kernel(const int32_t* __restr
 __global__ void __launch_bounds__(256) unique_scatter_kernel(const int32_t* __restrict__ leader_of,
                                                               const uint32_t* __restrict__ u_index, int64_t n_rec,
                                                               const uint32_t* __restrict__ mult_by_rec,
-                                                              const uint8_t* __restrict__ flags, int32_t* __restrict__ u_rec,
-                                                              uint32_t* __restrict__ u_mult, uint8_t* __restrict__ u_io) {
+                                                              const uint8_t* __restrict__ flags, const int64_t* __restrict__ off,
+                                                              int32_t* __restrict__ u_rec, uint32_t* __restrict__ u_mult,
+                                                              uint8_t* __restrict__ u_io, int32_t* __restrict__ u_len) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rec || leader_of[r] != (int32_t)r) return;
   const uint32_t u = u_index[r];
   u_rec[u] = (int32_t)r;
+  u_len[u] = (int32_t)(off[r + 1] - off[r]);
   u_mult[u] = mult_by_rec[r];
   u_io[u] = flags ? (flags[r] & 1u) : 0u;
 }
@@ -161,12 +163,13 @@ __device__ __forceinline__ bool window_code_dev(const uint8_t* seq, int x, int k
 
 // one warp per unique read: every window whose mer is a sample-only mer of the
 // region and that is the FIRST occurrence of that mer in the read emits
-//   key = [ global mer index : 40 | local read index : 24 ], value = position
+//   key  = [ global mer index : 40 | local read index : 24 ], value = position   (k-mer -> reads)
+//   key2 = [ global read index : 40 | local mer index : 24 ], value = position   (read -> k-mers)
 __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
     const uint8_t* __restrict__ rbases, const int64_t* __restrict__ roff, const int64_t* __restrict__ u_off,
     const int32_t* __restrict__ u_rec, int n_regions, int64_t n_uniq, const int64_t* __restrict__ so_off,
     const uint64_t* __restrict__ so_mer, int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-    unsigned long long* __restrict__ n_out, unsigned long long cap) {
+    uint64_t* __restrict__ keys2, unsigned long long* __restrict__ n_out, unsigned long long cap) {
   __shared__ int32_t ws[IDX_WARPS][IDX_READ_CAP];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * IDX_WARPS + w;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
         const unsigned long long dst = base + __popc(mk & ((1u << l) - 1u));
         if (dst < cap) {
           keys[dst] = ((uint64_t)(gm0 + s) << 24) | ulocal;
+          keys2[dst] = ((uint64_t)u << 24) | (uint64_t)s;
           vals[dst] = (uint32_t)x;
         }
       }

@@ -30,7 +30,9 @@ extern "C" int sim_assemble_region(
   int64_t u_off[2] = {0, n_reads};
   std::vector<int32_t> u_rec(n_reads);
   for (int i = 0; i < n_reads; ++i) u_rec[i] = i;
-  P.u_off = u_off; P.u_rec = u_rec.data(); P.u_mult = mult; P.u_io = io;
+  std::vector<int32_t> u_len(n_reads + 1);
+  for (int i = 0; i < n_reads; ++i) u_len[i] = (int32_t)(roff[i + 1] - roff[i]);
+  P.u_off = u_off; P.u_rec = u_rec.data(); P.u_mult = mult; P.u_io = io; P.u_len = u_len.data();
   int32_t rl = read_len;
   P.read_len = &rl;
   int64_t so_off[2] = {0, n_mers};
@@ -74,8 +76,21 @@ extern "C" int sim_assemble_region(
   post_off[n_mers] = (int64_t)post_read.size();
   post_read.push_back(0); post_pos.push_back(0);
   P.post_off = post_off.data(); P.post_read = post_read.data(); P.post_pos = post_pos.data();
-  std::vector<uint32_t> m_checked(n_mers + 1, 0), m_taken(n_mers + 1, 0);
-  P.m_alive = alive.data(); P.m_used = mused.data(); P.m_checked = m_checked.data(); P.m_taken = m_taken.data();
+  // read -> k-mers lists (kernel: index), ascending local mer index
+  std::vector<std::vector<std::pair<int, int>>> rk(n_reads);
+  for (int si = 0; si < n_mers; ++si)
+    for (auto& pr : post[si]) rk[pr.first].push_back({si, pr.second});
+  std::vector<int64_t> rk_off(n_reads + 1, 0);
+  std::vector<int32_t> rk_s, rk_pos;
+  for (int u = 0; u < n_reads; ++u) {
+    rk_off[u] = (int64_t)rk_s.size();
+    for (auto& e : rk[u]) { rk_s.push_back(e.first); rk_pos.push_back(e.second); }
+  }
+  rk_off[n_reads] = (int64_t)rk_s.size();
+  rk_s.push_back(0); rk_pos.push_back(0);
+  P.rk_off = rk_off.data(); P.rk_s = rk_s.data(); P.rk_pos = rk_pos.data();
+  std::vector<uint32_t> m_checked(n_mers + 1, 0), m_taken(n_mers + 1, 0), m_first(n_mers + 1, 0);
+  P.m_alive = alive.data(); P.m_used = mused.data(); P.m_checked = m_checked.data(); P.m_taken = m_taken.data(); P.m_first = m_first.data();
   const int U = n_reads + 1;
   std::vector<uint8_t> r_used(U, 0), r_deleted(U, 0), r_queued(U, 0);
   std::vector<uint32_t> r_buf(U, 0), r_inreads(U, 0);
@@ -102,7 +117,8 @@ extern "C" int sim_assemble_region(
   SpecShared sp;
   memset(&sp, 0, sizeof sp);
   RegionCtx c;
-  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), s_pred.data(), &sp, spec_w);
+  std::vector<int32_t> s_hash(MER_HASH_SIZE);
+  bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), s_pred.data(), s_hash.data(), &sp, spec_w);
   assemble_region(c);
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];
