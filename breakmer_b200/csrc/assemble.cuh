@@ -277,6 +277,36 @@ BK_DEV void sync_contig_to_smem(RegionCtx& c) {
 // ---- get_read_kmers_ordered (:126-143; Q8 skips the last window, Q26 floor) ----
 // windows of seq[base .. base+nlen) that are live sample-only mers, appended to
 // the contig's k-mer tuple list in the requested order
+// pass A of every "which windows are live sample-only mers" question: lane l owns a
+// contiguous run of windows and rolls the 2-bit code along it (k loads for the first
+// window, one per further window); win[x] = local mer index or -1
+BK_DEV void lookup_windows(RegionCtx& c, const uint8_t* seq, int nwin, int32_t* win) {
+  const int k = c.k;
+  const int per = (nwin + WARP - 1) / WARP;
+  const int x0 = lane() * per;
+  const int x1 = (x0 + per) < nwin ? (x0 + per) : nwin;
+  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+  uint64_t code = 0;
+  int bad = 0;                                  // windows (counting from x) still poisoned by a non-ACGT byte
+  for (int x = x0; x < x1; ++x) {
+    if (x == x0) {
+      for (int t = 0; t < k; ++t) {
+        const int bc = base_code_strict(seq[x + t]);
+        code = (code << 2) | (uint64_t)(bc & 3);
+        if (bc >= 4) bad = t + 1;
+      }
+    } else {
+      const int bc = base_code_strict(seq[x + k - 1]);
+      code = ((code << 2) | (uint64_t)(bc & 3)) & mask;
+      bad = bc >= 4 ? k : (bad > 0 ? bad - 1 : 0);
+    }
+    int sidx = -1;
+    if (bad == 0) sidx = find_mer(c, code);
+    win[x] = sidx;
+  }
+  syncwarp();
+}
+
 BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, int order) {
   const int k = c.k;
   const int nwin = nlen - k;              // range(0, len - l)
@@ -285,6 +315,8 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
   const int m = nlen / 2;
   const unsigned lt = lane_lt_mask();
   int32_t* Ks = c.K; int32_t* Kx = c.K + ASM_KCAP; int32_t* Km = c.K + 2 * ASM_KCAP; int32_t* Kb = c.K + 3 * ASM_KCAP;
+  int32_t* win = reinterpret_cast<int32_t*>(c.wcode);
+  lookup_windows(c, seq + base, nwin, win);
   // pass 0: ascending x over [lo0, hi0) ; pass 1: descending x over [lo1, hi1)
   int lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
   if (order == ORDER_FOR) { lo0 = 0; hi0 = nwin; }
@@ -295,19 +327,16 @@ BK_DEV void append_kmers(RegionCtx& c, const uint8_t* seq, int base, int nlen, i
     for (int b = 0; b < hi - lo; b += WARP) {
       const int t = b + lane();
       const int x = pass == 0 ? lo + t : hi - 1 - t;
-      int s = -1;
+      int sidx = -1;
       if (t < hi - lo) {
-        uint64_t code;
-        if (window_code(seq + base, x, k, code)) {
-          s = find_mer(c, code);
-          if (s >= 0 && !c.alive[s]) s = -1;
-        }
+        sidx = win[x];
+        if (sidx >= 0 && !c.alive[sidx]) sidx = -1;
       }
-      const unsigned mk = ballot(s >= 0);
-      if (s >= 0) {
+      const unsigned mk = ballot(sidx >= 0);
+      if (sidx >= 0) {
         const int dst = c.nK + popc(mk & lt);
         if (dst < ASM_KCAP) {
-          Ks[dst] = s; Kx[dst] = x;
+          Ks[dst] = sidx; Kx[dst] = x;
           const int lth = x < m ? 1 : 0, dist = x < m ? m - x : x - m;
           Km[dst] = lth | (order << 1) | (dist << 3);
           Kb[dst] = c.c0 + base + x;         // where the window sits in the gap buffer (stable under prepend/append)
@@ -474,8 +503,7 @@ BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_con
   const int lc = sp->la[w];
   NwDual r;
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  if (lr <= 128) nw_dual_warp_fast<4>(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
-  else nw_dual_warp_fast<8>(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  nw_dual_dispatch(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
   if (lane() == 0) { sp->v1[w] = r.b; sp->v2[w] = r.a; }
   syncwarp();
 }
@@ -758,33 +786,53 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
   const int n0 = (int)(b - a);
   const unsigned lt = lane_lt_mask();
   int n = 0;
-  for (int t = 0; t < n0; t += WARP) {
-    const int i = t + lane();
+  if (n0 <= WARP) {
+    // the whole posting list fits one warp pass: filter, rank and place from registers
+    const int i = lane();
     bool keep = false;
-    int u = 0, pos = 0;
+    int u = 0, key = 0, pos = 0;
     if (i < n0) {
       u = pr[i]; pos = pp[i];
       keep = !c.r_deleted[u] && !(filter_buffer && c.r_buf[u] == c.serial);
+      // sort key: primary pos (or -pos), secondary -len; both < 4096
+      key = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - c.u_len[u]);
     }
     const unsigned mk = ballot(keep);
+    n = popc(mk);
+    int rank = 0;
+#ifdef BK_SIM
+    (void)lt;
+#else
+    for (unsigned rest = mk; rest; rest &= rest - 1) {
+      const int j = __ffs((int)rest) - 1;
+      const int kj = __shfl_sync(0xffffffffu, key, j);
+      rank += (kj < key || (kj == key && j < i)) ? 1 : 0;          // stable: ties keep read order (Q9)
+    }
+#endif
     if (keep) {
-      const int dst = n + popc(mk & lt);
-      c.hit2_u[dst] = u;
-      // sort key: primary pos (or -pos), secondary -len; both < 4096
-      const int len = c.read_len_of(u);
-      c.hit2_pos[dst] = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - len);
+      c.hit_u[at + rank] = u;
+      c.hit_pos[at + rank] = pos;
       if (filter_buffer) c.r_buf[u] = c.serial;
     }
-    n += popc(mk);
-  }
-  syncwarp();
-  if (n == 1) {
-    if (lane() == 0) {
-      c.hit_u[at] = c.hit2_u[0];
-      const int hi = c.hit2_pos[0] >> 12;
-      c.hit_pos[at] = rev ? (ASM_CAP - 1 - hi) : hi;
-    }
   } else {
+    for (int t = 0; t < n0; t += WARP) {
+      const int i = t + lane();
+      bool keep = false;
+      int u = 0, pos = 0;
+      if (i < n0) {
+        u = pr[i]; pos = pp[i];
+        keep = !c.r_deleted[u] && !(filter_buffer && c.r_buf[u] == c.serial);
+      }
+      const unsigned mk = ballot(keep);
+      if (keep) {
+        const int dst = n + popc(mk & lt);
+        c.hit2_u[dst] = u;
+        c.hit2_pos[dst] = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - c.u_len[u]);
+        if (filter_buffer) c.r_buf[u] = c.serial;
+      }
+      n += popc(mk);
+    }
+    syncwarp();
     // stable rank sort (lists are short: at most the reads that contain one k-mer)
     for (int t = 0; t < n; t += WARP) {
       const int i = t + lane();
@@ -844,10 +892,11 @@ BK_DEV void emit_contig(RegionCtx& c) {
   // per-mer table: [serial | 4095 - x] under atomicMax keeps the smallest x of this contig
   const int nwin = len - k + 1;
   for (int x = lane(); x <= len; x += WARP) c.diff[x] = 0;
-  for (int x = lane(); x < nwin; x += WARP) {
-    uint64_t code;
-    if (window_code(c.s_contig, x, k, code)) {
-      const int s = find_mer(c, code);
+  {
+    int32_t* win = reinterpret_cast<int32_t*>(c.wcode);
+    lookup_windows(c, c.s_contig, nwin, win);
+    for (int x = lane(); x < nwin; x += WARP) {
+      const int s = win[x];
       if (s >= 0) atomic_max(&c.first[s], (c.serial << 12) | (unsigned)(4095 - x));
     }
   }
@@ -949,6 +998,13 @@ BK_DEV void grow(RegionCtx& c) {
     // order.  It does not depend on how the alignments turn out (see find_reads).
     int st = 0;
     for (int e = 0; e < nn; ++e) {
+#ifndef BK_SIM
+      if (e + 1 < nn) {                 // warm L1/L2 for the next tuple's posting list while this one is processed
+        const int64_t na = c.P->post_off[c.gm0 + Ns[e + 1]];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.P->post_read + na + lane()));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c.P->post_pos + na + lane()));
+      }
+#endif
       const int meta = Nm[e];
       const int lth = meta & 1, order = (meta >> 1) & 3;
       const bool rev = (order == ORDER_MID) ? (lth == 0) : (order == ORDER_FOR);

@@ -125,6 +125,9 @@ template <int C>
 inline void nw_dual_warp_fast(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, NwDual& out) {
   nw_dual_warp<C, false>(cs, m, rs, n, e0, e1, nullptr, out);
 }
+inline void nw_dual_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, NwDual& out) {
+  nw_dual_warp<4, false>(cs, m, rs, n, e0, e1, nullptr, out);
+}
 #else
 // ---------------------------------------------------------------------------
 // The product kernel.
@@ -239,7 +242,10 @@ __device__ __forceinline__ void nw_dual_warp(const uint8_t* __restrict__ cs, int
 // rows x two directions) overlap in the pipeline, and the step count is halved.
 // Row characters are fetched one step ahead.  `rs` must be 2-byte aligned and
 // readable up to index n (one byte past the sequence).
-template <int C>
+// OWN_C >= 0: column m is known at compile time to sit in slot OWN_C of its lane (single
+// column block), which turns the last-column tracker into two compares; OWN_C = -1 is
+// the general case.
+template <int C, int OWN_C = -1>
 __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs, int m,
                                                   const uint8_t* __restrict__ rs, int n,
                                                   int2* edge0, int2* edge1, NwDual& out) {
@@ -339,9 +345,14 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
           if (i1 <= n) eout[i1] = make_int2(lastA1, lastB1);
         }
         {   // last column (direction A): rows in increasing order, >= keeps the largest row
-          int c0 = r0A[0], c1 = colA[0];
+          int c0, c1;
+          if (OWN_C >= 0) {
+            c0 = r0A[OWN_C >= 0 ? OWN_C : 0]; c1 = colA[OWN_C >= 0 ? OWN_C : 0];
+          } else {
+            c0 = r0A[0]; c1 = colA[0];
 #pragma unroll
-          for (int c = 1; c < C; ++c) { c0 = (c == own_c) ? r0A[c] : c0; c1 = (c == own_c) ? colA[c] : c1; }
+            for (int c = 1; c < C; ++c) { c0 = (c == own_c) ? r0A[c] : c0; c1 = (c == own_c) ? colA[c] : c1; }
+          }
           const bool u0 = own && ((c0 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
           best_a = u0 ? c0 : best_a; best_ai = u0 ? i0 : best_ai;
           const bool u1 = own && (i1 <= n) && ((c1 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
@@ -375,6 +386,21 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
   }
   nw_decode_a(best_a, best_ai, m, out.a);
   nw_decode_b(best_b, best_bj, n, out.b);
+}
+// dispatch on the read length: 4 columns per lane up to 128 bases (with the last-column
+// slot resolved at compile time), 8 beyond
+__device__ __forceinline__ void nw_dual_dispatch(const uint8_t* __restrict__ cs, int m, const uint8_t* __restrict__ rs, int n,
+                                                 int2* e0, int2* e1, NwDual& out) {
+  if (m <= 128) {
+    switch ((m - 1) & 3) {
+      case 0: nw_dual_warp_fast<4, 0>(cs, m, rs, n, e0, e1, out); break;
+      case 1: nw_dual_warp_fast<4, 1>(cs, m, rs, n, e0, e1, out); break;
+      case 2: nw_dual_warp_fast<4, 2>(cs, m, rs, n, e0, e1, out); break;
+      default: nw_dual_warp_fast<4, 3>(cs, m, rs, n, e0, e1, out); break;
+    }
+  } else {
+    nw_dual_warp_fast<8>(cs, m, rs, n, e0, e1, out);
+  }
 }
 #endif  // BK_SIM
 

@@ -37,8 +37,7 @@ __device__ __forceinline__ void nw_dispatch(const uint8_t* cs, int m, const uint
     if (m <= 128) nw_dual_warp<4, true>(cs, m, rs, n, e0, e1, ptrmat, out);
     else nw_dual_warp<8, true>(cs, m, rs, n, e0, e1, ptrmat, out);
   } else {
-    if (m <= 128) nw_dual_warp_fast<4>(cs, m, rs, n, e0, e1, out);
-    else nw_dual_warp_fast<8>(cs, m, rs, n, e0, e1, out);
+    nw_dual_dispatch(cs, m, rs, n, e0, e1, out);
   }
 }
 
