@@ -214,7 +214,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     sc.table = h->dev.get<uint32_t>(256 * tiles);
     sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
     uint64_t* sk; uint32_t* sv;
-    radix_sort_pairs(hk, hv, n_rec, 64, sc, st, &sk, &sv, h->timers, true);
+    radix_sort_pairs(hk, hv, n_rec, 32, sc, st, &sk, &sv, h->timers, true);   // low 32 hash bits; runs are verified byte-wise
     int32_t* leader_of = h->dev.get<int32_t>(n_rec);
     uint32_t* mult_by_rec = dev_zero<uint32_t>(h, n_rec);
     uint32_t* flag = h->dev.get<uint32_t>(n_rec);
@@ -281,6 +281,18 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_tot, R, so_off);
   }
 
+  // per-region table sizes decide the field widths of the packed sort keys below
+  const int64_t* h_so_off = to_host(h, so_off, (size_t)R + 1);
+  const int64_t* h_u_off = to_host(h, u_off, (size_t)R + 1);
+  BK_CUDA(cudaStreamSynchronize(st));
+  int64_t max_s = 1, max_u = 1;
+  for (int r = 0; r < R; ++r) {
+    max_s = std::max<int64_t>(max_s, h_so_off[r + 1] - h_so_off[r]);
+    max_u = std::max<int64_t>(max_u, h_u_off[r + 1] - h_u_off[r]);
+  }
+  const int s_bits = std::max(1, bits_for((uint64_t)max_s)), u_bits = std::max(1, bits_for((uint64_t)max_u));
+  if (s_bits > 24 || u_bits > 24) fail(BK_ERR_CAPACITY, "a region has more than 2^24 reads or sample-only k-mers");
+
   // ---- 3. liveness + seed order -----------------------------------------------------------------
   uint8_t* m_alive = h->dev.get<uint8_t>(S_total);
   int32_t* seed_order = h->dev.get<int32_t>(S_total);
@@ -290,7 +302,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     uint32_t* sv0 = h->dev.get<uint32_t>(S_total);
     {
       TimedLaunch t(h->timers, st, KF_PREP);
-      mer_prep_kernel<<<nblk(S_total, 256), 256, 0, st>>>(so_mer, so_cnt, so_off, R, S_total, k, m_alive, sk0, sv0, d_overflow);
+      mer_prep_kernel<<<nblk(S_total, 256), 256, 0, st>>>(so_mer, so_cnt, so_off, R, S_total, k, s_bits, m_alive, sk0, sv0, d_overflow);
     }
     const int64_t tiles = rs_num_tiles(S_total);
     RadixSortScratch sc;
@@ -299,7 +311,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     sc.table = h->dev.get<uint32_t>(256 * tiles);
     sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
     uint64_t* sk; uint32_t* sv;
-    radix_sort_pairs(sk0, sv0, S_total, 64, sc, st, &sk, &sv, h->timers, true);
+    radix_sort_pairs(sk0, sv0, S_total, bits_for((uint64_t)R) + 24 + s_bits, sc, st, &sk, &sv, h->timers, true);
     TimedLaunch t(h->timers, st, KF_PREP);
     unpack_u32_to_i32_kernel<<<nblk(S_total, 256), 256, 0, st>>>(sv, S_total, seed_order);
   }
@@ -319,7 +331,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     {
       TimedLaunch t(h->timers, st, KF_INDEX);
       index_emit_kernel<<<nblk(NU, IDX_WARPS), 32 * IDX_WARPS, 0, st>>>(p.reads.bases, p.reads.off, u_off, u_rec, R, NU, so_off,
-                                                                        so_mer, k, ik, iv, ik2, d_n, (unsigned long long)cap);
+                                                                        so_mer, k, ik, iv, ik2, u_bits, s_bits, d_n, (unsigned long long)cap);
     }
     const unsigned long long* h_n = to_host(h, d_n, 1);
     BK_CUDA(cudaStreamSynchronize(st));
@@ -342,18 +354,18 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       sc.vals_alt = h->dev.get<uint32_t>(n_post);
       sc.table = h->dev.get<uint32_t>(256 * tiles);
       sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
-      radix_sort_pairs(ik, iv, n_post, 24 + bits_for((uint64_t)S_total + 1), sc, st, &sk, &sv, h->timers, true);
+      radix_sort_pairs(ik, iv, n_post, u_bits + bits_for((uint64_t)S_total + 1), sc, st, &sk, &sv, h->timers, true);
       RadixSortScratch sc2 = sc;
       sc2.keys_alt = h->dev.get<uint64_t>(n_post);
       sc2.vals_alt = h->dev.get<uint32_t>(n_post);
-      radix_sort_pairs(ik2, iv2, n_post, 24 + bits_for((uint64_t)NU + 1), sc2, st, &sk2, &sv2, h->timers, true);
+      radix_sort_pairs(ik2, iv2, n_post, s_bits + bits_for((uint64_t)NU + 1), sc2, st, &sk2, &sv2, h->timers, true);
     }
     TimedLaunch t(h->timers, st, KF_INDEX, 4);
-    post_off_kernel<<<nblk(S_total + 1, 256), 256, 0, st>>>(sk, n_post, S_total, post_off);
-    post_off_kernel<<<nblk(NU + 1, 256), 256, 0, st>>>(sk2, n_post, NU, rk_off);
+    post_off_kernel<<<nblk(S_total + 1, 256), 256, 0, st>>>(sk, n_post, S_total, u_bits, post_off);
+    post_off_kernel<<<nblk(NU + 1, 256), 256, 0, st>>>(sk2, n_post, NU, s_bits, rk_off);
     if (n_post > 0) {
-      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk, sv, n_post, post_read, post_pos);
-      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk2, sv2, n_post, rk_s, rk_pos);
+      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk, sv, n_post, u_bits, post_read, post_pos);
+      post_split_kernel<<<nblk(n_post, 256), 256, 0, st>>>(sk2, sv2, n_post, s_bits, rk_s, rk_pos);
     }
   } else {
     BK_CUDA(cudaMemsetAsync(post_off, 0, (S_total + 1) * sizeof(int64_t), st));
@@ -362,9 +374,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     rk_s = h->dev.get<int32_t>(1); rk_pos = h->dev.get<int32_t>(1);
   }
 
-  // region tables to the host: sizes, work order
-  const int64_t* h_so_off = to_host(h, so_off, (size_t)R + 1);
-  const int64_t* h_u_off = to_host(h, u_off, (size_t)R + 1);
+  // work order
   const int* h_overflow = to_host(h, d_overflow, 1);
   BK_CUDA(cudaStreamSynchronize(st));
   if (*h_overflow) fail(BK_ERR_CAPACITY, "seed order: a k-mer count or region size exceeds 2^24");

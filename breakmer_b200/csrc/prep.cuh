@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128) group_leader_kernel(const uint64_t* __res
   const int n = (int)(off[rec + 1] - a);
   const int seg = rec_seg[rec];
   int64_t j = i;
-  while (j > 0 && keys[j - 1] == key) --j;
+  while (j > 0 && (uint32_t)keys[j - 1] == (uint32_t)key) --j;     // the sort only orders the low 32 hash bits
   uint32_t leader = rec;
   for (int64_t t = j; t < i; ++t) {                   // stable sort: record indices ascend within the run
     const uint32_t cand = vals[t];
@@ -119,11 +119,11 @@ __global__ void __launch_bounds__(256) widen_scan_kernel(const uint32_t* __restr
 }
 
 // thread per sample-only mer: liveness + seed sort key
-//   key = [ region : 16 | 0xFFFFFF - count : 24 | 0xFFFFFF - local index : 24 ]
+//   key = [ region | 0xFFFFFF - count : 24 | max - local index : idx_bits ]
 // ascending key order == (count, mer) descending within a region (mers ascend with the index)
 __global__ void __launch_bounds__(256) mer_prep_kernel(const uint64_t* __restrict__ mers, const uint32_t* __restrict__ counts,
                                                         const int64_t* __restrict__ so_off, int n_regions, int64_t n_mers, int k,
-                                                        uint8_t* __restrict__ alive, uint64_t* __restrict__ keys,
+                                                        int idx_bits, uint8_t* __restrict__ alive, uint64_t* __restrict__ keys,
                                                         uint32_t* __restrict__ vals, int* __restrict__ overflow) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_mers) return;
@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(256) mer_prep_kernel(const uint64_t* __restric
   alive[g] = homo ? 0 : 1;
   const uint64_t local = (uint64_t)(g - so_off[lo]);
   const uint32_t c = counts[g];
-  if (c > 0xFFFFFFu || local > 0xFFFFFFu || lo > 0xFFFF) *overflow = 1;
-  keys[g] = ((uint64_t)lo << 48) | ((uint64_t)(0xFFFFFFu - (c > 0xFFFFFFu ? 0xFFFFFFu : c)) << 24) | (0xFFFFFFull - local);
+  const uint64_t imask = (1ull << idx_bits) - 1ull;
+  if (c > 0xFFFFFFu || local > imask) *overflow = 1;
+  keys[g] = ((uint64_t)lo << (24 + idx_bits)) | ((uint64_t)(0xFFFFFFu - (c > 0xFFFFFFu ? 0xFFFFFFu : c)) << idx_bits) | (imask - local);
   vals[g] = (uint32_t)local;
 }
 
@@ -163,13 +164,13 @@ __device__ __forceinline__ bool window_code_dev(const uint8_t* seq, int x, int k
 
 // one warp per unique read: every window whose mer is a sample-only mer of the
 // region and that is the FIRST occurrence of that mer in the read emits
-//   key  = [ global mer index : 40 | local read index : 24 ], value = position   (k-mer -> reads)
-//   key2 = [ global read index : 40 | local mer index : 24 ], value = position   (read -> k-mers)
+//   key  = [ global mer index | local read index : u_bits ], value = position   (k-mer -> reads)
+//   key2 = [ global read index | local mer index : s_bits ], value = position   (read -> k-mers)
 __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
     const uint8_t* __restrict__ rbases, const int64_t* __restrict__ roff, const int64_t* __restrict__ u_off,
     const int32_t* __restrict__ u_rec, int n_regions, int64_t n_uniq, const int64_t* __restrict__ so_off,
     const uint64_t* __restrict__ so_mer, int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-    uint64_t* __restrict__ keys2, unsigned long long* __restrict__ n_out, unsigned long long cap) {
+    uint64_t* __restrict__ keys2, int u_bits, int s_bits, unsigned long long* __restrict__ n_out, unsigned long long cap) {
   __shared__ int32_t ws[IDX_WARPS][IDX_READ_CAP];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * IDX_WARPS + w;
@@ -217,8 +218,8 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
       if (first) {
         const unsigned long long dst = base + __popc(mk & ((1u << l) - 1u));
         if (dst < cap) {
-          keys[dst] = ((uint64_t)(gm0 + s) << 24) | ulocal;
-          keys2[dst] = ((uint64_t)u << 24) | (uint64_t)s;
+          keys[dst] = ((uint64_t)(gm0 + s) << u_bits) | ulocal;
+          keys2[dst] = ((uint64_t)u << s_bits) | (uint64_t)s;
           vals[dst] = (uint32_t)x;
         }
       }
@@ -226,12 +227,12 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
   }
 }
 
-// thread per (mer + 1): post_off[g] = lower bound of g << 24 in the sorted keys
+// thread per (group + 1): post_off[g] = lower bound of g << low_bits in the sorted keys
 __global__ void __launch_bounds__(256) post_off_kernel(const uint64_t* __restrict__ keys, int64_t n_post, int64_t n_mers,
-                                                        int64_t* __restrict__ post_off) {
+                                                        int low_bits, int64_t* __restrict__ post_off) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g > n_mers) return;
-  const uint64_t target = (uint64_t)g << 24;
+  const uint64_t target = (uint64_t)g << low_bits;
   int64_t a = 0, b = n_post;
   while (a < b) {
     const int64_t mid = (a + b) >> 1;
@@ -241,11 +242,11 @@ __global__ void __launch_bounds__(256) post_off_kernel(const uint64_t* __restric
 }
 
 __global__ void __launch_bounds__(256) post_split_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                          int64_t n_post, int32_t* __restrict__ post_read,
+                                                          int64_t n_post, int low_bits, int32_t* __restrict__ post_read,
                                                           int32_t* __restrict__ post_pos) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_post) return;
-  post_read[i] = (int32_t)(keys[i] & 0xFFFFFFull);
+  post_read[i] = (int32_t)(keys[i] & ((1ull << low_bits) - 1ull));
   post_pos[i] = (int32_t)vals[i];
 }
 

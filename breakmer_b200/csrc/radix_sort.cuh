@@ -6,7 +6,8 @@
 // counting is a run-length pass (kmers.cuh).
 //
 // Per pass: (1) per-tile digit histogram, (2) exclusive scan of the
-// digit-major [256][n_tiles] table, (3) stable scatter (warp match-any ranking).
+// digit-major [256][n_tiles] table, (3) stable scatter (warp match-any ranking,
+// tile reordered in shared memory so that stores are coalesced per digit run).
 // Only the low `key_bits` bits are sorted: the caller knows how many bits the
 // composite key occupies.  HBM traffic per pass: keys read twice, values once,
 // both written once = 32 B/element; every access is coalesced except the
@@ -20,7 +21,7 @@ namespace bk {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // keys per tile
 constexpr int RS_WCHUNK = 32 * RS_ITEMS;             // contiguous keys per warp
 
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_count_kernel(const uint64_t* __
   hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
+#pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const int64_t i = base + k * RS_THREADS + threadIdx.x;
     if (i < n) atomicAdd(&hist[(unsigned)(keys[i] >> shift) & 255u], 1u);
@@ -39,16 +40,23 @@ __global__ void __launch_bounds__(RS_THREADS) rs_count_kernel(const uint64_t* __
   table[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = hist[threadIdx.x];
 }
 
+// Stable scatter of one tile.  Ranks come from warp match-any; the tile is first put in
+// digit order in shared memory, so the global stores of a warp go to consecutive
+// addresses of (at most a few) digit runs instead of 32 scattered sectors.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* __restrict__ keys_in,
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint64_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int64_t n, int shift,
                                                                  const uint32_t* __restrict__ table, int64_t n_tiles) {
   __shared__ uint32_t wcount[RS_WARPS][256];
+  __shared__ uint64_t skeys[RS_TILE];
+  __shared__ uint32_t svals[RS_TILE];
+  __shared__ uint32_t dbase[256];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int d = l; d < 256; d += 32) wcount[w][d] = 0;
   __syncwarp();
-  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WCHUNK;
+  const int64_t tile0 = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t base = tile0 + (int64_t)w * RS_WCHUNK;
   const unsigned lt = (1u << l) - 1u;
   uint64_t key[RS_ITEMS];
   uint32_t val[RS_ITEMS];
@@ -72,25 +80,41 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
   }
   __syncthreads();
   {
-    // one thread per digit: turn per-warp counts into per-warp start offsets
+    // one thread per digit: tile-local start of the digit, then per-warp starts inside it
     const int d = threadIdx.x;
-    uint32_t run = table[(int64_t)d * n_tiles + blockIdx.x];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) tot += wcount[ww][d];
+    uint32_t tile_total;
+    const uint32_t tstart = block_excl_scan(tot, &tile_total);
+    uint32_t run = tstart;
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ++ww) {
       const uint32_t c = wcount[ww][d];
       wcount[ww][d] = run;
       run += c;
     }
+    dbase[d] = table[(int64_t)d * n_tiles + blockIdx.x] - tstart;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
-    const int64_t i = base + k * 32 + l;
-    if (i < n) {
-      const unsigned d = (unsigned)(key[k] >> shift) & 255u;
-      const uint32_t dst = wcount[w][d] + rank[k];
-      keys_out[dst] = key[k];
-      vals_out[dst] = val[k];
+    const unsigned d = (unsigned)(key[k] >> shift) & 255u;
+    const uint32_t lpos = wcount[w][d] + rank[k];
+    skeys[lpos] = key[k];
+    svals[lpos] = val[k];
+  }
+  __syncthreads();
+  const int64_t left = n - tile0;
+  const int tile_n = left < RS_TILE ? (int)left : RS_TILE;     // padding sorts to the end of digit 255, i.e. past tile_n
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int i = k * RS_THREADS + threadIdx.x;
+    if (i < tile_n) {
+      const uint64_t kk = skeys[i];
+      const uint32_t dst = dbase[(unsigned)(kk >> shift) & 255u] + (uint32_t)i;
+      keys_out[dst] = kk;
+      vals_out[dst] = svals[i];
     }
   }
 }
