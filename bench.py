@@ -261,9 +261,9 @@ def gpu_arm(args):
         lat_ms.append(float(r.gpu_ms))
     ktimes = h.kernel_times()
     kt_steps = 3
-    spec_w = args.spec_width if args.spec_width else (4 if n_fly == 1 else 1)
+    spec_w = args.spec_width if args.spec_width else 4
     for hh in handles:
-        hh.set_option("spec_width", spec_w)      # several batches in flight: no speculative work, more regions per SM
+        hh.set_option("spec_width", spec_w)
         batch.run(hh, pk, resident=True, decode=False)
         hh.kernel_times_reset(False)             # timers off, launch counters zeroed for the timed region
     sampler = ClockSampler(local_rank)

@@ -400,7 +400,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   int spec_w = h->spec_width;
   if (const char* e = getenv("BK_SPEC_W")) spec_w = atoi(e);
   spec_w = spec_w >= 4 ? 4 : (spec_w >= 2 ? 2 : 1);
-  int ctas_per_sm = spec_w == 4 ? 2 : (spec_w == 2 ? 4 : 6);
+  int ctas_per_sm = spec_w == 4 ? 3 : (spec_w == 2 ? 6 : 8);
   if (const char* e = getenv("BK_ASM_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(e));
   int grid = std::min<int64_t>(R, (int64_t)h->sm_count * ctas_per_sm);
   // static shared memory of the kernel + padding = 1/ctas_per_sm of the SM's shared memory
