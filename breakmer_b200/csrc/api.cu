@@ -19,7 +19,7 @@ struct bk_handle_s {
   int device = 0;
   cudaStream_t st = nullptr;
   int sm_count = 148;
-  int spec_width = 4;      // assembler speculation width (bk_set_option)
+  int spec_width = 0;      // assembler speculation width (bk_set_option); 0 = choose per batch
   Arena<false> dev;        // per-call device scratch
   Arena<true> pin;         // per-call pinned host staging / results
   Arena<false> resident;   // bk_batch_upload
@@ -359,7 +359,7 @@ int bk_set_option(bk_handle_t h, const char* name, int64_t value) {
   return guarded(h, [&] {
     if (!name) fail(BK_ERR_ARG, "bk_set_option: null name");
     if (strcmp(name, "spec_width") == 0) {
-      if (value != 1 && value != 2 && value != 4) fail(BK_ERR_ARG, "spec_width must be 1, 2 or 4");
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) fail(BK_ERR_ARG, "spec_width must be 0 (auto), 1, 2, 4 or 8");
       h->spec_width = (int)value;
     } else {
       fail(BK_ERR_ARG, "bk_set_option: unknown option %s", name);

@@ -39,7 +39,7 @@ constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 // the slot was aligned against; otherwise a new round starts there.  The outcome is
 // therefore identical to checking the reads one by one (the prediction is a hint).
 #ifndef ASM_SPEC_W
-#define ASM_SPEC_W 4
+#define ASM_SPEC_W 8     // maximum width (array sizes); the width of a launch is a kernel template argument
 #endif
 
 struct SpecShared {               // command + results of one speculation round (shared memory)
@@ -1129,13 +1129,22 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 // `pad_smem` bytes of dynamic shared memory do nothing but bound the CTAs resident per
 // SM, so that the short k-mer stage kernels of other in-flight batches can still get
 // registers while long assemblies occupy the machine.
+// dynamic shared memory of one CTA: W read buffers, the contig, W-1 predicted contigs,
+// the mer hash, the round mailbox (then padding, see above)
 template <int W>
-__global__ void __launch_bounds__(32 * W, (W >= 4 ? 3 : (W == 2 ? 5 : 8))) assemble_kernel(AsmParams P) {
-  __shared__ __align__(16) uint8_t s_reads[W * ASM_CAP];
-  __shared__ __align__(16) uint8_t s_contig[ASM_CAP];
-  __shared__ __align__(16) uint8_t s_pred[(W > 1 ? W - 1 : 1) * ASM_CAP];
-  __shared__ int32_t s_hash[MER_HASH_SIZE];
-  __shared__ SpecShared sp;
+constexpr size_t assemble_smem_bytes() {
+  return (size_t)W * ASM_CAP + ASM_CAP + (size_t)(W > 1 ? W - 1 : 1) * ASM_CAP + MER_HASH_SIZE * sizeof(int32_t) +
+         ((sizeof(SpecShared) + 15) & ~size_t(15));
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? 3 : (W == 2 ? 5 : 8)))) assemble_kernel(AsmParams P) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* s_reads = smem_raw;
+  uint8_t* s_contig = s_reads + (size_t)W * ASM_CAP;
+  uint8_t* s_pred = s_contig + ASM_CAP;
+  int32_t* s_hash = reinterpret_cast<int32_t*>(s_pred + (size_t)(W > 1 ? W - 1 : 1) * ASM_CAP);
+  SpecShared& sp = *reinterpret_cast<SpecShared*>(s_hash + MER_HASH_SIZE);
   const int64_t slot = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   if (W > 1 && warp > 0) {

@@ -396,17 +396,20 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.so_off = so_off; A.so_mer = so_mer; A.so_cnt = so_cnt; A.seed_order = seed_order;
   A.post_off = post_off; A.post_read = post_read; A.post_pos = post_pos;
   A.work_order = to_device(h, h->dev, order.data(), (size_t)R);
-  // speculation width and residency of the assembler (see assemble_kernel)
+  // speculation width and residency of the assembler (see assemble_kernel).  Auto = 4: one aligning warp per SM
+  // sub-partition; 8 warps share the four ALU pipes of the SM and finish a round no sooner (measured on C4).
   int spec_w = h->spec_width;
   if (const char* e = getenv("BK_SPEC_W")) spec_w = atoi(e);
-  spec_w = spec_w >= 4 ? 4 : (spec_w >= 2 ? 2 : 1);
-  int ctas_per_sm = spec_w == 4 ? 3 : (spec_w == 2 ? 6 : 8);
+  if (spec_w <= 0) spec_w = 4;
+  spec_w = spec_w >= 8 ? 8 : (spec_w >= 4 ? 4 : (spec_w >= 2 ? 2 : 1));
+  int ctas_per_sm = spec_w == 8 ? 1 : (spec_w == 4 ? 3 : (spec_w == 2 ? 6 : 8));
   if (const char* e = getenv("BK_ASM_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(e));
   int grid = std::min<int64_t>(R, (int64_t)h->sm_count * ctas_per_sm);
-  // static shared memory of the kernel + padding = 1/ctas_per_sm of the SM's shared memory
-  const int static_smem = spec_w * ASM_CAP + ASM_CAP + 256;
-  int pad_smem = (int)((227 * 1024) / ctas_per_sm) - static_smem - 1024;
-  if (pad_smem < 0) pad_smem = 0;
+  // dynamic shared memory: what the kernel needs, padded to 1/ctas_per_sm of the SM so residency is bounded
+  const size_t need_smem = spec_w == 8 ? assemble_smem_bytes<8>() : (spec_w == 4 ? assemble_smem_bytes<4>() :
+                           (spec_w == 2 ? assemble_smem_bytes<2>() : assemble_smem_bytes<1>()));
+  int dyn_smem = (int)((227 * 1024) / ctas_per_sm) - 1024;
+  if (dyn_smem < (int)need_smem) dyn_smem = (int)need_smem;
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
@@ -457,15 +460,18 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     if (S_total) BK_CUDA(cudaMemcpyAsync(alive_run, m_alive, S_total, cudaMemcpyDeviceToDevice, st));
     if (R > 0) {
       TimedLaunch t(h->timers, st, KF_ASSEMBLE);
-      if (spec_w == 4) {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
-        assemble_kernel<4><<<grid, 128, pad_smem, st>>>(A);
+      if (spec_w == 8) {
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        assemble_kernel<8><<<grid, 256, dyn_smem, st>>>(A);
+      } else if (spec_w == 4) {
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        assemble_kernel<4><<<grid, 128, dyn_smem, st>>>(A);
       } else if (spec_w == 2) {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
-        assemble_kernel<2><<<grid, 64, pad_smem, st>>>(A);
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        assemble_kernel<2><<<grid, 64, dyn_smem, st>>>(A);
       } else {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_smem));
-        assemble_kernel<1><<<grid, 32, pad_smem, st>>>(A);
+        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        assemble_kernel<1><<<grid, 32, dyn_smem, st>>>(A);
       }
     }
     BK_CUDA(cudaGetLastError());

@@ -148,9 +148,9 @@ int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_res
  * (ms, CUDA events on the handle's stream) and launch count per kernel family since the
  * last bk_kernel_times_reset; names is a ';'-separated list in the same order. */
 int bk_batch_upload(bk_handle_t h, const bk_batch_input* in);
-/* Tuning knobs.  "spec_width" = 1 | 2 | 4: warps per region in the assembler.  4 (default)
- * minimises the latency of one batch; 1 does no speculative work and suits several batches
- * in flight on one device (one handle each).  Results never depend on it. */
+/* Tuning knobs.  "spec_width" = 0 | 1 | 2 | 4 | 8: warps per region in the assembler (how many
+ * reads are aligned speculatively at once).  0 (default) = 4, one aligning warp per SM
+ * sub-partition.  Results never depend on it. */
 int bk_set_option(bk_handle_t h, const char* name, int64_t value);
 int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out);
 int bk_kernel_times(bk_handle_t h, const char** names, const double** ms, const int64_t** launches, int32_t* n);

@@ -89,3 +89,35 @@ def test_long_reads_use_the_blocked_dp(handle):
     regions = [synth.make_region("lr%d" % i, seed=700 + i, L=3000, cov=120, k=21, e=0.01,
                                  event=("del", 200, None), rl=300, rl_jitter=40) for i in range(3)]
     check_batch(handle, regions)
+
+
+def test_results_do_not_depend_on_speculation_width(handle):
+    from breakmer_b200 import batch
+    regions = list(synth.config_regions("C2", n=16, start=40)) + [synth.config_region("C1", 0)]
+    pk = batch.PackedBatch(regions)
+    ref = None
+    try:
+        for w in (1, 2, 4, 8):
+            handle.set_option("spec_width", w)
+            out = batch.run(handle, pk)
+            got = [(out.sample_only(i), out.contig_records(i)) for i in range(len(regions))]
+            if ref is None:
+                ref = got
+                for i, r in enumerate(regions):
+                    only, ctg = oracle_region(r)
+                    assert got[i] == (only, ctg)
+            else:
+                assert got == ref, "spec_width %d changed the result" % w
+    finally:
+        handle.set_option("spec_width", 0)
+
+
+def test_capacity_error_is_reported_per_call(handle):
+    from breakmer_b200 import _lib, batch
+    r = synth.Region(name="long", k=15, ref_fwd="ACGT" * 50, reads=[("@a:1:1:1:1/1_0", "ACGT" * 1100, "I" * 4400, False)],
+                     sc_records=[("a", "ACGT" * 10)])
+    with pytest.raises(_lib.BreakmerError) as e:
+        batch.run(handle, batch.PackedBatch([r]))
+    assert e.value.code == _lib.BK_ERR_CAPACITY
+    # the handle stays usable
+    check_batch(handle, [synth.config_region("C2", 7)])
