@@ -270,6 +270,7 @@ int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int
       }
     }
     const int64_t n_bases = n_rec ? rec_off[n_rec] - rec_off[0] : 0;
+    if (n_bases >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "bk_count_kmers: more than 2^31 bases in one call");
     off.push_back(n_bases);
     if (n_bases == 0) return;
     EmitParams E{};

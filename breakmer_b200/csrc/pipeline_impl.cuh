@@ -179,9 +179,13 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   memset(out, 0, sizeof *out);
   Pipeline local;
   Pipeline* pp;
-  cudaEvent_t ev0, ev1;
-  BK_CUDA(cudaEventCreate(&ev0));
-  BK_CUDA(cudaEventCreate(&ev1));
+  struct EventPair {                       // destroyed on every exit path, including exceptions
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } evs;
+  BK_CUDA(cudaEventCreate(&evs.a));
+  BK_CUDA(cudaEventCreate(&evs.b));
+  cudaEvent_t ev0 = evs.a, ev1 = evs.b;
   BK_CUDA(cudaEventRecord(ev0, st));
   if (resident) {
     if (!h->pipe) fail(BK_ERR_ARG, "bk_compare_kmers_resident: no batch uploaded");
@@ -259,6 +263,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     BK_CUDA(cudaMemcpyAsync(so_off, p.in_mers_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   } else {
     const int64_t n_keys = 2 * p.ref.n_bases + p.reads.n_bases + p.sc.n_bases + p.normal.n_bases;
+    if (n_keys >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows; use fewer regions per call");
     out->n_kmer_occurrences = n_keys;
     uint64_t* keys = h->dev.get<uint64_t>(n_keys);
     uint32_t* vals = h->dev.get<uint32_t>(n_keys);
@@ -558,8 +563,6 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   BK_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
   BK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   out->gpu_ms = ms;
 
   // contigs left the device in completion order; the table below puts them in
