@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--regions", type=int, default=0, help="override regions per GPU (debugging)")
     ap.add_argument("--spec-width", type=int, default=0, help="assembler warps per region (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) kept on the device at once")
+    ap.add_argument("--inflight", type=int, default=6, help="independent batches (steps) kept on the device at once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
