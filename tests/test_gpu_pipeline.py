@@ -121,3 +121,30 @@ def test_capacity_error_is_reported_per_call(handle):
     assert e.value.code == _lib.BK_ERR_CAPACITY
     # the handle stays usable
     check_batch(handle, [synth.config_region("C2", 7)])
+
+
+def _mutated(region, fn):
+    reads = [(rid, fn(i, seq), qual, io) for i, (rid, seq, qual, io) in enumerate(region.reads)]
+    return synth.Region(name=region.name + "_m", k=region.k, ref_fwd=region.ref_fwd, reads=reads,
+                        sc_records=region.sc_records, normal_reads=region.normal_reads)
+
+
+def test_odd_inputs_lowercase_n_rich_and_duplicates(handle):
+    base = [synth.make_region("odd%d" % i, seed=1200 + i, L=1500, cov=150, k=15, e=0.01,
+                              event=[("del", 120, None), ("ins", 40), ("tdup", 200)][i], indel_p=0.3) for i in range(3)]
+    # lower-case reads: jellyfish folds case when counting, str.find/== in the assembler do not
+    lower = _mutated(base[0], lambda i, s: s.lower() if i % 5 == 0 else s)
+    # N-rich reads: 'N' == 'N' scores as a match in olc.nw, windows with N never match a k-mer
+    nrich = _mutated(base[1], lambda i, s: (s[:20] + "NNNN" + s[24:]) if i % 3 == 0 else s)
+    # every record four times: multiplicities, counts and support vectors scale
+    dup = synth.Region(name="dup", k=15, ref_fwd=base[2].ref_fwd,
+                       reads=[(rid + "x%d" % j if j else rid, s, q, io) for (rid, s, q, io) in base[2].reads for j in range(4)],
+                       sc_records=base[2].sc_records)
+    check_batch(handle, [lower, nrich, dup] + base)
+
+
+@pytest.mark.parametrize("k", [11, 25, 31])
+def test_other_k(handle, k):
+    regions = [synth.make_region("k%d_%d" % (k, i), seed=1300 + i, L=1200, cov=120, k=k, e=0.005,
+                                 event=("del", 150, None), indel_p=0.2) for i in range(3)]
+    check_batch(handle, regions)
