@@ -77,8 +77,8 @@ struct SelectOut {
   uint32_t* seg_counts;   // device, n_seg (or null)
 };
 
-SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int tag_bits, int seg_bits,
-                          int mode, int64_t n_seg) {
+SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int seg_bits, int mode,
+                          int64_t n_seg) {
   SelectOut o{nullptr, nullptr, 0, nullptr};
   cudaStream_t st = h->st;
   if (n_seg > 0) {
@@ -94,10 +94,10 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
   sc.scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(256 * tiles));
   uint64_t* sk;
   uint32_t* sv;
-  const int key_bits = 2 * k + tag_bits + seg_bits + 1;   // +1: the all-ones invalid key sorts last
+  const int key_bits = 2 * k + seg_bits + 1;   // +1: the all-ones invalid key sorts last
   radix_sort_pairs(keys, vals, n, key_bits, sc, st, &sk, &sv, h->timers);
   RunParams rp{};
-  rp.keys = sk; rp.vals = sv; rp.n = n; rp.tag_bits = tag_bits; rp.k = k; rp.mode = mode;
+  rp.keys = sk; rp.vals = sv; rp.n = n; rp.k = k; rp.mode = mode;
   rp.flags = h->dev.get<uint32_t>(n);
   rp.run_count = h->dev.get<uint32_t>(n);
   uint32_t* pos = h->dev.get<uint32_t>(n);
@@ -279,14 +279,14 @@ int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int
     E.rec_off = to_device(h, h->dev, off.data(), off.size());
     E.n_rec = (int64_t)off.size() - 1;
     E.rec_mult = rec_mult ? to_device(h, h->dev, mult.data(), mult.size()) : nullptr;
-    E.k = k; E.tag = 0; E.tag_bits = 0; E.emit_rc = 0;
+    E.k = k; E.tag = 0; E.emit_rc = 0;
     E.keys = h->dev.get<uint64_t>(n_bases);
     E.vals = h->dev.get<uint32_t>(n_bases);
     {
       TimedLaunch t(h->timers, h->st, KF_EMIT);
       kmer_emit_kernel<<<(unsigned)((n_bases + EMIT_TILE - 1) / EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
     }
-    SelectOut so = sort_and_select(h, E.keys, E.vals, n_bases, k, 0, 0, SELECT_ALL, 0);
+    SelectOut so = sort_and_select(h, E.keys, E.vals, n_bases, k, 0, SELECT_ALL, 0);
     uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
     uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
     if (so.n) {
@@ -304,7 +304,7 @@ int bk_sample_only(bk_handle_t h, int k, const uint64_t* case_mers, const uint32
                    int64_t* n_out) {
   return guarded(h, [&] {
     if (!mers || !counts || !n_out) fail(BK_ERR_ARG, "bk_sample_only: null output");
-    if (k < 1 || k > 30) fail(BK_ERR_ARG, "bk_sample_only: k must be in 1..30");
+    if (k < 1 || k > 31) fail(BK_ERR_ARG, "bk_sample_only: k must be in 1..31");
     if ((n_case && (!case_mers || !case_counts)) || (n_sc && !sc_mers) || (n_ref && !ref_mers) || (n_normal && !normal_mers))
       fail(BK_ERR_ARG, "bk_sample_only: null input");
     h->dev.reset();
@@ -317,13 +317,16 @@ int bk_sample_only(bk_handle_t h, int k, const uint64_t* case_mers, const uint32
     uint64_t* hk = h->pin.get<uint64_t>(n);
     uint32_t* hv = h->pin.get<uint32_t>(n);
     int64_t w = 0;
-    for (int64_t i = 0; i < n_case; ++i, ++w) { hk[w] = (case_mers[i] << 2) | TAG_CASE; hv[w] = case_counts[i]; }
-    for (int64_t i = 0; i < n_sc; ++i, ++w) { hk[w] = (sc_mers[i] << 2) | TAG_SC; hv[w] = 1; }
-    for (int64_t i = 0; i < n_ref; ++i, ++w) { hk[w] = (ref_mers[i] << 2) | TAG_REF; hv[w] = 1; }
-    for (int64_t i = 0; i < n_normal; ++i, ++w) { hk[w] = (normal_mers[i] << 2) | TAG_NORMAL; hv[w] = 1; }
+    for (int64_t i = 0; i < n_case; ++i, ++w) {
+      if (case_counts[i] >= (1u << 30)) fail(BK_ERR_CAPACITY, "bk_sample_only: a count exceeds 2^30");
+      hk[w] = case_mers[i]; hv[w] = case_counts[i] | ((uint32_t)TAG_CASE << 30);
+    }
+    for (int64_t i = 0; i < n_sc; ++i, ++w) { hk[w] = sc_mers[i]; hv[w] = 1u | ((uint32_t)TAG_SC << 30); }
+    for (int64_t i = 0; i < n_ref; ++i, ++w) { hk[w] = ref_mers[i]; hv[w] = 1u | ((uint32_t)TAG_REF << 30); }
+    for (int64_t i = 0; i < n_normal; ++i, ++w) { hk[w] = normal_mers[i]; hv[w] = 1u | ((uint32_t)TAG_NORMAL << 30); }
     uint64_t* dk = to_device(h, h->dev, hk, (size_t)n);
     uint32_t* dv = to_device(h, h->dev, hv, (size_t)n);
-    SelectOut so = sort_and_select(h, dk, dv, n, k, 2, 0, SELECT_SAMPLE_ONLY, 0);
+    SelectOut so = sort_and_select(h, dk, dv, n, k, 0, SELECT_SAMPLE_ONLY, 0);
     uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
     uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
     if (so.n) {

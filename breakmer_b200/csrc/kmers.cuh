@@ -9,7 +9,7 @@
 //                      of every window is emitted too -- that is the second
 //                      FASTA the reference writes and counts for the target
 //                      (utils.py:367-371, sv_processor.py:613-615).
-//   (radix_sort.cuh)   G3: sort by (region, mer, set tag)
+//   (radix_sort.cuh)   G3: sort by (region, mer); the set tag travels in the value
 //   run_select_kernel  G3+G4: one pass over the sorted keys does the run-length
 //                      count AND the set algebra of sv_processor.py:621-622:
 //                      all occurrences of a (region, mer) are adjacent whatever
@@ -17,8 +17,8 @@
 //                      is a property of the run.
 //   run_scatter_kernel compaction of the selected runs to (mer, count) arrays.
 //
-// Key layout (tag_bits = 2 for the batched path, 0 for plain counting):
-//      [ 0 | region | mer (2k bits) | set tag ]
+// Key layout:    [ 0 | region | mer (2k bits) ]          (one spare top bit: the all-ones invalid key sorts last)
+// Value layout:  [ set tag : 2 | multiplicity : 30 ]
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -40,8 +40,9 @@ struct EmitParams {
   const uint32_t* rec_mult;   // multiplicity of each record, or null (all 1)
   int k;
   int tag;
-  int tag_bits;
   int emit_rc;
+  int64_t off_shift;          // rec_off values are relative to `bases` after subtracting this (region chunks)
+  int seg_shift;              // region ids are stored relative to this (region chunks)
   uint64_t* keys;             // [out_base + p] forward, [out_base_rc + p] reverse complement
   uint32_t* vals;
   int64_t out_base, out_base_rc;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
     int64_t lo = 0, hi = P.n_rec;           // rec_off[lo] <= p0 < rec_off[hi]
     while (hi - lo > 1) {
       const int64_t mid = (lo + hi) >> 1;
-      if (P.rec_off[mid] <= p0) lo = mid; else hi = mid;
+      if (P.rec_off[mid] - P.off_shift <= p0) lo = mid; else hi = mid;
     }
     s_rfirst = lo;
   }
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
   const int64_t rfirst = s_rfirst;
   const int64_t lim = p0 + EMIT_TILE + k - 1;
   for (int64_t r = rfirst + 1 + tid; r < P.n_rec; r += EMIT_THREADS) {
-    const int64_t o = P.rec_off[r];
+    const int64_t o = P.rec_off[r] - P.off_shift;
     if (o >= lim) break;
     code[o - p0] |= 8;                       // a record starts here
   }
@@ -100,15 +101,16 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
     uint64_t seg = 0;
     uint32_t mult = 1;
     if (ok) {
-      if (P.rec_seg) seg = (uint64_t)P.rec_seg[rec];
+      if (P.rec_seg) seg = (uint64_t)(P.rec_seg[rec] - P.seg_shift);
       if (P.rec_mult) mult = P.rec_mult[rec];
     }
     const uint64_t hi = seg << (2 * k);
-    P.keys[P.out_base + p] = ok ? (((hi | fwd) << P.tag_bits) | (uint64_t)P.tag) : KEY_INVALID;
-    P.vals[P.out_base + p] = mult;
+    const uint32_t v = (mult & 0x3FFFFFFFu) | ((uint32_t)P.tag << 30);
+    P.keys[P.out_base + p] = ok ? (hi | fwd) : KEY_INVALID;
+    P.vals[P.out_base + p] = v;
     if (P.emit_rc) {
-      P.keys[P.out_base_rc + p] = ok ? (((hi | rc) << P.tag_bits) | (uint64_t)P.tag) : KEY_INVALID;
-      P.vals[P.out_base_rc + p] = mult;
+      P.keys[P.out_base_rc + p] = ok ? (hi | rc) : KEY_INVALID;
+      P.vals[P.out_base_rc + p] = v;
     }
   }
 }
@@ -120,7 +122,6 @@ struct RunParams {
   const uint64_t* keys;       // sorted
   const uint32_t* vals;
   int64_t n;
-  int tag_bits;
   int k;
   int mode;
   uint32_t* flags;            // n : 1 at the head of a selected run
@@ -138,17 +139,15 @@ __global__ void __launch_bounds__(256) run_select_kernel(RunParams P) {
   const uint64_t key = P.keys[i];
   uint32_t flag = 0, total = 0;
   if (key != KEY_INVALID) {
-    const uint64_t g = key >> P.tag_bits;
-    const bool head = (i == 0) || ((P.keys[i - 1] >> P.tag_bits) != g);
+    const bool head = (i == 0) || (P.keys[i - 1] != key);
     if (head) {
-      const uint64_t tmask = (1ull << P.tag_bits) - 1ull;
       uint32_t c_case = 0;
       unsigned seen = 0;
       for (int64_t j = i; j < P.n; ++j) {
-        const uint64_t kj = P.keys[j];
-        if (kj == KEY_INVALID || (kj >> P.tag_bits) != g) break;
-        const unsigned tag = (unsigned)(kj & tmask);
-        const uint32_t v = P.vals[j];
+        if (P.keys[j] != key) break;
+        const uint32_t vv = P.vals[j];
+        const unsigned tag = vv >> 30;
+        const uint32_t v = vv & 0x3FFFFFFFu;
         seen |= 1u << tag;
         total += v;
         if (tag == TAG_CASE) c_case += v;
@@ -172,7 +171,7 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(RunParams P) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
   if (!P.flags[i]) return;
-  const uint64_t g = P.keys[i] >> P.tag_bits;
+  const uint64_t g = P.keys[i];
   const uint64_t mer = g & ((P.k == 32) ? ~0ull : ((1ull << (2 * P.k)) - 1ull));
   const uint32_t dst = P.pos[i];
   P.out_mers[dst] = mer;

@@ -30,6 +30,8 @@ struct RecordSet {          // one of: reads, soft clips, normal reads (device c
   const int64_t* koff = nullptr;
   const int32_t* kseg = nullptr;
   int64_t kn_rec = 0;
+  // host copies of the region boundaries (bases, compacted records): the k-mer stage may run in region chunks
+  std::vector<int64_t> reg_base, reg_krec;
 };
 
 struct Pipeline {
@@ -68,8 +70,12 @@ void upload_record_set(bk_handle_t h, Arena<false>& A, const char* bases, const 
   std::vector<int64_t> koff;
   koff.reserve(n_rec + 1);
   kseg.reserve(n_rec + 1);
+  rs.reg_base.assign(n_regions + 1, 0);
+  rs.reg_krec.assign(n_regions + 1, 0);
   for (int r = 0; r < n_regions; ++r) {
     if (reg_off[r + 1] < reg_off[r]) fail(BK_ERR_ARG, "batch: %s region offsets not monotone", what);
+    rs.reg_base[r] = off[reg_off[r]];
+    rs.reg_krec[r] = (int64_t)koff.size();
     for (int64_t i = reg_off[r]; i < reg_off[r + 1]; ++i) {
       seg[i] = r;
       if (off[i + 1] < off[i]) fail(BK_ERR_ARG, "batch: %s record offsets not monotone", what);
@@ -77,6 +83,8 @@ void upload_record_set(bk_handle_t h, Arena<false>& A, const char* bases, const 
     }
   }
   const int64_t n_bases = off[n_rec];
+  rs.reg_base[n_regions] = n_bases;
+  rs.reg_krec[n_regions] = (int64_t)koff.size();
   koff.push_back(n_bases);
   if (n_bases > 0 && !bases) fail(BK_ERR_ARG, "batch: %s bases missing", what);
   rs.n_bases = n_bases;
@@ -96,11 +104,6 @@ void pipeline_upload_into(bk_handle_t h, Arena<false>& A, const bk_batch_input* 
   if (in->k < 2 || in->k > 31) fail(BK_ERR_ARG, "batch: k must be in 2..31");
   const int R = in->n_regions;
   p.n_regions = R; p.k = in->k; p.rc_thresh = in->rc_thresh; p.have_mers = in->have_mers;
-  if (!in->have_mers) {
-    const int seg_bits = bits_for((uint64_t)R);
-    if (2 * in->k + 2 + seg_bits + 1 > 64)
-      fail(BK_ERR_ARG, "batch: k=%d with %d regions does not fit the 64-bit sort key; use fewer regions per call", in->k, R);
-  }
   if (!in->read_off || !in->read_reg_off) fail(BK_ERR_ARG, "batch: read arrays missing");
   upload_record_set(h, A, in->read_bases, in->read_off, in->read_reg_off, R, p.reads, p.h2d_bytes, "read");
   p.read_reg_off = to_device(h, A, in->read_reg_off, (size_t)R + 1);
@@ -161,15 +164,19 @@ const T* to_host(bk_handle_t h, const T* d, size_t n) {
 
 inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-void emit_set(bk_handle_t h, const RecordSet& rs, int k, int tag, bool rc, uint64_t* keys, uint32_t* vals, int64_t base,
-              int64_t base_rc) {
-  if (rs.n_bases == 0) return;
+// k-mer windows of the records of regions [r0, r1) of one input set
+void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag, bool rc, uint64_t* keys, uint32_t* vals,
+              int64_t base, int64_t base_rc) {
+  if (rs.reg_base.empty()) return;
+  const int64_t b0 = rs.reg_base[r0], b1 = rs.reg_base[r1];
+  if (b1 == b0) return;
+  const int64_t kr0 = rs.reg_krec[r0], kr1 = rs.reg_krec[r1];
   EmitParams E{};
-  E.bases = rs.bases; E.n_bases = rs.n_bases; E.rec_off = rs.koff; E.n_rec = rs.kn_rec; E.rec_seg = rs.kseg;
-  E.rec_mult = nullptr; E.k = k; E.tag = tag; E.tag_bits = 2; E.emit_rc = rc ? 1 : 0;
+  E.bases = rs.bases + b0; E.n_bases = b1 - b0; E.rec_off = rs.koff + kr0; E.n_rec = kr1 - kr0; E.rec_seg = rs.kseg + kr0;
+  E.rec_mult = nullptr; E.k = k; E.tag = tag; E.emit_rc = rc ? 1 : 0; E.off_shift = b0; E.seg_shift = r0;
   E.keys = keys; E.vals = vals; E.out_base = base; E.out_base_rc = base_rc;
   TimedLaunch t(h->timers, h->st, KF_EMIT);
-  kmer_emit_kernel<<<nblk(rs.n_bases, EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
+  kmer_emit_kernel<<<nblk(E.n_bases, EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
 }
 
 void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_batch_result* out) {
@@ -263,26 +270,58 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     BK_CUDA(cudaMemcpyAsync(so_off, p.in_mers_off, (R + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   } else {
     const int64_t n_keys = 2 * p.ref.n_bases + p.reads.n_bases + p.sc.n_bases + p.normal.n_bases;
-    if (n_keys >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows; use fewer regions per call");
     out->n_kmer_occurrences = n_keys;
-    uint64_t* keys = h->dev.get<uint64_t>(n_keys);
-    uint32_t* vals = h->dev.get<uint32_t>(n_keys);
-    int64_t at = 0;
-    emit_set(h, p.ref, k, TAG_REF, true, keys, vals, at, at + p.ref.n_bases);   // forward + reverse FASTA (Q2)
-    at += 2 * p.ref.n_bases;
-    emit_set(h, p.reads, k, TAG_CASE, false, keys, vals, at, 0);                // every record, duplicates included (Q3)
-    at += p.reads.n_bases;
-    emit_set(h, p.sc, k, TAG_SC, false, keys, vals, at, 0);
-    at += p.sc.n_bases;
-    emit_set(h, p.normal, k, TAG_NORMAL, false, keys, vals, at, 0);             // K4
-    SelectOut so = sort_and_select(h, keys, vals, n_keys, k, 2, bits_for((uint64_t)R), SELECT_SAMPLE_ONLY, R);
-    S_total = so.n;
-    so_mer = so.mers; so_cnt = so.counts;
+    // The sort key is [0 | region | mer]: 2k + region bits + 1 <= 64.  Large k leaves few region bits, so the stage runs
+    // over chunks of regions (one chunk for the usual k); selected mers come out in (region, mer) order either way.
+    const int max_seg_bits = 63 - 2 * k;
+    const int chunk = (int)std::min<int64_t>(R > 0 ? R : 1, int64_t(1) << std::min(max_seg_bits, 16));
+    struct ChunkOut { SelectOut so; int r0, r1; };
+    std::vector<ChunkOut> chunks;
+    uint32_t* seg_counts_all = dev_zero<uint32_t>(h, (size_t)R + 1);
+    auto span = [&](const RecordSet& rs, int r0, int r1) { return rs.reg_base.empty() ? int64_t(0) : rs.reg_base[r1] - rs.reg_base[r0]; };
+    for (int r0 = 0; r0 < R; r0 += chunk) {
+      const int r1 = std::min(R, r0 + chunk);
+      const int64_t nr = span(p.ref, r0, r1), nd = span(p.reads, r0, r1), ns = span(p.sc, r0, r1), nn = span(p.normal, r0, r1);
+      const int64_t nk = 2 * nr + nd + ns + nn;
+      if (nk >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows in one chunk; use fewer regions per call");
+      uint64_t* keys = h->dev.get<uint64_t>(nk);
+      uint32_t* vals = h->dev.get<uint32_t>(nk);
+      int64_t at = 0;
+      emit_set(h, p.ref, r0, r1, k, TAG_REF, true, keys, vals, at, at + nr);      // forward + reverse FASTA (Q2)
+      at += 2 * nr;
+      emit_set(h, p.reads, r0, r1, k, TAG_CASE, false, keys, vals, at, 0);        // every record, duplicates included (Q3)
+      at += nd;
+      emit_set(h, p.sc, r0, r1, k, TAG_SC, false, keys, vals, at, 0);
+      at += ns;
+      emit_set(h, p.normal, r0, r1, k, TAG_NORMAL, false, keys, vals, at, 0);     // K4
+      ChunkOut co;
+      co.so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0);
+      co.r0 = r0; co.r1 = r1;
+      BK_CUDA(cudaMemcpyAsync(seg_counts_all + r0, co.so.seg_counts, (size_t)(r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      chunks.push_back(co);
+    }
+    if (chunks.size() == 1) {
+      S_total = chunks[0].so.n;
+      so_mer = chunks[0].so.mers; so_cnt = chunks[0].so.counts;
+    } else {
+      for (auto& c : chunks) S_total += c.so.n;
+      uint64_t* all_m = h->dev.get<uint64_t>(S_total);
+      uint32_t* all_c = h->dev.get<uint32_t>(S_total);
+      int64_t at = 0;
+      for (auto& c : chunks) {
+        if (c.so.n) {
+          BK_CUDA(cudaMemcpyAsync(all_m + at, c.so.mers, c.so.n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+          BK_CUDA(cudaMemcpyAsync(all_c + at, c.so.counts, c.so.n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        }
+        at += c.so.n;
+      }
+      so_mer = all_m; so_cnt = all_c;
+    }
     uint32_t* seg_excl = h->dev.get<uint32_t>(R + 1);
     uint32_t* d_tot = h->dev.get<uint32_t>(1);
     uint32_t* stmp = h->dev.get<uint32_t>(scan_tmp_elems(R));
     TimedLaunch t(h->timers, st, KF_SCAN, 4);
-    exclusive_scan_u32(so.seg_counts, seg_excl, R, stmp, d_tot, st);
+    exclusive_scan_u32(seg_counts_all, seg_excl, R, stmp, d_tot, st);
     widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_tot, R, so_off);
   }
 
