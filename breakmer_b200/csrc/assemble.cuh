@@ -38,6 +38,9 @@ constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 // is used only if the actual contig at that moment is byte-identical to the contig
 // the slot was aligned against; otherwise a new round starts there.  The outcome is
 // therefore identical to checking the reads one by one (the prediction is a hint).
+#ifndef ASM_W4_CTAS
+#define ASM_W4_CTAS 3
+#endif
 #ifndef ASM_SPEC_W
 #define ASM_SPEC_W 8     // maximum width (array sizes); the width of a launch is a kernel template argument
 #endif
@@ -55,7 +58,7 @@ struct SpecShared {               // command + results of one speculation round 
 };
 
 // optional phase timing (-DBK_PHASE_PROF, experiments only): cycles per phase, summed over regions
-enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_STAGE, PH_TOTAL, PH_MAXREGION, PH_COUNT_ };
+enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_PREDICT, PH_TOTAL, PH_MAXREGION, PH_COUNT_ };
 #if defined(BK_PHASE_PROF) && !defined(BK_SIM)
 #define BK_PH_BEGIN long long _ph_t0 = clock64();
 #define BK_PH_END(c, ph) (c).ph_cycles[ph] += clock64() - _ph_t0;
@@ -259,13 +262,11 @@ BK_DEV int find_mer(const RegionCtx& c, uint64_t code) {
 }
 
 BK_DEV int stage_read(RegionCtx& c, int u) {
-  BK_PH_BEGIN
   const int n = c.read_len_of(u);
   const uint8_t* src = c.read_ptr(u);
   syncwarp();
   for (int x = lane(); x < n; x += WARP) c.s_read[x] = src[x];
   syncwarp();
-  BK_PH_END(c, PH_STAGE)
   return n;
 }
 BK_DEV void sync_contig_to_smem(RegionCtx& c) {
@@ -611,7 +612,7 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
       if (lane() == 0) { sp->abuf[w] = buf; sp->la[w] = la; }
     }
     syncwarp();
-    BK_PH_END(c, PH_STAGE)
+    BK_PH_END(c, PH_PREDICT)
   }
   // 3. every warp aligns its read against its contig
 #ifdef BK_SIM
@@ -1138,7 +1139,7 @@ constexpr size_t assemble_smem_bytes() {
 }
 
 template <int W>
-__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? 3 : (W == 2 ? 5 : 8)))) assemble_kernel(AsmParams P) {
+__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : 8)))) assemble_kernel(AsmParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* s_reads = smem_raw;
   uint8_t* s_contig = s_reads + (size_t)W * ASM_CAP;

@@ -536,7 +536,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   out->n_check_align = (int64_t)h_stats[0];
   out->n_dp_cells = (int64_t)h_stats[1];
   if (getenv("BK_PHASE_PRINT")) {
-    static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "stage", "total", "max_region"};
+    static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "predict", "total", "max_region"};
     for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
     fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu rounds %llu slots %llu\n", h_stats[2], h_stats[3], h_stats[0],
             h_stats[4], h_stats[5]);
@@ -576,7 +576,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       }
       for (int t = 0; t < 4 && t < R; ++t) {
         const unsigned long long* q = &pr[(size_t)ids[t] * 12];
-        fprintf(stderr, "region %d (U=%lld S=%lld): total %llu nw %llu find %llu kmers %llu finalize %llu emit %llu stage %llu\n", ids[t],
+        fprintf(stderr, "region %d (U=%lld S=%lld): total %llu nw %llu find %llu kmers %llu finalize %llu emit %llu predict %llu\n", ids[t],
                 (long long)(h_u_off[ids[t] + 1] - h_u_off[ids[t]]), (long long)(h_so_off[ids[t] + 1] - h_so_off[ids[t]]), q[6], q[0], q[1],
                 q[2], q[3], q[4], q[5]);
       }
