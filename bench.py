@@ -124,6 +124,20 @@ def _cpu_region_by_index(args):
     return n_only, n_ctg, time.time() - t0
 
 
+def cpu_c_nw_single(regions, max_regions=40):
+    """Context only: the same oracle with its C restatement of olc.nw (what a compiled single-core port of the
+    reference would roughly do)."""
+    from oracle import assembler_py, kmers_py
+    t0 = time.time()
+    done = 0
+    for r in regions[:max_regions]:
+        normal = [x[1] for x in r.normal_reads] if r.normal_reads else None
+        _r, _c, _s, only = kmers_py.sample_only(r.ref_fwd, [x[1] for x in r.reads], [x[1] for x in r.sc_records], r.k, normal)
+        assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
+        done += 1
+    return done / (time.time() - t0)
+
+
 def cpu_baseline_single(workload, regions, budget_s=20.0, max_regions=8):
     t0 = time.time()
     done = 0
@@ -213,7 +227,7 @@ def gpu_arm(args):
     if args.regions:
         per_gpu = args.regions
     regions = make_regions(args.workload, per_gpu, rank)
-    pk = batch.PackedBatch(regions)
+    pk = batch.PackedBatch(regions).pin()        # pinned host buffers for the end-to-end leg
     h = _lib.Handle(local_rank)
     hbm_peak, peak_src = load_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -399,6 +413,7 @@ def gpu_arm(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(args.workload, regions)
+        line["cpu_baseline"]["value_with_c_nw_for_context"] = cpu_c_nw_single(regions)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

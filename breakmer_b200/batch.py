@@ -58,6 +58,18 @@ class PackedBatch:
         self.in_mers = self.in_counts = self.in_mers_off = None
         self.read_len = None
 
+    def pin(self):
+        """Move the host arrays to page-locked memory (through torch, which is only plumbing here) so that the
+        library's host->device copies are true asynchronous DMA transfers."""
+        import torch
+        for name in ("ref_bases", "ref_off", "read_bases", "read_off", "read_reg_off", "read_flags", "sc_bases", "sc_off",
+                     "sc_reg_off", "normal_bases", "normal_off", "normal_reg_off", "in_mers", "in_counts", "in_mers_off",
+                     "read_len"):
+            a = getattr(self, name)
+            if a is not None and a.size:
+                setattr(self, name, torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy())
+        return self
+
     def set_mers(self, per_region_mers):
         """init_assembly shape: give each region's sample-only {mer: count} instead of
         running the k-mer stage."""
