@@ -67,7 +67,7 @@ class PackedBatch:
                      "read_len"):
             a = getattr(self, name)
             if a is not None and a.size:
-                setattr(self, name, torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy())
+                setattr(self, name, torch.from_numpy(np.array(a, copy=True)).pin_memory().numpy())
         return self
 
     def set_mers(self, per_region_mers):

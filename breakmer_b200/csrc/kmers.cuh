@@ -83,20 +83,36 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
   for (int q = 0; q < EMIT_PER_THREAD; ++q) cnt += (code[xb + q] >> 3) & 1u;
   uint32_t total;
   uint32_t run = block_excl_scan(cnt, &total);
+  // the thread's EMIT_PER_THREAD consecutive windows share k-1 bases: build the first
+  // window (k loads), then roll (one load per further window)
+  const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+  uint64_t fwd = 0, rc = 0;
+  int bad = 0;
 #pragma unroll
   for (int q = 0; q < EMIT_PER_THREAD; ++q) {
     const int x = xb + q;
     run += (code[x] >> 3) & 1u;
     const int64_t p = p0 + x;
     if (p >= P.n_bases) break;
-    uint64_t fwd = 0, rc = 0;
-    bool ok = true;
-    for (int t = 0; t < k; ++t) {
-      const unsigned c = code[x + t];
-      ok = ok && !(c & 4u) && !(t > 0 && (c & 8u));
-      fwd = (fwd << 2) | (c & 3u);
-      rc |= (uint64_t)(3u - (c & 3u)) << (2 * t);
+    // `bad` = how many consecutive windows, starting with the current one, are ruled out by positions seen so
+    // far: an invalid base at relative position t rules out windows 0..t, a record start at t >= 1 windows 0..t-1
+    if (q == 0) {
+      for (int t = 0; t < k; ++t) {
+        const unsigned c = code[x + t];
+        fwd = (fwd << 2) | (c & 3u);
+        rc |= (uint64_t)(3u - (c & 3u)) << (2 * t);
+        const int b = (c & 4u) ? t + 1 : ((t > 0 && (c & 8u)) ? t : 0);
+        bad = b > bad ? b : bad;
+      }
+    } else {
+      const unsigned c = code[x + k - 1];
+      fwd = ((fwd << 2) | (c & 3u)) & kmask;
+      rc = (rc >> 2) | ((uint64_t)(3u - (c & 3u)) << (2 * (k - 1)));
+      bad = bad > 0 ? bad - 1 : 0;
+      const int b = (c & 4u) ? k : (((c & 8u) && k > 1) ? k - 1 : 0);
+      bad = b > bad ? b : bad;
     }
+    const bool ok = bad == 0;
     const int64_t rec = rfirst + run;
     uint64_t seg = 0;
     uint32_t mult = 1;
