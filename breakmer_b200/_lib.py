@@ -91,9 +91,11 @@ def load():
                                     POINTER(c_int32)]
     lib.bk_kernel_times_reset.argtypes = [H, c_int]
     lib.bk_set_option.argtypes = [H, c_char_p, c_int64]
+    lib.bk_ref_cache_build.argtypes = [H, c_void_p, c_void_p, c_int32, c_int32]
+    lib.bk_ref_cache_clear.argtypes = [H]
     for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_count_kmers", "bk_sample_only",
                  "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
-                 "bk_kernel_times_reset", "bk_set_option"):
+                 "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear"):
         getattr(lib, name).restype = c_int
     _lib = lib
     return lib
@@ -102,7 +104,7 @@ def load():
 EXPORTED_SYMBOLS = (
     "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_count_kmers",
     "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
-    "bk_kernel_times_reset", "bk_set_option")
+    "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear")
 
 
 def _ptr(a):
@@ -194,6 +196,13 @@ class Handle:
         if n.value == 0:
             return np.zeros(0, np.uint64), np.zeros(0, np.uint32)
         return (np.ctypeslib.as_array(pm, shape=(n.value,)).copy(), np.ctypeslib.as_array(pc, shape=(n.value,)).copy())
+
+    def ref_cache_build(self, ref_seqs, k):
+        data, off = concat(ref_seqs)
+        self._check(self.lib.bk_ref_cache_build(self.h, _ptr(data), _ptr(off), len(ref_seqs), int(k)))
+
+    def ref_cache_clear(self):
+        self._check(self.lib.bk_ref_cache_clear(self.h))
 
     def set_option(self, name, value):
         self._check(self.lib.bk_set_option(self.h, name.encode(), int(value)))

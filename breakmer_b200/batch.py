@@ -23,7 +23,7 @@ def _concat(seqs):
 class PackedBatch:
     """Host arrays of one batch (kept alive for the duration of the calls)."""
 
-    def __init__(self, regions, rc_thresh=None, with_normal=None):
+    def __init__(self, regions, rc_thresh=None, with_normal=None, with_ref=True):
         self.n = len(regions)
         ks = {r.k for r in regions}
         if len(ks) > 1:
@@ -31,7 +31,8 @@ class PackedBatch:
         self.k = ks.pop() if ks else 15
         self.rc_thresh = int(rc_thresh if rc_thresh is not None else (regions[0].rc_thresh if regions else 2))
         self.names = [getattr(r, "name", str(i)) for i, r in enumerate(regions)]
-        self.ref_bases, self.ref_off = _concat([r.ref_fwd for r in regions])
+        self.with_ref = with_ref          # False: the handle's reference k-mer cache is used (Handle.ref_cache_build)
+        self.ref_bases, self.ref_off = _concat([r.ref_fwd for r in regions] if with_ref else [])
         reads, sc, normal = [], [], []
         self.read_reg_off = np.zeros(self.n + 1, np.int64)
         self.sc_reg_off = np.zeros(self.n + 1, np.int64)
@@ -91,7 +92,8 @@ class PackedBatch:
         s.k = self.k
         s.rc_thresh = self.rc_thresh
         s.have_mers = 1 if self.in_mers is not None else 0
-        s.ref_bases, s.ref_off = p(self.ref_bases), p(self.ref_off)
+        if self.with_ref:
+            s.ref_bases, s.ref_off = p(self.ref_bases), p(self.ref_off)
         s.read_bases, s.read_off = p(self.read_bases), p(self.read_off)
         s.read_reg_off, s.read_flags = p(self.read_reg_off), p(self.read_flags)
         s.sc_bases, s.sc_off, s.sc_reg_off = p(self.sc_bases), p(self.sc_off), p(self.sc_reg_off)

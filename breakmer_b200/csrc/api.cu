@@ -23,6 +23,10 @@ struct bk_handle_s {
   Arena<false> dev;        // per-call device scratch
   Arena<true> pin;         // per-call pinned host staging / results
   Arena<false> resident;   // bk_batch_upload
+  Arena<false> cache;      // bk_ref_cache_build
+  const uint64_t* ref_cache_mers = nullptr;   // sorted reference k-mers per region (forward + reverse complement)
+  const int64_t* ref_cache_koff = nullptr;    // n_regions + 1
+  int ref_cache_regions = 0, ref_cache_k = 0;
   KernelTimers timers;
   std::string err;
   std::unique_ptr<Pipeline> pipe;
@@ -78,7 +82,7 @@ struct SelectOut {
 };
 
 SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int seg_bits, int mode,
-                          int64_t n_seg) {
+                          int64_t n_seg, bool use_ref_cache = false, int seg_shift = 0) {
   SelectOut o{nullptr, nullptr, 0, nullptr};
   cudaStream_t st = h->st;
   if (n_seg > 0) {
@@ -98,6 +102,7 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
   radix_sort_pairs(keys, vals, n, key_bits, sc, st, &sk, &sv, h->timers);
   RunParams rp{};
   rp.keys = sk; rp.vals = sv; rp.n = n; rp.k = k; rp.mode = mode;
+  if (use_ref_cache) { rp.ref_mers = h->ref_cache_mers; rp.ref_koff = h->ref_cache_koff; rp.seg_shift = seg_shift; }
   rp.flags = h->dev.get<uint32_t>(n);
   rp.run_count = h->dev.get<uint32_t>(n);
   uint32_t* pos = h->dev.get<uint32_t>(n);
@@ -169,6 +174,7 @@ int bk_destroy(bk_handle_t h) {
   h->dev.release();
   h->pin.release();
   h->resident.release();
+  h->cache.release();
   cudaStreamDestroy(h->st);
   delete h;
   return BK_OK;
@@ -356,6 +362,22 @@ int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out) {
   return guarded(h, [&] {
     if (!out) fail(BK_ERR_ARG, "bk_compare_kmers_resident: null argument");
     pipeline_run(h, nullptr, /*resident=*/true, out);
+  });
+}
+
+int bk_ref_cache_build(bk_handle_t h, const char* ref_bases, const int64_t* ref_off, int32_t n_regions, int32_t k) {
+  return guarded(h, [&] {
+    if (!ref_off || n_regions < 0 || (n_regions > 0 && ref_off[n_regions] > 0 && !ref_bases)) fail(BK_ERR_ARG, "bk_ref_cache_build: null argument");
+    if (k < 2 || k > 31) fail(BK_ERR_ARG, "bk_ref_cache_build: k must be in 2..31");
+    ref_cache_build(h, ref_bases, ref_off, n_regions, k);
+  });
+}
+
+int bk_ref_cache_clear(bk_handle_t h) {
+  return guarded(h, [&] {
+    BK_CUDA(cudaStreamSynchronize(h->st));
+    h->cache.reset();
+    h->ref_cache_mers = nullptr; h->ref_cache_koff = nullptr; h->ref_cache_regions = 0; h->ref_cache_k = 0;
   });
 }
 

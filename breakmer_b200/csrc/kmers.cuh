@@ -147,6 +147,10 @@ struct RunParams {
   uint64_t* out_mers;
   uint32_t* out_counts;
   uint32_t* seg_counts;       // per region number of selected runs (atomic), may be null
+  // optional persistent reference k-mer cache: sorted mers of region r at ref_mers[ref_koff[r] .. ref_koff[r+1])
+  const uint64_t* ref_mers;
+  const int64_t* ref_koff;
+  int seg_shift;              // region id in the key + seg_shift = region id of the cache
 };
 
 __global__ void __launch_bounds__(256) run_select_kernel(RunParams P) {
@@ -172,8 +176,19 @@ __global__ void __launch_bounds__(256) run_select_kernel(RunParams P) {
         flag = 1;
       } else {
         // (case & case_sc) - ref - normal ; reported count is the case count (sv_processor.py:621-631)
-        const bool sel = (seen & (1u << TAG_CASE)) && (seen & (1u << TAG_SC)) && !(seen & (1u << TAG_REF)) &&
-                         !(seen & (1u << TAG_NORMAL));
+        bool sel = (seen & (1u << TAG_CASE)) && (seen & (1u << TAG_SC)) && !(seen & (1u << TAG_REF)) &&
+                   !(seen & (1u << TAG_NORMAL));
+        if (sel && P.ref_mers) {
+          // the reference set was counted once and cached: membership by binary search in the region's sorted mers
+          const uint64_t mer = key & ((P.k == 32) ? ~0ull : ((1ull << (2 * P.k)) - 1ull));
+          const int64_t seg = (int64_t)(key >> (2 * P.k)) + P.seg_shift;
+          int64_t lo = P.ref_koff[seg], hi = P.ref_koff[seg + 1];
+          while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (P.ref_mers[mid] < mer) lo = mid + 1; else hi = mid;
+          }
+          if (lo < P.ref_koff[seg + 1] && P.ref_mers[lo] == mer) sel = false;
+        }
         flag = sel ? 1u : 0u;
         total = c_case;
       }

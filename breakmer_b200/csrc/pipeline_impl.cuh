@@ -36,6 +36,7 @@ struct RecordSet {          // one of: reads, soft clips, normal reads (device c
 
 struct Pipeline {
   int n_regions = 0, k = 0, rc_thresh = 0, have_mers = 0;
+  bool use_ref_cache = false;
   RecordSet ref, reads, sc, normal;
   const uint8_t* read_flags = nullptr;
   const int64_t* read_reg_off = nullptr;  // device
@@ -132,10 +133,17 @@ void pipeline_upload_into(bk_handle_t h, Arena<false>& A, const bk_batch_input* 
     p.in_mers_off = to_device(h, A, in->in_mers_off, (size_t)R + 1);
     p.h2d_bytes += p.n_in_mers * 12;
   } else {
-    if (!in->ref_off) fail(BK_ERR_ARG, "batch: ref arrays missing");
-    std::vector<int64_t> ident(R + 1);
-    std::iota(ident.begin(), ident.end(), 0);
-    upload_record_set(h, A, in->ref_bases, in->ref_off, ident.data(), R, p.ref, p.h2d_bytes, "ref");
+    if (in->ref_off) {
+      std::vector<int64_t> ident(R + 1);
+      std::iota(ident.begin(), ident.end(), 0);
+      upload_record_set(h, A, in->ref_bases, in->ref_off, ident.data(), R, p.ref, p.h2d_bytes, "ref");
+    } else {
+      // no reference sequence in this batch: the handle's reference k-mer cache stands in for it
+      if (!h->ref_cache_mers) fail(BK_ERR_ARG, "batch: ref arrays missing and no reference k-mer cache on the handle");
+      if (h->ref_cache_regions != R || h->ref_cache_k != in->k)
+        fail(BK_ERR_ARG, "batch: the reference k-mer cache was built for %d regions, k=%d", h->ref_cache_regions, h->ref_cache_k);
+      p.use_ref_cache = true;
+    }
     upload_record_set(h, A, in->sc_bases, in->sc_off, in->sc_reg_off, R, p.sc, p.h2d_bytes, "soft-clip");
     upload_record_set(h, A, in->normal_bases, in->normal_off, in->normal_reg_off, R, p.normal, p.h2d_bytes, "normal");
   }
@@ -177,6 +185,55 @@ void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag
   E.keys = keys; E.vals = vals; E.out_base = base; E.out_base_rc = base_rc;
   TimedLaunch t(h->timers, h->st, KF_EMIT);
   kmer_emit_kernel<<<nblk(E.n_bases, EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
+}
+
+// Persistent reference k-mer cache: forward + reverse-complement k-mers of every target window, counted once,
+// kept as sorted per-region mer arrays (the analogue of the marker-file cache of the reference dumps, utils.py:157).
+void ref_cache_build(bk_handle_t h, const char* ref_bases, const int64_t* ref_off, int R, int k) {
+  cudaStream_t st = h->st;
+  h->dev.reset();
+  h->pin.reset();
+  h->cache.reset();
+  h->ref_cache_mers = nullptr; h->ref_cache_koff = nullptr; h->ref_cache_regions = 0; h->ref_cache_k = 0;
+  std::vector<int64_t> ident(R + 1);
+  std::iota(ident.begin(), ident.end(), 0);
+  RecordSet ref;
+  int64_t h2d = 0;
+  upload_record_set(h, h->dev, ref_bases, ref_off, ident.data(), R, ref, h2d, "ref");
+  const int max_seg_bits = 63 - 2 * k;
+  const int chunk = (int)std::min<int64_t>(R > 0 ? R : 1, int64_t(1) << std::min(max_seg_bits, 16));
+  std::vector<SelectOut> outs;
+  std::vector<uint32_t> counts_host;
+  uint32_t* seg_counts_all = dev_zero<uint32_t>(h, (size_t)R + 1);
+  int64_t total = 0;
+  for (int r0 = 0; r0 < R; r0 += chunk) {
+    const int r1 = std::min(R, r0 + chunk);
+    const int64_t nr = ref.reg_base[r1] - ref.reg_base[r0];
+    const int64_t nk = 2 * nr;
+    if (nk >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "ref cache: more than 2^31 k-mer windows in one chunk");
+    uint64_t* keys = h->dev.get<uint64_t>(nk);
+    uint32_t* vals = h->dev.get<uint32_t>(nk);
+    emit_set(h, ref, r0, r1, k, TAG_REF, true, keys, vals, 0, nr);
+    SelectOut so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_ALL, r1 - r0);
+    BK_CUDA(cudaMemcpyAsync(seg_counts_all + r0, so.seg_counts, (size_t)(r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    outs.push_back(so);
+    total += so.n;
+  }
+  uint64_t* mers = h->cache.get<uint64_t>(total);
+  int64_t* koff = h->cache.get<int64_t>(R + 1);
+  int64_t at = 0;
+  for (auto& so : outs) {
+    if (so.n) BK_CUDA(cudaMemcpyAsync(mers + at, so.mers, so.n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    at += so.n;
+  }
+  uint32_t* seg_excl = h->dev.get<uint32_t>(R + 1);
+  uint32_t* d_tot = h->dev.get<uint32_t>(1);
+  uint32_t* stmp = h->dev.get<uint32_t>(scan_tmp_elems(R));
+  exclusive_scan_u32(seg_counts_all, seg_excl, R, stmp, d_tot, st);
+  widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_tot, R, koff);
+  BK_CUDA(cudaGetLastError());
+  BK_CUDA(cudaStreamSynchronize(st));
+  h->ref_cache_mers = mers; h->ref_cache_koff = koff; h->ref_cache_regions = R; h->ref_cache_k = k;
 }
 
 void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_batch_result* out) {
@@ -295,7 +352,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       at += ns;
       emit_set(h, p.normal, r0, r1, k, TAG_NORMAL, false, keys, vals, at, 0);     // K4
       ChunkOut co;
-      co.so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0);
+      co.so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0, p.use_ref_cache, r0);
       co.r0 = r0; co.r1 = r1;
       BK_CUDA(cudaMemcpyAsync(seg_counts_all + r0, co.so.seg_counts, (size_t)(r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
       chunks.push_back(co);

@@ -148,6 +148,15 @@ int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_res
  * (ms, CUDA events on the handle's stream) and launch count per kernel family since the
  * last bk_kernel_times_reset; names is a ';'-separated list in the same order. */
 int bk_batch_upload(bk_handle_t h, const bk_batch_input* in);
+/* ---- persistent reference k-mer cache ------------------------------------------------------
+ * The GPU analogue of the reference's marker-file cache of the target reference dumps
+ * (utils.py:157 skips jellyfish when the dump exists; preset_ref_data, sv_processor.py:108-162):
+ * the forward and reverse-complement k-mers of every target window are counted once and kept on
+ * the device.  A later bk_compare_kmers_batch / bk_batch_upload on this handle whose ref_bases and
+ * ref_off are NULL uses the cache instead (same n_regions, same k, regions in the same order). */
+int bk_ref_cache_build(bk_handle_t h, const char* ref_bases, const int64_t* ref_off, int32_t n_regions, int32_t k);
+int bk_ref_cache_clear(bk_handle_t h);
+
 /* Tuning knobs.  "spec_width" = 0 | 1 | 2 | 4 | 8: warps per region in the assembler (how many
  * reads are aligned speculatively at once).  0 (default) = 4, one aligning warp per SM
  * sub-partition.  Results never depend on it. */

@@ -148,3 +148,23 @@ def test_other_k(handle, k):
     regions = [synth.make_region("k%d_%d" % (k, i), seed=1300 + i, L=1200, cov=120, k=k, e=0.005,
                                  event=("del", 150, None), indel_p=0.2) for i in range(3)]
     check_batch(handle, regions)
+
+
+def test_reference_kmer_cache_gives_the_same_result(handle):
+    from breakmer_b200 import _lib, batch
+    regions = list(synth.config_regions("C3", n=10)) + list(synth.config_regions("C2", n=10, start=100))
+    exp = [oracle_region(r) for r in regions]
+    handle.ref_cache_build([r.ref_fwd for r in regions], regions[0].k)
+    try:
+        out = batch.run(handle, batch.PackedBatch(regions, with_ref=False))
+        for i in range(len(regions)):
+            assert out.sample_only(i) == exp[i][0]
+            assert out.contig_records(i) == exp[i][1]
+        # a batch of a different shape must be refused, not silently mis-served
+        with pytest.raises(_lib.BreakmerError):
+            batch.run(handle, batch.PackedBatch(regions[:5], with_ref=False))
+    finally:
+        handle.ref_cache_clear()
+    with pytest.raises(_lib.BreakmerError):
+        batch.run(handle, batch.PackedBatch(regions, with_ref=False))
+    check_batch(handle, regions[:4])
