@@ -255,10 +255,12 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
   const int nblk = (m + W - 1) / W;
   int best_a = NW_BIAS + m, best_ai = 0;        // score[0][m] = 0 (olc.py:79-83 starts at row 0)
   int best_b = NW_BIAS, best_bj = 0;            // score[n][0] = 0
-  const int steps = ((n + 1) >> 1) + 31;
   for (int b = 0; b < nblk; ++b) {
     const int jb = b * W;
     const int jfirst = jb + L * C + 1;          // 1-based column held in slot 0
+    // the sweep ends when the last lane that holds a real column has done the last row pair
+    const int cols_here = (m - jb) < W ? (m - jb) : W;
+    const int steps = ((n + 1) >> 1) + (cols_here + C - 1) / C - 1;
     int colA[C], colB[C], ch[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
