@@ -250,9 +250,12 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
                                                   const uint8_t* __restrict__ rs, int n,
                                                   int2* edge0, int2* edge1, NwDual& out) {
   const unsigned FULL = 0xffffffffu;
+  constexpr bool SINGLE = OWN_C >= 0;           // one column block, last column in a known slot
+  constexpr int LOW = (1 << NW_SHIFT) - 1;      // everything below the score field
   const int L = lane();
   constexpr int W = 32 * C;
-  const int nblk = (m + W - 1) / W;
+  const int nblk = SINGLE ? 1 : (m + W - 1) / W;
+  const int hn = (n + 1) >> 1;                  // row pairs
   int best_a = NW_BIAS + m, best_ai = 0;        // score[0][m] = 0 (olc.py:79-83 starts at row 0)
   int best_b = NW_BIAS, best_bj = 0;            // score[n][0] = 0
   for (int b = 0; b < nblk; ++b) {
@@ -260,49 +263,51 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
     const int jfirst = jb + L * C + 1;          // 1-based column held in slot 0
     // the sweep ends when the last lane that holds a real column has done the last row pair
     const int cols_here = (m - jb) < W ? (m - jb) : W;
-    const int steps = ((n + 1) >> 1) + (cols_here + C - 1) / C - 1;
-    int colA[C], colB[C], ch[C];
+    const int steps = hn + (cols_here + C - 1) / C - 1;
+    int colA[C], colB[C], ch[C], r0A[C], r0B[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = jfirst + c;
       colA[c] = colB[c] = NW_BIAS + j;          // row 0: score 0, origin (0, j)
+      r0A[c] = r0B[c] = 0;
       ch[c] = (j <= m) ? (int)cs[j - 1] : 0x100;
     }
     int diagA = NW_BIAS + (jfirst - 1), diagB = diagA;
     int lastA0 = 0, lastB0 = 0, lastA1 = colA[C - 1], lastB1 = colB[C - 1];
     const int2* ein = (b & 1) ? edge1 : edge0;
     int2* eout = (b & 1) ? edge0 : edge1;
-    const bool more = (b + 1 < nblk);
+    const bool more = !SINGLE && (b + 1 < nblk);
     const bool own = (m > jb) && (m <= jb + W) && (L == (m - 1 - jb) / C);
     const int own_c = (m - 1 - jb) % C;
+    const bool lane0_first = (L == 0) && (b == 0);
     // row characters of the first step this lane is active in (t == L): rows 1 and 2
-    unsigned rc_next = *reinterpret_cast<const unsigned short*>(rs);
+    int rc0_next = rs[0], rc1_next = rs[1];
     for (int t = 0; t < steps; ++t) {
       int hA0 = __shfl_up_sync(FULL, lastA0, 1);
       int hB0 = __shfl_up_sync(FULL, lastB0, 1);
       int hA1 = __shfl_up_sync(FULL, lastA1, 1);
       int hB1 = __shfl_up_sync(FULL, lastB1, 1);
-      const int i0 = 2 * (t - L) + 1, i1 = i0 + 1;
-      const bool active = (t >= L) && (i0 <= n);
-      if (L == 0) {
-        if (b == 0) {
-          hA0 = hB0 = NW_BIAS - i0;             // column 0: score 0, origin (i, 0)
-          hA1 = hB1 = NW_BIAS - i1;
-        } else if (active) {
+      const int q = t - L;                      // row pair this lane works on
+      const bool active = (unsigned)q < (unsigned)hn;
+      const int i0 = 2 * q + 1, i1 = i0 + 1;
+      if (lane0_first) {
+        hA0 = hB0 = NW_BIAS - i0;               // column 0: score 0, origin (i, 0)
+        hA1 = hB1 = NW_BIAS - i1;
+      }
+      if (!SINGLE) {
+        if (L == 0 && b > 0 && active) {
           const int2 e0 = ein[i0];
           hA0 = e0.x; hB0 = e0.y;
           if (i1 <= n) { const int2 e1 = ein[i1]; hA1 = e1.x; hB1 = e1.y; }
         }
       }
       if (active) {
-        const unsigned rc = rc_next;
+        const int rc0 = rc0_next, rc1 = rc1_next;
         {   // prefetch the two row characters of the next step (clamped, always in bounds)
           int nx = i0 + 1;                      // index of row i0+2 in rs
-          nx = nx > NW_MAX_LEN - 1 ? NW_MAX_LEN - 1 : nx;
-          rc_next = *reinterpret_cast<const unsigned short*>(rs + nx);
+          nx = nx > NW_MAX_LEN - 2 ? NW_MAX_LEN - 2 : nx;
+          rc0_next = rs[nx]; rc1_next = rs[nx + 1];
         }
-        const int rc0 = (int)(rc & 0xffu), rc1 = (int)(rc >> 8);
-        int r0A[C], r0B[C];
         // ---- row i0 ----
         {
           int dA = diagA, dB = diagB, hA = hA0, hB = hB0;
@@ -342,34 +347,35 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
         diagA = hA1; diagB = hB1;               // Q(i1, jfirst-1): diagonal input of the next step's first row
         lastA0 = r0A[C - 1]; lastB0 = r0B[C - 1];
         lastA1 = colA[C - 1]; lastB1 = colB[C - 1];
-        if (more && L == 31) {
-          eout[i0] = make_int2(lastA0, lastB0);
-          if (i1 <= n) eout[i1] = make_int2(lastA1, lastB1);
+        if (!SINGLE) {
+          if (more && L == 31) {
+            eout[i0] = make_int2(lastA0, lastB0);
+            if (i1 <= n) eout[i1] = make_int2(lastA1, lastB1);
+          }
         }
-        {   // last column (direction A): rows in increasing order, >= keeps the largest row
+        {   // last column (direction A): rows in increasing order, >= keeps the largest row.
+            // score(c) >= score(best)  <=>  (c | LOW) >= best   (the score is the top field of the packed word)
           int c0, c1;
-          if (OWN_C >= 0) {
-            c0 = r0A[OWN_C >= 0 ? OWN_C : 0]; c1 = colA[OWN_C >= 0 ? OWN_C : 0];
+          if (SINGLE) {
+            c0 = r0A[SINGLE ? OWN_C : 0]; c1 = colA[SINGLE ? OWN_C : 0];
           } else {
             c0 = r0A[0]; c1 = colA[0];
 #pragma unroll
             for (int c = 1; c < C; ++c) { c0 = (c == own_c) ? r0A[c] : c0; c1 = (c == own_c) ? colA[c] : c1; }
           }
-          const bool u0 = own && ((c0 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
+          const bool u0 = own && ((c0 | LOW) >= best_a);
           best_a = u0 ? c0 : best_a; best_ai = u0 ? i0 : best_ai;
-          const bool u1 = own && (i1 <= n) && ((c1 >> NW_SHIFT) >= (best_a >> NW_SHIFT));
+          const bool u1 = own && (i1 <= n) && ((c1 | LOW) >= best_a);
           best_a = u1 ? c1 : best_a; best_ai = u1 ? i1 : best_ai;
         }
-        if (i0 == n) {
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-            if (jfirst + c <= m && (r0B[c] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = r0B[c]; best_bj = jfirst + c; }
-        } else if (i1 == n) {
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-            if (jfirst + c <= m && (colB[c] >> NW_SHIFT) >= (best_b >> NW_SHIFT)) { best_b = colB[c]; best_bj = jfirst + c; }
-        }
       }
+    }
+    // last row (direction B): every lane's registers still hold the last row pair it worked on -- row n is its
+    // first row if n is odd, its second if n is even.  Columns in increasing order, >= keeps the largest column.
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int v = (n & 1) ? r0B[c] : colB[c];
+      if (jfirst + c <= m && (v | LOW) >= best_b) { best_b = v; best_bj = jfirst + c; }
     }
     __syncwarp();
   }
