@@ -407,7 +407,7 @@ def gpu_arm(args):
     # INT32 ALU-pipe ceiling of the DP: 8 alu-pipe instructions per cell (nw.cuh), 16 lanes/clk/SMSP (B300_MICROARCH.md)
     int_peak_cells = 148 * 4 * 16 * sm_mhz * 1e6 / 8.0
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_*.md); only valid for the default workload
-    asm_traffic = 34547456 if (args.workload == "C2" and per_gpu == 500) else None
+    asm_traffic = 35980288 if (args.workload == "C2" and per_gpu == 500) else None
     sort_traffic = 460892928 if (args.workload == "C2" and per_gpu == 500) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -435,7 +435,7 @@ def gpu_arm(args):
         "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": int_peak_cells,
                          "unit": "DP cell updates/s", "frac": cells_per_s / int_peak_cells if int_peak_cells else None,
                          "peak_source": "148 SM x 4 SMSP x 16 alu lanes/clk x measured sm clock / 8 alu-pipe instructions per cell; "
-                                        "ncu: pipe_alu 46% busy on active SMs, launch bounded by the longest region (profiles/r1_assemble_kernel.md)"},
+                                        "ncu: pipe_alu 48% busy on active SMs, launch bounded by the longest region (profiles/r1_assemble_kernel.md)"},
         "roofline_kstage": {"kernel": "rs_scatter_kernel", "bound": "hbm", "achieved": sort_gbs, "peak": hbm_peak,
                             "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": sort_traffic,
                             "algorithmic_bytes_per_launch": sort_bytes, "launches": sc_n},
