@@ -431,8 +431,12 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     unsigned long long* d_n = dev_zero<unsigned long long>(h, 1);
     {
       TimedLaunch t(h->timers, st, KF_INDEX);
-      index_emit_kernel<<<nblk(NU, IDX_WARPS), 32 * IDX_WARPS, 0, st>>>(p.reads.bases, p.reads.off, u_off, u_rec, R, NU, so_off,
-                                                                        so_mer, k, ik, iv, ik2, u_bits, s_bits, d_n, (unsigned long long)cap);
+      const int ws_stride = ((p.max_read_len + 31) / 32) * 32 + 32;
+      const size_t idx_smem = (size_t)IDX_WARPS * ws_stride * sizeof(int32_t);
+      if (idx_smem > 48 * 1024) BK_CUDA(cudaFuncSetAttribute(index_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)idx_smem));
+      index_emit_kernel<<<nblk(NU, IDX_WARPS), 32 * IDX_WARPS, idx_smem, st>>>(p.reads.bases, p.reads.off, u_off, u_rec, R, NU, so_off,
+                                                                               so_mer, k, ik, iv, ik2, u_bits, s_bits, ws_stride, d_n,
+                                                                               (unsigned long long)cap);
     }
     const unsigned long long* h_n = to_host(h, d_n, 1);
     BK_CUDA(cudaStreamSynchronize(st));

@@ -147,8 +147,7 @@ __global__ void __launch_bounds__(256) mer_prep_kernel(const uint64_t* __restric
 // ---------------------------------------------------------------------------------
 // inverted index
 // ---------------------------------------------------------------------------------
-constexpr int IDX_WARPS = 2;
-constexpr int IDX_READ_CAP = 4096;
+constexpr int IDX_WARPS = 8;     // one read per warp; shared memory is sized by the longest read of the batch
 
 __device__ __forceinline__ bool window_code_dev(const uint8_t* seq, int x, int k, uint64_t& code) {
   uint64_t c = 0;
@@ -170,9 +169,11 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
     const uint8_t* __restrict__ rbases, const int64_t* __restrict__ roff, const int64_t* __restrict__ u_off,
     const int32_t* __restrict__ u_rec, int n_regions, int64_t n_uniq, const int64_t* __restrict__ so_off,
     const uint64_t* __restrict__ so_mer, int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-    uint64_t* __restrict__ keys2, int u_bits, int s_bits, unsigned long long* __restrict__ n_out, unsigned long long cap) {
-  __shared__ int32_t ws[IDX_WARPS][IDX_READ_CAP];
+    uint64_t* __restrict__ keys2, int u_bits, int s_bits, int ws_stride, unsigned long long* __restrict__ n_out,
+    unsigned long long cap) {
+  extern __shared__ int32_t ws_all[];          // IDX_WARPS x ws_stride : local mer index of every window of the warp's read
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  int32_t* ws = ws_all + (size_t)w * ws_stride;
   const int64_t u = (int64_t)blockIdx.x * IDX_WARPS + w;
   if (u >= n_uniq) return;
   int lo = 0, hi = n_regions;
@@ -203,13 +204,13 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
         }
         if (a < S && mer[a] == code) s = a;
       }
-      ws[w][x] = s;
+      ws[x] = s;
     }
     __syncwarp();
     bool first = s >= 0;
     if (first)
       for (int y = 0; y < x; ++y)
-        if (ws[w][y] == s) { first = false; break; }
+        if (ws[y] == s) { first = false; break; }
     const unsigned mk = __ballot_sync(0xffffffffu, first);
     if (mk) {
       unsigned long long base = 0;
