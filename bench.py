@@ -266,7 +266,7 @@ def gpu_arm(args):
     # per-kernel device times: a short SEQUENTIAL pass on one handle with the library's CUDA-event timers on
     # (in the pipelined region kernels of different batches share the SMs, so their durations are not comparable)
     lat_ms = []
-    h.set_option("spec_width", 4)                # latency-oriented setting for the sequential pass
+    h.set_option("spec_width", int(os.environ.get("BK_BENCH_SEQ_W", "4")))   # latency-oriented setting for the sequential pass
     h.kernel_times_reset(True)
     for _ in range(3):
         flush.zero_()

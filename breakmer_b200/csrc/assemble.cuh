@@ -41,6 +41,9 @@ constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 #ifndef ASM_W4_CTAS
 #define ASM_W4_CTAS 3
 #endif
+#ifndef ASM_W1_CTAS
+#define ASM_W1_CTAS 13
+#endif
 #ifndef ASM_SPEC_W
 #define ASM_SPEC_W 8     // maximum width (array sizes); the width of a launch is a kernel template argument
 #endif
@@ -1134,17 +1137,17 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 // the mer hash, the round mailbox (then padding, see above)
 template <int W>
 constexpr size_t assemble_smem_bytes() {
-  return (size_t)W * ASM_CAP + ASM_CAP + (size_t)(W > 1 ? W - 1 : 1) * ASM_CAP + MER_HASH_SIZE * sizeof(int32_t) +
+  return (size_t)W * ASM_CAP + ASM_CAP + (size_t)(W - 1) * ASM_CAP + MER_HASH_SIZE * sizeof(int32_t) +
          ((sizeof(SpecShared) + 15) & ~size_t(15));
 }
 
 template <int W>
-__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : 8)))) assemble_kernel(AsmParams P) {
+__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : ASM_W1_CTAS)))) assemble_kernel(AsmParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* s_reads = smem_raw;
   uint8_t* s_contig = s_reads + (size_t)W * ASM_CAP;
   uint8_t* s_pred = s_contig + ASM_CAP;
-  int32_t* s_hash = reinterpret_cast<int32_t*>(s_pred + (size_t)(W > 1 ? W - 1 : 1) * ASM_CAP);
+  int32_t* s_hash = reinterpret_cast<int32_t*>(s_pred + (size_t)(W - 1) * ASM_CAP);
   SpecShared& sp = *reinterpret_cast<SpecShared*>(s_hash + MER_HASH_SIZE);
   const int64_t slot = blockIdx.x;
   const int warp = threadIdx.x >> 5;
