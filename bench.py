@@ -389,6 +389,11 @@ def gpu_arm(args):
         for hh in handles:
             hh.ref_cache_clear()
 
+    # ---- ingest row: the same steps starting from FASTA/FASTQ FILES (tmpfs) -------------------
+    from_files = None
+    if not args.no_ingest_leg:
+        from_files = ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_ranks, n_regions_total, rank)
+
     # ---- roofline of the dominant kernel (the assembler) and of the dominant k-mer stage kernel -----
     asm_ms, asm_n = ktimes["assemble"]
     asm_ms_per_launch = asm_ms / max(1, asm_n)
@@ -412,7 +417,7 @@ def gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
+        "dtype": "int32", "data": "synthetic", "from_files": from_files,
         "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": pk.k, "rc_thresh": pk.rc_thresh,
                    "input_bytes_per_gpu": pk.input_bytes, "steps_in_flight": n_fly, "assembler_spec_width": spec_w,
                    "l2": ("256 MB buffer written between timed steps (flush)" if n_fly == 1 else
@@ -461,6 +466,89 @@ def gpu_arm(args):
     return 0
 
 
+def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_ranks, n_regions_total, rank):
+    """Every step = bk_ingest_files (text of the four files of each target -> page-locked arrays, host threads) followed by
+    bk_compare_kmers_batch.  Files live in tmpfs; writing them is not timed.  Python marshalling of the same regions
+    (batch.PackedBatch) is timed beside it for context."""
+    import shutil
+    import tempfile
+    import torch
+    from breakmer_b200 import batch, ingest
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    d = tempfile.mkdtemp(prefix="bk_bench_r%d_" % rank, dir=root)
+    try:
+        refs, fqs, scs, nms = [], [], [], []
+        any_normal = any(r.normal_reads for r in regions)
+        n_bytes = 0
+        for i, r in enumerate(regions):
+            base = os.path.join(d, "t%05d" % i)
+            texts = {
+                "_ref.fa": ">%s\n%s\n" % (r.name, "\n".join(r.ref_fwd[a:a + 60] for a in range(0, len(r.ref_fwd), 60))),
+                "_reads.fastq": "".join("%s\n%s\n+\n%s\n" % (rec[0], rec[1], rec[2]) for rec in r.reads),
+                "_sc.fa": "".join(">%s\n%s\n" % (rec[0], rec[1]) for rec in r.sc_records),
+            }
+            if any_normal:
+                texts["_normal.fastq"] = "".join("@%s\n%s\n+\n%s\n" % (rec[0].lstrip("@"), rec[1], "I" * len(rec[1]))
+                                                 for rec in r.normal_reads)
+            for suffix, t in texts.items():
+                with open(base + suffix, "w", newline="\n") as f:
+                    f.write(t)
+                n_bytes += len(t)
+            refs.append(base + "_ref.fa"); fqs.append(base + "_reads.fastq"); scs.append(base + "_sc.fa")
+            nms.append(base + "_normal.fastq" if any_normal else None)
+        normal = nms if any_normal else None
+        cores = os.cpu_count() or 1
+        per = max(1, cores // n_fly)
+        ings = [ingest.Ingest(n_threads=per) for _ in range(n_fly)]
+        kw = dict(normal=normal, k=pk.k, rc_thresh=pk.rc_thresh)
+        # parser alone, all cores on one batch
+        solo = ingest.Ingest(n_threads=cores)
+        solo.files(refs, fqs, scs, **kw)
+        t0 = time.time()
+        reps = 5
+        for _ in range(reps):
+            solo.files(refs, fqs, scs, **kw)
+        parse_s = (time.time() - t0) / reps
+        solo.close()
+        t0 = time.time()
+        batch.PackedBatch(regions)
+        py_s = time.time() - t0
+        for j, hh in enumerate(handles):
+            batch.run(hh, ings[j].files(refs, fqs, scs, **kw), decode=False)
+        box = {}
+
+        def worker(j):
+            hh = handles[j]
+            if stagger_s:
+                time.sleep(j * stagger_s)
+            for step in range(j, args.steps, n_fly):
+                box[j] = batch.run(hh, ings[j].files(refs, fqs, scs, **kw), decode=False)
+
+        barrier()
+        t0 = time.time()
+        threads = [threading.Thread(target=worker, args=(j,)) for j in range(n_fly)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        torch.cuda.synchronize()
+        local = time.time() - t0
+        barrier()
+        ff_s = max_over_ranks(local)
+        n_contigs = int(box[0].n_contigs)
+        for g in ings:
+            g.close()
+        return {"value": n_regions_total * args.steps / ff_s, "unit": UNIT, "ms_per_step": 1000.0 * ff_s / args.steps,
+                "text_bytes_per_step": n_bytes, "n_contigs": n_contigs,
+                "parse_only": {"ms_per_batch": 1000.0 * parse_s, "regions_per_s": len(regions) / parse_s,
+                               "text_MB_per_s": n_bytes / parse_s / 1e6, "host_threads": cores},
+                "python_marshalling_ms_per_batch": 1000.0 * py_s,
+                "note": "each step parses the targets' FASTA/FASTQ files (tmpfs) with bk_ingest_files into page-locked memory "
+                        "and calls bk_compare_kmers_batch; %d ingest threads per in-flight batch" % per}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -473,6 +561,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=6, help="independent batches (steps) kept on the device at once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
+    ap.add_argument("--no-ingest-leg", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -20,6 +20,8 @@ BK_ERR_ARG = -2
 BK_ERR_NOMEM = -3
 BK_ERR_CAPACITY = -4
 BK_ERR_EMPTY_SEQ = -5
+BK_ERR_FORMAT = -6
+BK_ERR_IO = -7
 
 
 class BreakmerError(RuntimeError):
@@ -55,6 +57,16 @@ class BatchResult(Structure):
         ("n_check_align", c_int64), ("n_dp_cells", c_int64), ("n_kmer_occurrences", c_int64),
         ("gpu_ms", c_double),
     ]
+
+
+class Text(Structure):
+    _fields_ = [("p", c_void_p), ("n", c_int64)]
+
+
+class IngestText(Structure):
+    _fields_ = [("id_bytes", POINTER(c_uint8)), ("id_off", POINTER(c_int64)),
+                ("qual_bytes", POINTER(c_uint8)), ("qual_off", POINTER(c_int64)),
+                ("n_reads", c_int64), ("read_flags", POINTER(c_uint8))]
 
 
 _lib = None
@@ -93,6 +105,16 @@ def load():
     lib.bk_set_option.argtypes = [H, c_char_p, c_int64]
     lib.bk_ref_cache_build.argtypes = [H, c_void_p, c_void_p, c_int32, c_int32]
     lib.bk_ref_cache_clear.argtypes = [H]
+    lib.bk_ingest_create.argtypes = [c_int, c_int, POINTER(H)]
+    lib.bk_ingest_destroy.argtypes = [H]
+    lib.bk_ingest_last_error.argtypes = [H]
+    lib.bk_ingest_last_error.restype = c_char_p
+    lib.bk_ingest_buffers.argtypes = [H, c_int32, POINTER(Text), POINTER(Text), POINTER(Text), POINTER(Text),
+                                      POINTER(BatchInput), POINTER(IngestText)]
+    lib.bk_ingest_files.argtypes = [H, c_int32, POINTER(c_char_p), POINTER(c_char_p), POINTER(c_char_p),
+                                    POINTER(c_char_p), POINTER(BatchInput), POINTER(IngestText)]
+    for name in ("bk_ingest_create", "bk_ingest_destroy", "bk_ingest_buffers", "bk_ingest_files"):
+        getattr(lib, name).restype = c_int
     for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_count_kmers", "bk_sample_only",
                  "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
                  "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear"):
@@ -104,7 +126,8 @@ def load():
 EXPORTED_SYMBOLS = (
     "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_count_kmers",
     "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
-    "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear")
+    "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear",
+    "bk_ingest_create", "bk_ingest_destroy", "bk_ingest_last_error", "bk_ingest_buffers", "bk_ingest_files")
 
 
 def _ptr(a):

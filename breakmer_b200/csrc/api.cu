@@ -12,6 +12,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "pipeline.cuh"
+#include "ingest.cuh"
 
 using namespace bk;
 
@@ -409,6 +410,114 @@ int bk_kernel_times_reset(bk_handle_t h, int enable) {
     BK_CUDA(cudaStreamSynchronize(h->st));
     h->timers.reset();
     h->timers.enabled = enable != 0;
+  });
+}
+
+}  // extern "C"
+
+// ---- ingest (host threads; see ingest.cuh) ---------------------------------------------------
+struct bk_ingest_s {
+  Ingest g;
+};
+
+namespace {
+template <typename F>
+int guarded_ingest(bk_ingest_t g, F&& f) {
+  if (!g) return BK_ERR_ARG;
+  try {
+    f();
+    return BK_OK;
+  } catch (const ApiError& e) {
+    g->g.err = e.msg;
+    return e.code;
+  } catch (const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at ingest line %d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
+    g->g.err = buf;
+    cudaGetLastError();
+    return BK_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    g->g.err = "host allocation failed";
+    return BK_ERR_NOMEM;
+  }
+}
+void fill_text(const IngestText& t, bk_ingest_text* out) {
+  if (!out) return;
+  out->id_bytes = t.id_bytes; out->id_off = t.id_off;
+  out->qual_bytes = t.qual_bytes; out->qual_off = t.qual_off;
+  out->n_reads = t.n_reads; out->read_flags = t.read_flags;
+}
+}  // namespace
+
+extern "C" {
+
+int bk_ingest_create(int n_threads, int pinned, bk_ingest_t* out) {
+  if (!out) return BK_ERR_ARG;
+  *out = nullptr;
+  if (pinned) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return BK_ERR_CUDA; }
+  }
+  bk_ingest_s* g = new (std::nothrow) bk_ingest_s();
+  if (!g) return BK_ERR_NOMEM;
+  if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+  g->g.n_threads = std::max(1, std::min(n_threads, 256));
+  g->g.pinned = pinned != 0;
+  g->g.buf.pinned = g->g.pinned;
+  *out = g;
+  return BK_OK;
+}
+
+int bk_ingest_destroy(bk_ingest_t g) {
+  if (!g) return BK_ERR_ARG;
+  delete g;
+  return BK_OK;
+}
+
+const char* bk_ingest_last_error(bk_ingest_t g) { return g ? g->g.err.c_str() : "null ingest handle"; }
+
+int bk_ingest_buffers(bk_ingest_t g, int32_t n_regions, const bk_text* ref_fa, const bk_text* reads_fq,
+                      const bk_text* sc_fa, const bk_text* normal_fq, bk_batch_input* in, bk_ingest_text* text) {
+  return guarded_ingest(g, [&] {
+    if (n_regions < 0 || !in) fail(BK_ERR_ARG, "bk_ingest_buffers: bad arguments");
+    auto views = [&](const bk_text* t, std::vector<TextView>& v) -> const TextView* {
+      if (!t) return nullptr;
+      v.resize((size_t)n_regions);
+      for (int r = 0; r < n_regions; ++r) v[r] = TextView{t[r].p, t[r].p ? (size_t)t[r].n : 0};
+      return v.data();
+    };
+    std::vector<TextView> a, b, c, d;
+    IngestText t{};
+    ingest_texts(g->g, n_regions, views(ref_fa, a), views(reads_fq, b), views(sc_fa, c), views(normal_fq, d), in, &t);
+    fill_text(t, text);
+  });
+}
+
+int bk_ingest_files(bk_ingest_t g, int32_t n_regions, const char* const* ref_fa, const char* const* reads_fq,
+                    const char* const* sc_fa, const char* const* normal_fq, bk_batch_input* in, bk_ingest_text* text) {
+  return guarded_ingest(g, [&] {
+    if (n_regions < 0 || !in) fail(BK_ERR_ARG, "bk_ingest_files: bad arguments");
+    Ingest& G = g->g;
+    const char* const* lists[4] = {ref_fa, reads_fq, sc_fa, normal_fq};
+    G.file_text.assign((size_t)n_regions * 4, std::string());
+    std::vector<TextView> v[4];
+    std::vector<int> bad((size_t)n_regions, -1);
+    for (int s = 0; s < 4; ++s) if (lists[s]) v[s].assign((size_t)n_regions, TextView{nullptr, 0});
+    G.parallel_for(n_regions, [&](int r) {
+      for (int s = 0; s < 4; ++s) {
+        if (!lists[s] || !lists[s][r] || !lists[s][r][0]) continue;
+        std::string& txt = G.file_text[(size_t)r * 4 + s];
+        if (!read_whole_file(lists[s][r], txt)) { bad[r] = s; return; }
+        v[s][r] = TextView{txt.data(), txt.size()};
+      }
+    });
+    for (int r = 0; r < n_regions; ++r)
+      if (bad[r] >= 0) fail(BK_ERR_IO, "cannot read %s", lists[bad[r]][r]);
+    IngestText t{};
+    ingest_texts(G, n_regions, lists[0] ? v[0].data() : nullptr, lists[1] ? v[1].data() : nullptr,
+                 lists[2] ? v[2].data() : nullptr, lists[3] ? v[3].data() : nullptr, in, &t);
+    fill_text(t, text);
+    G.file_text.clear();
   });
 }
 

@@ -22,6 +22,14 @@ An optional files['normal_fq'] enables normal-sample subtraction (K4).
 `compare_kmers_batch(targets)` does the same for many targets in ONE device
 pass; the reference loop becomes: extract+clean all targets, one batched call,
 then resolve_sv per target.
+
+With `ingest="native"` the inputs are not marshalled from the Python objects at all:
+the four files of every target (target_ref_fn[0], cleaned_fq -- the filtered FASTQ
+get_fastq_reads wrote next to cleaned_read_recs, utils.py:206,237 -- sv_sc_unmapped_fa,
+normal_fq) are parsed by the library's host threads straight into page-locked memory
+(bk_ingest_files).  The reads of the returned contigs are then
+fresh fq_read objects built from the parsed records (same .id/.seq/.qual/.indel_only as the
+caller's; of these the rest of the reference only reads .id/.seq/.qual).
 """
 import os
 
@@ -48,15 +56,67 @@ class _TargetInput:
         self.read_len = int(trgt.read_len)
 
 
-def compare_kmers_batch(targets, device=0):
+class _LazyReads:
+    """objs[i] for the native ingest: fq_read of record i, built on first use."""
+
+    def __init__(self, pk):
+        self._pk = pk
+        self._cache = {}
+        self._cols = None
+
+    def __getitem__(self, i):
+        fr = self._cache.get(i)
+        if fr is None:
+            if self._cols is None:
+                self._cols = (self._pk.read_ids, self._pk.read_seqs(), self._pk.read_quals())
+            ids, seqs, quals = self._cols
+            fr = self._cache[i] = utils.fq_read(ids[i], seqs[i], quals[i], bool(self._pk.read_flags[i]))
+        return fr
+
+
+_ingests = {}
+
+
+def _get_ingest():
+    import threading
+    from . import ingest as _ingest
+    key = threading.get_ident()                    # an ingest object's buffer is reused call to call: one per thread
+    if key not in _ingests:
+        _ingests[key] = _ingest.Ingest()
+    return _ingests[key]
+
+
+class _K:
+    def __init__(self, k):
+        self.k = k
+
+
+def compare_kmers_batch(targets, device=0, ingest="python"):
     import numpy as np
     if not targets:
         return
-    inputs = [_TargetInput(t) for t in targets]
-    pk = batch.PackedBatch(inputs, rc_thresh=inputs[0].rc_thresh)
-    pk.read_len = np.array([inp.read_len for inp in inputs] + [0], dtype=np.int32)
+    if ingest == "native":
+        get = lambda t, key: (t.files.get(key) if hasattr(t.files, "get") else None)   # noqa: E731
+        k = int(targets[0].params.get_kmer_size())
+        if any(int(t.params.get_kmer_size()) != k for t in targets):
+            raise ValueError("one k per batch")
+        nfq = [get(t, 'normal_fq') for t in targets]
+        pk = _get_ingest().files([t.files['target_ref_fn'][0] for t in targets], [t.files['cleaned_fq'] for t in targets],
+                                 [t.files['sv_sc_unmapped_fa'] for t in targets], normal=nfq if any(nfq) else None,
+                                 k=k, rc_thresh=int(targets[0].params.get_sr_thresh('min')),
+                                 names=[t.name for t in targets])
+        for i, t in enumerate(targets):             # target.read_len is what get_fastq_reads returned (utils.py:236,246)
+            pk.read_len[i] = int(t.read_len)
+        inputs = [_K(k)] * len(targets)
+        objs = _LazyReads(pk)
+    elif ingest == "python":
+        inputs = [_TargetInput(t) for t in targets]
+        pk = batch.PackedBatch(inputs, rc_thresh=inputs[0].rc_thresh)
+        pk.read_len = np.array([inp.read_len for inp in inputs] + [0], dtype=np.int32)
+        objs = [o for inp in inputs for o in inp.objs]
+    else:
+        raise ValueError("ingest must be 'python' or 'native'")
     out = batch.run(get_handle(device), pk)
-    objs = [o for inp in inputs for o in inp.objs]
     for i, trgt in enumerate(targets):
         if out.region_status[i] != 0:
             raise RuntimeError("compare_kmers: device capacity exceeded for target %s" % trgt.name)
@@ -81,5 +141,5 @@ def compare_kmers_batch(targets, device=0):
         trgt.kmers['case_only'] = {}
 
 
-def compare_kmers(target, device=0):
-    compare_kmers_batch([target], device=device)
+def compare_kmers(target, device=0, ingest="python"):
+    compare_kmers_batch([target], device=device, ingest=ingest)

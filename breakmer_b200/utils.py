@@ -13,6 +13,7 @@ cache: it writes "<fa_fn>_<k>mers_dump" ("<MER> <count>" per line, the format
 """
 import logging
 import os
+import re
 
 from . import _lib, get_handle
 
@@ -27,13 +28,19 @@ class fq_read:
         self.indel_only = indel_only
 
 
+_WS = " \t\n\r\x0b\x0c"                       # what str.strip() removes on CPython 2.7
+_INT = re.compile(r"^[ \t\n\r\x0b\x0c]*[+-]?[0-9]+[ \t\n\r\x0b\x0c]*$")
+
+
 class FastqFile(object):
-    """Iterator over (header, seq, qual); like the reference it insists on the
-    five ':'-separated header fields (utils.py:704-712)."""
+    """Iterator over (header, seq, qual) with the reference's checks (utils.py:692-720): five
+    ':'-separated header fields, exactly one '/' (and at most one '#') in the fifth, integer lane /
+    tile / x / y; a trailing group of fewer than four lines ends the iteration.  Lines end at "\\n"
+    only, as in CPython 2.7 text mode on Linux."""
 
     def __init__(self, f):
         if isinstance(f, str):
-            f = open(f)
+            f = open(f, newline="\n")
         self._f = f
 
     def __iter__(self):
@@ -41,9 +48,18 @@ class FastqFile(object):
 
     def __next__(self):
         header, seq, _qh, qual = [next(self._f) for _ in range(4)]
-        header = header.strip()
+        header = header.strip(_WS)
         inst, lane, tile, x, y_end = header.split(':')
-        return (header, seq.strip(), qual.strip())
+        if y_end.count('/') != 1:
+            raise ValueError("FASTQ header %r: the last field needs exactly one '/'" % header)
+        y = y_end.split('/')[0]
+        if y.count('#') > 1:
+            raise ValueError("FASTQ header %r: more than one '#'" % header)
+        y = y.split('#')[0]
+        for v in (lane, tile, x, y):
+            if not _INT.match(v):
+                raise ValueError("FASTQ header %r: lane, tile, x and y must be integers" % header)
+        return (header, seq.strip(_WS), qual.strip(_WS))
 
     next = __next__
 
@@ -54,27 +70,29 @@ def get_marker_fn(fn):
 
 def read_sequences(fn):
     """Record sequences of a FASTA or FASTQ file (format sniffed from the first
-    byte, as jellyfish does); multi-line FASTA records are joined."""
+    byte, as jellyfish does); multi-line FASTA records are joined.  The batched path parses the
+    same way natively (bk_ingest_files, csrc/ingest.cuh)."""
     seqs = []
-    with open(fn) as f:
-        first = f.read(1)
-        f.seek(0)
-        if first == "@":
-            lines = f.read().splitlines()
-            for i in range(1, len(lines), 4):
-                seqs.append(lines[i].strip())
-        else:
-            cur = None
-            for line in f:
-                line = line.strip()
-                if line.startswith(">"):
-                    if cur is not None:
-                        seqs.append("".join(cur))
-                    cur = []
-                elif cur is not None:
-                    cur.append(line)
+    with open(fn, newline="\n") as f:
+        text = f.read()
+    if not text:
+        return seqs
+    lines = text.split("\n")
+    if lines[-1] == "":
+        lines.pop()
+    if text[0] == "@":
+        return [lines[i].strip(_WS) for i in range(1, len(lines), 4)]
+    cur = None
+    for line in lines:
+        line = line.strip(_WS)
+        if line.startswith(">"):
             if cur is not None:
                 seqs.append("".join(cur))
+            cur = []
+        elif cur is not None:
+            cur.append(line)
+    if cur is not None:
+        seqs.append("".join(cur))
     return seqs
 
 

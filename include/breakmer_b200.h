@@ -37,6 +37,8 @@ extern "C" {
 #define BK_ERR_NOMEM (-3)
 #define BK_ERR_CAPACITY (-4)  /* a sequence exceeds a device-side hard limit (4095 bases for nw) */
 #define BK_ERR_EMPTY_SEQ (-5) /* olc.nw raises NameError on an empty sequence (olc.py:86-87) */
+#define BK_ERR_FORMAT (-6)    /* malformed FASTQ record (FastqFile raises, utils.py:704-719) */
+#define BK_ERR_IO (-7)        /* an input file cannot be read */
 
 typedef struct bk_handle_s* bk_handle_t;
 
@@ -164,6 +166,42 @@ int bk_set_option(bk_handle_t h, const char* name, int64_t value);
 int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out);
 int bk_kernel_times(bk_handle_t h, const char** names, const double** ms, const int64_t** launches, int32_t* n);
 int bk_kernel_times_reset(bk_handle_t h, int enable);
+
+/* ---- ingest: text -> bk_batch_input ----------------------------
+ * Stands in for the readers on the way INTO target.compare_kmers:
+ *   FastqFile / fq_read            utils.py:681-720   cleaned FASTQ -> (header, seq, qual) records
+ *   get_fastq_reads                utils.py:203-246   records -> fq_recs + read_len (the sv_reads
+ *                                                     filter of :213-236 stays with the caller, who
+ *                                                     passes the filtered text)
+ *   the readers of `jellyfish count`  utils.py:160    FASTA / FASTQ inputs of the three k-mer sets
+ * For each of n_regions targets the caller gives up to four texts (in memory, or as file paths):
+ * the reference window FASTA (files['target_ref_fn'][0]; its first record is used), the cleaned
+ * reads FASTQ (files['cleaned_fq']), the soft-clip FASTA (files['sv_sc_unmapped_fa']) and
+ * optionally a normal-sample FASTQ/FASTA.  A NULL list, NULL entry or empty path means "no
+ * records".  The texts are parsed on n_threads host threads (0 = all cores) straight into ONE
+ * host buffer owned by the ingest object -- page-locked when pinned != 0, so that
+ * bk_compare_kmers_batch copies from it by DMA -- and `in` is filled with pointers into it
+ * (k, rc_thresh, have_mers are left 0 for the caller; read_len = max record length per region,
+ * utils.py:236; read_flags = the "_1" suffix fq_line writes, utils.py:436-443, and may be
+ * overwritten in place through text->read_flags).  `text` (optional) gives the record ids and
+ * quality strings needed to rebuild fq_read objects lazily.  Everything stays valid until the
+ * next bk_ingest_* call on the object or bk_ingest_destroy.  Malformed FASTQ -> BK_ERR_FORMAT.
+ * Host code only: no device work, usable without a GPU when pinned == 0. */
+typedef struct bk_ingest_s* bk_ingest_t;
+typedef struct bk_text { const char* p; int64_t n; } bk_text;
+typedef struct bk_ingest_text {
+  const char* id_bytes;   const int64_t* id_off;      /* n_reads + 1 */
+  const char* qual_bytes; const int64_t* qual_off;    /* n_reads + 1 */
+  int64_t n_reads;
+  uint8_t* read_flags;                                /* mutable view of in->read_flags */
+} bk_ingest_text;
+int bk_ingest_create(int n_threads, int pinned, bk_ingest_t* out);
+int bk_ingest_destroy(bk_ingest_t g);
+const char* bk_ingest_last_error(bk_ingest_t g);
+int bk_ingest_buffers(bk_ingest_t g, int32_t n_regions, const bk_text* ref_fa, const bk_text* reads_fq,
+                      const bk_text* sc_fa, const bk_text* normal_fq, bk_batch_input* in, bk_ingest_text* text);
+int bk_ingest_files(bk_ingest_t g, int32_t n_regions, const char* const* ref_fa, const char* const* reads_fq,
+                    const char* const* sc_fa, const char* const* normal_fq, bk_batch_input* in, bk_ingest_text* text);
 
 #ifdef __cplusplus
 }

@@ -115,3 +115,41 @@ def load():
         else:
             sys.modules["olc"] = saved
     return olc, asm
+
+
+def load_readers():
+    """Namespace holding the reference's own ``fq_read``, ``FastqFile`` and
+    ``get_fastq_reads`` (utils.py:203-246, 681-720), used to pin the ingest row
+    (SURVEY.md section 8.7 f.1).  ``utils.py`` as a whole cannot be imported
+    (pysam, Biopython), so the three definitions are cut out of the file's text by
+    their delimiting comment rulers and exec'd; rewrites:
+
+      * ``self._f.next()``  -> ``next(self._f)``  and ``__next__ = next``  (:703)
+        (a StopIteration escaping the list comprehension still ends the iteration,
+        on Python 3 as on 2.7)
+      * ``open`` is shadowed by ``open(..., newline="\\n")``: CPython 2.7's text mode
+        on Linux ends lines at "\\n" only (no universal-newline translation)
+    """
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, "utils.py")):
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    with open(os.path.join(REFERENCE_ROOT, "utils.py")) as f:
+        src = f.read().expandtabs(8)
+
+    def cut(start_pat, end_pat):
+        a = re.search(start_pat, src, flags=re.M)
+        if a is None:
+            raise RuntimeError("ref_shim: %r not found" % start_pat)
+        b = re.search(end_pat, src[a.start():], flags=re.M)
+        if b is None:
+            raise RuntimeError("ref_shim: %r not found" % end_pat)
+        return src[a.start():a.start() + b.start()]
+
+    text = cut(r"^def get_fastq_reads\(fn, sv_reads\)", r"^#-{10,}")
+    text += "\n" + cut(r"^class fq_read", r"^#@{10,}")
+    fastq = cut(r"^class FastqFile", r"^# End FastqFile class")
+    fastq = _must_sub(r"self\._f\.next\(\)", "next(self._f)", fastq, 1)
+    fastq = _must_sub(r"^  def next\(self\) :", "  def __next__(self) :", fastq, 1, flags=re.M)
+    text += "\n" + fastq
+    ns = {"open": lambda fn, mode="r": builtins.open(fn, mode, newline="\n")}
+    exec(compile(text, os.path.join(REFERENCE_ROOT, "utils.py"), "exec"), ns)
+    return types.SimpleNamespace(fq_read=ns["fq_read"], FastqFile=ns["FastqFile"], get_fastq_reads=ns["get_fastq_reads"])

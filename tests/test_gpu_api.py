@@ -143,3 +143,53 @@ def test_compare_kmers_single_and_batched(tmp_path):
         assert [sorted(x.id for x in ct.reads) for ct in t.kmers["clusters"]] == [e["reads"] for e in exp]
         assert t.cleaned_read_recs is None and t.kmers["case_only"] == {} and t.kmers["ref"] == {}
         assert t.files["kmer_clusters"].endswith("_sample_kmers_merged.out")
+
+
+def test_compare_kmers_native_ingest(tmp_path):
+    """ingest="native": the same targets through bk_ingest_files."""
+    from breakmer_b200 import sv_processor
+    regions = [synth.make_region(n, **kw) for n, kw in region_scenarios()[:10] if kw["k"] == 15]
+    targets = [_Target(r, str(tmp_path)) for r in regions]
+    sv_processor.compare_kmers_batch(targets, ingest="native")
+    for r, t in zip(regions, targets):
+        _a, _b, _c, only = oracle_sample_only(r)
+        exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
+        with open(t.files["sample_kmers"]) as f:
+            lines = dict(l.split("\t") for l in f.read().splitlines())
+        assert {m: int(c) for m, c in lines.items()} == only
+        got = [{"seq": ct.get_contig_seq(), "indel_only": ct.get_contig_counts().indel_only,
+                "others": ct.get_contig_counts().others, "reads": sorted(x.id for x in ct.reads),
+                "kmers": [list(k) for k in ct.kmers], "kmer_locs": ct.get_kmer_locs()} for ct in t.kmers["clusters"]]
+        assert got == exp, r.name
+        by_id = {rec[0]: rec for rec in r.reads}
+        for ct in t.kmers["clusters"]:
+            for fr in ct.reads:
+                rid, seq, qual, io = by_id[fr.id]
+                assert (fr.seq, fr.qual, bool(fr.indel_only)) == (seq, qual, bool(io))
+        assert t.cleaned_read_recs is None
+
+
+def test_ingested_batch_equals_packed_batch(tmp_path):
+    """Files -> Ingest -> bk_compare_kmers_batch gives the records PackedBatch gives, normal sample included."""
+    from breakmer_b200 import batch, get_handle, ingest
+    regions = list(synth.config_regions("C3", 6)) + list(synth.config_regions("C2", 4, start=17))
+    d = str(tmp_path)
+    refs, fqs, scs, nms = [], [], [], []
+    for r in regions:
+        ref_f, _ref_r, fq, sc = _write_region_files(r, d)
+        nm = None
+        if r.normal_reads:
+            nm = os.path.join(d, r.name + "_normal.fastq")
+            with open(nm, "w") as f:
+                for rec in r.normal_reads:
+                    f.write("%s\n%s\n+\n%s\n" % (rec[0] if rec[0].startswith("@") else "@" + rec[0], rec[1], "I" * len(rec[1])))
+        refs.append(ref_f); fqs.append(fq); scs.append(sc); nms.append(nm)
+    h = get_handle()
+    want = batch.run(h, batch.PackedBatch(regions, with_normal=True))
+    want_rec = [(want.sample_only(i), want.contig_records(i)) for i in range(len(regions))]
+    g = ingest.Ingest(n_threads=4)                      # pinned buffer
+    pk = g.files(refs, fqs, scs, normal=nms, k=15, rc_thresh=regions[0].rc_thresh)
+    got = batch.run(h, pk)
+    assert [(got.sample_only(i), got.contig_records(i)) for i in range(len(regions))] == want_rec
+    assert sum(len(c) for _s, c in want_rec) > 0
+    g.close()
