@@ -521,4 +521,15 @@ int bk_ingest_files(bk_ingest_t g, int32_t n_regions, const char* const* ref_fa,
   });
 }
 
+int bk_write_contigs(bk_ingest_t g, const bk_batch_result* res, const bk_batch_input* in, const bk_ingest_text* text,
+                     const char* const* contigs_dir, const char* const* cluster_fn, int64_t* n_files) {
+  return guarded_ingest(g, [&] {
+    if (!res || !in || !text || !contigs_dir) fail(BK_ERR_ARG, "bk_write_contigs: bad arguments");
+    if (in->k < 1 || in->k > 31) fail(BK_ERR_ARG, "bk_write_contigs: in->k must be the k of the batch");
+    IngestText t{text->id_bytes, text->id_off, text->qual_bytes, text->qual_off, text->n_reads, text->read_flags};
+    const int64_t n = write_contig_files(g->g, res, in, &t, contigs_dir, cluster_fn, in->k);
+    if (n_files) *n_files = n;
+  });
+}
+
 }  // extern "C"

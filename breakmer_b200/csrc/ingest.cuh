@@ -330,3 +330,99 @@ void ingest_texts(Ingest& g, int n, const TextView* ref, const TextView* reads, 
 }
 
 }  // namespace bk
+
+// ---- contig hand-off -------------------------------------------
+// The files sv_processor.contig.setup writes for every contig before blat (sv_processor.py:749-782),
+// for all contigs of a batch result at once, on host threads:
+//   <contigs_dir>/<id>/<id>.fq   reads of the contig: id, seq, "+", qual             (write_read_fq, :767-772)
+//   <contigs_dir>/<id>/<id>.fa   ">contig1\n" + sequence, no trailing newline         (write_contig_fa, :776-781)
+//   <cluster_fn>                 "<id> <n kmers>\n<mers,>\n<read ids,>\n\n"; opened with 'w' for every contig
+//                                (:758-763), so what survives is the LAST contig of the target -- only that is written
+// id = "contig<n>", n = 1, 2, ... in acceptance order (resolve_sv, sv_processor.py:649-653).
+// Order policy: the reference iterates a Python set of reads (arbitrary order); here reads are written in the
+// order of ctg_reads.
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <errno.h>
+
+namespace bk {
+
+inline bool make_dirs(const std::string& path) {
+  std::string cur;
+  size_t i = 0;
+  while (i <= path.size()) {
+    const size_t j = path.find('/', i);
+    const size_t e = j == std::string::npos ? path.size() : j;
+    cur = path.substr(0, e);
+    if (!cur.empty() && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST) return false;
+    if (j == std::string::npos) break;
+    i = j + 1;
+  }
+  struct stat st;
+  return stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
+inline bool write_whole_file(const std::string& path, const std::string& data) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = data.empty() || fwrite(data.data(), 1, data.size(), f) == data.size();
+  return (fclose(f) == 0) && ok;
+}
+
+inline void append_mer(std::string& s, uint64_t code, int k) {
+  for (int t = k - 1; t >= 0; --t) s.push_back("ACGT"[(code >> (2 * t)) & 3u]);
+}
+
+template <typename Result, typename BatchInput>
+int64_t write_contig_files(Ingest& g, const Result* res, const BatchInput* in, const IngestText* text,
+                           const char* const* contigs_dir, const char* const* cluster_fn, int k) {
+  const int R = res->n_regions;
+  struct Job { int region; int64_t contig; int ordinal; bool last; };
+  std::vector<Job> jobs;
+  for (int r = 0; r < R; ++r) {
+    if (!contigs_dir[r] || !contigs_dir[r][0]) continue;
+    const int64_t a = res->ctg_reg_off[r], b = res->ctg_reg_off[r + 1];
+    for (int64_t c = a; c < b; ++c) jobs.push_back({r, c, (int)(c - a) + 1, c + 1 == b});
+  }
+  std::atomic<int64_t> n_files{0};
+  std::atomic<int> failed{-1};
+  g.parallel_for((int)jobs.size(), [&](int ji) {
+    const Job& J = jobs[ji];
+    const std::string id = "contig" + std::to_string(J.ordinal);
+    const std::string dir = std::string(contigs_dir[J.region]) + "/" + id;
+    if (!make_dirs(dir)) { failed = ji; return; }
+    const int64_t so = res->ctg_seq_off[2 * J.contig], sl = res->ctg_seq_off[2 * J.contig + 1];
+    const int64_t ro = res->ctg_reads_off[2 * J.contig], nr = res->ctg_reads_off[2 * J.contig + 1];
+    const int64_t ko = res->ctg_kmers_off[2 * J.contig], nk = res->ctg_kmers_off[2 * J.contig + 1];
+    std::string fq, ids;
+    for (int64_t i = 0; i < nr; ++i) {
+      const int64_t rec = res->ctg_reads[ro + i];
+      const char* idp = text->id_bytes + text->id_off[rec];
+      const size_t idn = (size_t)(text->id_off[rec + 1] - text->id_off[rec]);
+      fq.append(idp, idn); fq.push_back('\n');
+      fq.append(in->read_bases + in->read_off[rec], (size_t)(in->read_off[rec + 1] - in->read_off[rec]));
+      fq.append("\n+\n");
+      fq.append(text->qual_bytes + text->qual_off[rec], (size_t)(text->qual_off[rec + 1] - text->qual_off[rec]));
+      fq.push_back('\n');
+      if (J.last && cluster_fn && cluster_fn[J.region]) { if (i) ids.push_back(','); ids.append(idp, idn); }
+    }
+    std::string fa = ">contig1\n";
+    fa.append(res->ctg_seq + so, (size_t)sl);
+    if (!write_whole_file(dir + "/" + id + ".fq", fq) || !write_whole_file(dir + "/" + id + ".fa", fa)) { failed = ji; return; }
+    n_files += 2;
+    if (J.last && cluster_fn && cluster_fn[J.region] && cluster_fn[J.region][0]) {
+      std::string cl = id + " " + std::to_string(nk) + "\n";
+      for (int64_t e = 0; e < nk; ++e) { if (e) cl.push_back(','); append_mer(cl, res->ctg_kmer_mer[ko + e], k); }
+      cl.push_back('\n');
+      cl += ids;
+      cl += "\n\n";
+      if (!write_whole_file(cluster_fn[J.region], cl)) { failed = ji; return; }
+      n_files += 1;
+    }
+  });
+  if (failed >= 0) fail(BK_ERR_IO, "cannot write the files of contig %d of region %d under %s", jobs[failed].ordinal,
+                        jobs[failed].region, contigs_dir[jobs[failed].region]);
+  return n_files.load();
+}
+
+}  // namespace bk

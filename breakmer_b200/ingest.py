@@ -172,3 +172,23 @@ class Ingest:
         text = _lib.IngestText()
         self._check(self.lib.bk_ingest_files(self.g, n, arr(ref), arr(reads), arr(sc), arr(normal), byref(s), byref(text)))
         return IngestedBatch(self, s, text, n, k, rc_thresh, names, normal is not None, with_ref)
+
+    def write_contigs(self, res, pk, contigs_dirs, cluster_fns=None):
+        """bk_write_contigs: the contig.setup files (sv_processor.py:749-782) of every contig of `res`, the raw
+        result (batch.run(..., decode=False)) of the call made with the IngestedBatch `pk`.  Returns the number
+        of files written."""
+        n = pk.n
+
+        def arr(lst):
+            if lst is None:
+                return None
+            a = (c_char_p * max(n, 1))()
+            for i, p in enumerate(lst):
+                a[i] = p.encode() if p else None
+            return a
+
+        nf = ctypes.c_int64(0)
+        s = pk.struct()
+        self._check(self.lib.bk_write_contigs(self.g, byref(res), byref(s), byref(pk._text), arr(contigs_dirs),
+                                              arr(cluster_fns), byref(nf)))
+        return int(nf.value)

@@ -30,6 +30,9 @@ normal_fq) are parsed by the library's host threads straight into page-locked me
 (bk_ingest_files).  The reads of the returned contigs are then
 fresh fq_read objects built from the parsed records (same .id/.seq/.qual/.indel_only as the
 caller's; of these the rest of the reference only reads .id/.seq/.qual).
+`write_contigs=True` additionally writes, for every contig of every target, the files
+contig.setup writes before blat (sv_processor.py:749-782) under target.paths['contigs'], on the
+library's host threads (bk_write_contigs).
 """
 import os
 
@@ -91,7 +94,7 @@ class _K:
         self.k = k
 
 
-def compare_kmers_batch(targets, device=0, ingest="python"):
+def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False):
     import numpy as np
     if not targets:
         return
@@ -116,7 +119,15 @@ def compare_kmers_batch(targets, device=0, ingest="python"):
         objs = [o for inp in inputs for o in inp.objs]
     else:
         raise ValueError("ingest must be 'python' or 'native'")
-    out = batch.run(get_handle(device), pk)
+    if write_contigs and ingest != "native":
+        raise ValueError("write_contigs needs ingest='native' (the writer reads the parsed record text)")
+    res = batch.run(get_handle(device), pk, decode=False)
+    if write_contigs:
+        # contig.setup's files for every contig of every target in one pass (sv_processor.py:749-782, bk_write_contigs);
+        # the reference-side contig.__init__ then skips its own setup() call
+        _get_ingest().write_contigs(res, pk, [t.paths['contigs'] for t in targets],
+                                    [os.path.join(t.paths['kmers'], t.name + "_sample_kmers_merged.out") for t in targets])
+    out = batch.BatchOutput(res, pk)
     for i, trgt in enumerate(targets):
         if out.region_status[i] != 0:
             raise RuntimeError("compare_kmers: device capacity exceeded for target %s" % trgt.name)

@@ -203,6 +203,20 @@ int bk_ingest_buffers(bk_ingest_t g, int32_t n_regions, const bk_text* ref_fa, c
 int bk_ingest_files(bk_ingest_t g, int32_t n_regions, const char* const* ref_fa, const char* const* reads_fq,
                     const char* const* sc_fa, const char* const* normal_fq, bk_batch_input* in, bk_ingest_text* text);
 
+/* ---- contig hand-off --------------------------------------------
+ * The files sv_processor.contig.setup writes for every contig before blat
+ * (sv_processor.py:749-782), for ALL contigs of a batch result on the ingest object's host threads:
+ *   <contigs_dir[r]>/contig<n>/contig<n>.fq   write_read_fq   (:767-772)  id, seq, "+", qual per read
+ *   <contigs_dir[r]>/contig<n>/contig<n>.fa   write_contig_fa (:776-781)  ">contig1\n" + sequence
+ *   <cluster_fn[r]>                           write_cluster_file (:758-763) of the target's LAST contig
+ *                                             (the reference reopens the file with 'w' for every contig)
+ * n = 1.. in acceptance order (resolve_sv, sv_processor.py:649-653).  `res` is the result of the
+ * bk_compare_kmers_batch call made with `in`; `in` and `text` come from bk_ingest_* (in->k set).
+ * contigs_dir[r] NULL/"" skips region r; cluster_fn may be NULL.  Reads are written in ctg_reads
+ * order (the reference iterates a Python set: no defined order). */
+int bk_write_contigs(bk_ingest_t g, const bk_batch_result* res, const bk_batch_input* in, const bk_ingest_text* text,
+                     const char* const* contigs_dir, const char* const* cluster_fn, int64_t* n_files);
+
 #ifdef __cplusplus
 }
 #endif

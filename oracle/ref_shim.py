@@ -153,3 +153,24 @@ def load_readers():
     ns = {"open": lambda fn, mode="r": builtins.open(fn, mode, newline="\n")}
     exec(compile(text, os.path.join(REFERENCE_ROOT, "utils.py"), "exec"), ns)
     return types.SimpleNamespace(fq_read=ns["fq_read"], FastqFile=ns["FastqFile"], get_fastq_reads=ns["get_fastq_reads"])
+
+
+def load_contig_writers():
+    """A class holding the reference's own ``setup`` / ``write_cluster_file`` / ``write_read_fq`` /
+    ``write_contig_fa`` methods of ``sv_processor.contig`` (sv_processor.py:749-782), cut out of the file's
+    text (the module as a whole needs pysam) -- used to pin the contig hand-off row.
+    No rewrites are needed."""
+    fn = os.path.join(REFERENCE_ROOT, "sv_processor.py")
+    if not os.path.isfile(fn):
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    with open(fn) as f:
+        src = f.read().expandtabs(8)
+    a = re.search(r"^  def setup\(self, cluster_fn\) :", src, flags=re.M)
+    b = re.search(r"^  def has_result\(self\) :", src, flags=re.M)
+    if a is None or b is None or b.start() < a.start():
+        raise RuntimeError("ref_shim: contig writers not found")
+    text = "class contig_writers:\n" + src[a.start():b.start()]
+    import logging
+    ns = {"os": os, "logging": logging}
+    exec(compile(text, fn, "exec"), ns)
+    return ns["contig_writers"]

@@ -150,8 +150,15 @@ def test_compare_kmers_native_ingest(tmp_path):
     from breakmer_b200 import sv_processor
     regions = [synth.make_region(n, **kw) for n, kw in region_scenarios()[:10] if kw["k"] == 15]
     targets = [_Target(r, str(tmp_path)) for r in regions]
-    sv_processor.compare_kmers_batch(targets, ingest="native")
+    for t in targets:
+        t.paths["contigs"] = os.path.join(str(tmp_path), t.name, "contigs")
+    sv_processor.compare_kmers_batch(targets, ingest="native", write_contigs=True)
     for r, t in zip(regions, targets):
+        for n, ct in enumerate(t.kmers["clusters"], 1):
+            with open(os.path.join(t.paths["contigs"], "contig%d" % n, "contig%d.fa" % n)) as f:
+                assert f.read() == ">contig1\n" + ct.get_contig_seq()
+            with open(os.path.join(t.paths["contigs"], "contig%d" % n, "contig%d.fq" % n)) as f:
+                assert sorted(f.read().splitlines()[0::4]) == sorted(x.id for x in ct.reads)
         _a, _b, _c, only = oracle_sample_only(r)
         exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
         with open(t.files["sample_kmers"]) as f:
