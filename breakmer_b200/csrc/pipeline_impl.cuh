@@ -514,7 +514,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   const size_t need_smem = spec_w == 8 ? assemble_smem_bytes<8>() : (spec_w == 4 ? assemble_smem_bytes<4>() :
                            (spec_w == 2 ? assemble_smem_bytes<2>() : assemble_smem_bytes<1>()));
   int dyn_smem = (int)((227 * 1024) / ctas_per_sm) - 1024;
-  if (dyn_smem < (int)need_smem) dyn_smem = (int)need_smem;
+  if (dyn_smem < (int)need_smem || getenv("BK_ASM_NO_PAD")) dyn_smem = (int)need_smem;
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
