@@ -439,6 +439,11 @@ def gpu_arm(args):
                              "see roofline_alu and roofline_kstage"},
         "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": int_peak_cells,
                          "unit": "DP cell updates/s", "frac": cells_per_s / int_peak_cells if int_peak_cells else None,
+                         "achieved_in_flight": n_cells * args.steps / dev_s,
+                         "frac_in_flight": (n_cells * args.steps / dev_s) / int_peak_cells if int_peak_cells else None,
+                         "note": "`achieved`/`frac`: one launch alone (sequential pass; bounded by the longest region's serial "
+                                 "chain, most SMs idle in the tail); `*_in_flight`: all DP cells of the timed region / its device "
+                                 "time with %d batches in flight (other stages included)" % n_fly,
                          "peak_source": "148 SM x 4 SMSP x 16 alu lanes/clk x measured sm clock / 8 alu-pipe instructions per cell; "
                                         "ncu: pipe_alu 48% busy on active SMs, launch bounded by the longest region (profiles/r1_assemble_kernel.md)"},
         "roofline_kstage": {"kernel": "rs_scatter_kernel", "bound": "hbm", "achieved": sort_gbs, "peak": hbm_peak,
@@ -552,7 +557,7 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
