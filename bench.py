@@ -296,7 +296,8 @@ def gpu_arm(args):
                 torch.cuda.synchronize()
             res = batch.run(hh, pk, resident=True, decode=False)
             last_box[j] = (int(res.n_contigs), int(res.n_check_align), int(res.n_dp_cells),
-                           int(res.n_kmer_occurrences), int(res.so_off[res.n_regions]), float(res.gpu_ms))
+                           int(res.n_kmer_occurrences), int(res.so_off[res.n_regions]), float(res.gpu_ms),
+                           int(res.n_sorted_keys))
 
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
@@ -321,7 +322,7 @@ def gpu_arm(args):
     step_ms = [1000.0 * dev_s / args.steps] * args.steps
     n_regions_total = per_gpu * world
     value = n_regions_total * args.steps / dev_s
-    n_contigs, n_check, n_cells, n_occ, n_only, _ = last_box[0]
+    n_contigs, n_check, n_cells, n_occ, n_only, _, n_sorted = last_box[0]
     kmers_per_s = sum_over_ranks(float(n_only)) * args.steps / dev_s
 
     # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------------------
@@ -405,7 +406,7 @@ def gpu_arm(args):
     asm_bytes = uniq_bases + 12 * n_only + d2h
     asm_gbs = asm_bytes / (asm_ms_per_launch * 1e-3) / 1e9 if asm_ms_per_launch > 0 else 0.0
     sc_ms, sc_n = ktimes["sort_scatter"]
-    sort_bytes = 2 * 12 * n_occ          # one pass: keys+values read once, written once
+    sort_bytes = 2 * 12 * n_sorted       # one pass: keys+values of the sorted (sample) windows read once, written once
     sort_gbs = sort_bytes / (sc_ms / max(1, sc_n) * 1e-3) / 1e9 if sc_ms > 0 else 0.0
     cells_per_s = n_cells * kt_steps / (asm_ms * 1e-3) if asm_ms > 0 else 0.0
     sm_mhz = clocks.get("sm_mhz") or 1965.0
@@ -429,7 +430,7 @@ def gpu_arm(args):
         "sample_only_kmers_per_s": kmers_per_s,
         "with_ref_kmer_cache": ref_cache,
         "per_step": {"contigs": n_contigs, "check_align_calls": n_check, "dp_cells": n_cells,
-                     "kmer_occurrences": n_occ, "sample_only_kmers": n_only},
+                     "kmer_occurrences": n_occ, "sorted_keys": n_sorted, "sample_only_kmers": n_only},
         "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": asm_gbs / hbm_peak, "traffic": asm_traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": asm_ms_per_launch,

@@ -56,6 +56,7 @@ class BatchResult(Structure):
         ("region_status", POINTER(c_int32)),
         ("n_check_align", c_int64), ("n_dp_cells", c_int64), ("n_kmer_occurrences", c_int64),
         ("gpu_ms", c_double),
+        ("n_sorted_keys", c_int64),
     ]
 
 

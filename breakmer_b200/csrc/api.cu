@@ -4,6 +4,7 @@
 #include "../../include/breakmer_b200.h"
 
 #include <algorithm>
+#include <functional>
 #include <memory>
 
 #include "host_util.cuh"
@@ -82,8 +83,17 @@ struct SelectOut {
   uint32_t* seg_counts;   // device, n_seg (or null)
 };
 
+// candidate hash table handed to the caller's probe callback (kmers.cuh, probe mode)
+struct ProbeTable {
+  const uint64_t* keys;
+  const uint32_t* idx;
+  uint64_t mask;
+  uint8_t* dead;
+};
+
 SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int seg_bits, int mode,
-                          int64_t n_seg, bool use_ref_cache = false, int seg_shift = 0) {
+                          int64_t n_seg, bool use_ref_cache = false, int seg_shift = 0,
+                          const std::function<void(const ProbeTable&)>& probe = nullptr) {
   SelectOut o{nullptr, nullptr, 0, nullptr};
   cudaStream_t st = h->st;
   if (n_seg > 0) {
@@ -125,12 +135,52 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
   o.mers = h->dev.get<uint64_t>(o.n ? o.n : 1);
   o.counts = h->dev.get<uint32_t>(o.n ? o.n : 1);
   rp.pos = pos; rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts;
-  {
+  if (!probe || o.n == 0) {
     TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
     run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
+    BK_CUDA(cudaGetLastError());
+    return o;
+  }
+  // ---- probe mode: the selected runs are only candidates; the caller streams further windows past them -----------
+  const int64_t n_cand = o.n;
+  uint32_t* cand_seg = h->dev.get<uint32_t>(n_cand);
+  rp.seg_counts = nullptr; rp.out_seg = cand_seg;
+  uint64_t cap = 1024;
+  while (cap < 2 * (uint64_t)n_cand) cap <<= 1;
+  uint64_t* tkeys = h->dev.get<uint64_t>(cap);
+  uint32_t* tidx = h->dev.get<uint32_t>(cap);
+  uint8_t* dead = h->dev.get<uint8_t>(n_cand);
+  BK_CUDA(cudaMemsetAsync(tkeys, 0xFF, cap * sizeof(uint64_t), st));
+  BK_CUDA(cudaMemsetAsync(dead, 0, n_cand, st));
+  {
+    TimedLaunch t(h->timers, st, KF_RUN_SCATTER, 2);
+    run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
+    cand_insert_kernel<<<blocks, 256, 0, st>>>(rp, tkeys, tidx, cap - 1);
+  }
+  probe(ProbeTable{tkeys, tidx, cap - 1, dead});
+  uint32_t* flags2 = h->dev.get<uint32_t>(n_cand);
+  uint32_t* pos2 = h->dev.get<uint32_t>(n_cand);
+  uint32_t* scan_tmp2 = h->dev.get<uint32_t>(scan_tmp_elems(n_cand));
+  const unsigned blocks2 = (unsigned)((n_cand + 255) / 256);
+  {
+    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
+    survivor_flag_kernel<<<blocks2, 256, 0, st>>>(dead, n_cand, flags2);
+  }
+  {
+    TimedLaunch t(h->timers, st, KF_SCAN, 3);
+    exclusive_scan_u32(flags2, pos2, n_cand, scan_tmp2, d_total, st);
+  }
+  BK_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  BK_CUDA(cudaStreamSynchronize(st));
+  SelectOut f{nullptr, nullptr, (int64_t)*h_total, o.seg_counts};
+  f.mers = h->dev.get<uint64_t>(f.n ? f.n : 1);
+  f.counts = h->dev.get<uint32_t>(f.n ? f.n : 1);
+  {
+    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
+    survivor_scatter_kernel<<<blocks2, 256, 0, st>>>(flags2, pos2, n_cand, o.mers, o.counts, cand_seg, f.mers, f.counts, f.seg_counts);
   }
   BK_CUDA(cudaGetLastError());
-  return o;
+  return f;
 }
 
 }  // namespace

@@ -16,6 +16,11 @@
 //                      set they came from, so (case & case_sc) - ref [- normal]
 //                      is a property of the run.
 //   run_scatter_kernel compaction of the selected runs to (mer, count) arrays.
+//   probe mode         the batched pipeline does not sort the reference (or normal) windows at all: it sorts only
+//                      the sample's windows, selects case & case_sc, puts those candidates in a hash table
+//                      (cand_insert_kernel) and streams the reference / normal windows past it with
+//                      kmer_emit_kernel in probe mode -- a hit marks the candidate dead -- then compacts the
+//                      survivors (survivor_* kernels).  Same set algebra, ~4x fewer keys through the sort.
 //
 // Key layout:    [ 0 | region | mer (2k bits) ]          (one spare top bit: the all-ones invalid key sorts last)
 // Value layout:  [ set tag : 2 | multiplicity : 30 ]
@@ -46,7 +51,30 @@ struct EmitParams {
   uint64_t* keys;             // [out_base + p] forward, [out_base_rc + p] reverse complement
   uint32_t* vals;
   int64_t out_base, out_base_rc;
+  // probe mode (probe_keys != null): nothing is written; every valid window (and its reverse complement if emit_rc)
+  // is looked up in the open-addressed candidate table and a hit sets dead[probe_idx[slot]]
+  const uint64_t* probe_keys;
+  const uint32_t* probe_idx;
+  uint64_t probe_mask;
+  uint8_t* dead;
 };
+
+__device__ __forceinline__ uint64_t cand_hash(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 29;
+  return x;
+}
+
+__device__ __forceinline__ void probe_candidate(const EmitParams& P, uint64_t key) {
+  uint64_t slot = cand_hash(key) & P.probe_mask;
+  for (;;) {
+    const uint64_t t = P.probe_keys[slot];
+    if (t == key) { P.dead[P.probe_idx[slot]] = 1; return; }
+    if (t == KEY_INVALID) return;
+    slot = (slot + 1) & P.probe_mask;
+  }
+}
 
 __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
   __shared__ uint8_t code[EMIT_TILE + 32];
@@ -121,6 +149,13 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
       if (P.rec_mult) mult = P.rec_mult[rec];
     }
     const uint64_t hi = seg << (2 * k);
+    if (P.probe_keys) {
+      if (ok) {
+        probe_candidate(P, hi | fwd);
+        if (P.emit_rc) probe_candidate(P, hi | rc);
+      }
+      continue;
+    }
     const uint32_t v = (mult & 0x3FFFFFFFu) | ((uint32_t)P.tag << 30);
     P.keys[P.out_base + p] = ok ? (hi | fwd) : KEY_INVALID;
     P.vals[P.out_base + p] = v;
@@ -147,6 +182,7 @@ struct RunParams {
   uint64_t* out_mers;
   uint32_t* out_counts;
   uint32_t* seg_counts;       // per region number of selected runs (atomic), may be null
+  uint32_t* out_seg;          // region of each selected run, may be null (probe mode)
   // optional persistent reference k-mer cache: sorted mers of region r at ref_mers[ref_koff[r] .. ref_koff[r+1])
   const uint64_t* ref_mers;
   const int64_t* ref_koff;
@@ -207,7 +243,45 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(RunParams P) {
   const uint32_t dst = P.pos[i];
   P.out_mers[dst] = mer;
   P.out_counts[dst] = P.run_count[i];
+  if (P.out_seg) P.out_seg[dst] = (uint32_t)(g >> (2 * P.k));
   if (P.seg_counts) atomicAdd(&P.seg_counts[(uint32_t)(g >> (2 * P.k))], 1u);
+}
+
+// ---- probe mode: candidate hash table + survivor compaction -------------------------------------------------
+// insert every selected run head [region | mer] -> its compacted index
+__global__ void __launch_bounds__(256) cand_insert_kernel(RunParams P, uint64_t* __restrict__ tkeys,
+                                                          uint32_t* __restrict__ tidx, uint64_t mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  if (!P.flags[i]) return;
+  const uint64_t key = P.keys[i];
+  uint64_t slot = cand_hash(key) & mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS((unsigned long long*)&tkeys[slot], (unsigned long long)KEY_INVALID,
+                                              (unsigned long long)key);
+    if (prev == (unsigned long long)KEY_INVALID) { tidx[slot] = P.pos[i]; return; }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) survivor_flag_kernel(const uint8_t* __restrict__ dead, int64_t n,
+                                                            uint32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = dead[i] ? 0u : 1u;
+}
+
+__global__ void __launch_bounds__(256) survivor_scatter_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos,
+                                                               int64_t n, const uint64_t* __restrict__ in_mers,
+                                                               const uint32_t* __restrict__ in_counts,
+                                                               const uint32_t* __restrict__ in_seg,
+                                                               uint64_t* __restrict__ out_mers, uint32_t* __restrict__ out_counts,
+                                                               uint32_t* __restrict__ seg_counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  const uint32_t dst = pos[i];
+  out_mers[dst] = in_mers[i];
+  out_counts[dst] = in_counts[i];
+  atomicAdd(&seg_counts[in_seg[i]], 1u);
 }
 
 }  // namespace bk

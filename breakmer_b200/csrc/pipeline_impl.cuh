@@ -174,7 +174,7 @@ inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per
 
 // k-mer windows of the records of regions [r0, r1) of one input set
 void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag, bool rc, uint64_t* keys, uint32_t* vals,
-              int64_t base, int64_t base_rc) {
+              int64_t base, int64_t base_rc, const ProbeTable* probe = nullptr) {
   if (rs.reg_base.empty()) return;
   const int64_t b0 = rs.reg_base[r0], b1 = rs.reg_base[r1];
   if (b1 == b0) return;
@@ -183,6 +183,7 @@ void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag
   E.bases = rs.bases + b0; E.n_bases = b1 - b0; E.rec_off = rs.koff + kr0; E.n_rec = kr1 - kr0; E.rec_seg = rs.kseg + kr0;
   E.rec_mult = nullptr; E.k = k; E.tag = tag; E.emit_rc = rc ? 1 : 0; E.off_shift = b0; E.seg_shift = r0;
   E.keys = keys; E.vals = vals; E.out_base = base; E.out_base_rc = base_rc;
+  if (probe) { E.probe_keys = probe->keys; E.probe_idx = probe->idx; E.probe_mask = probe->mask; E.dead = probe->dead; }
   TimedLaunch t(h->timers, h->st, KF_EMIT);
   kmer_emit_kernel<<<nblk(E.n_bases, EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
 }
@@ -328,6 +329,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   } else {
     const int64_t n_keys = 2 * p.ref.n_bases + p.reads.n_bases + p.sc.n_bases + p.normal.n_bases;
     out->n_kmer_occurrences = n_keys;
+    int64_t n_sorted = 0;
     // The sort key is [0 | region | mer]: 2k + region bits + 1 <= 64.  Large k leaves few region bits, so the stage runs
     // over chunks of regions (one chunk for the usual k); selected mers come out in (region, mer) order either way.
     const int max_seg_bits = 63 - 2 * k;
@@ -339,24 +341,29 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     for (int r0 = 0; r0 < R; r0 += chunk) {
       const int r1 = std::min(R, r0 + chunk);
       const int64_t nr = span(p.ref, r0, r1), nd = span(p.reads, r0, r1), ns = span(p.sc, r0, r1), nn = span(p.normal, r0, r1);
-      const int64_t nk = 2 * nr + nd + ns + nn;
-      if (nk >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows in one chunk; use fewer regions per call");
+      // Only the sample's windows are sorted.  The reference (forward + reverse FASTA, Q2) and normal (K4) windows are
+      // streamed past the candidates (case & case_sc) afterwards: a hit removes the candidate.
+      const bool probe_ref = nr > 0 && !p.use_ref_cache, probe_normal = nn > 0;
+      const int64_t nk = nd + ns;
+      if (2 * nr + nk + nn >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows in one chunk; use fewer regions per call");
+      n_sorted += nk;
       uint64_t* keys = h->dev.get<uint64_t>(nk);
       uint32_t* vals = h->dev.get<uint32_t>(nk);
-      int64_t at = 0;
-      emit_set(h, p.ref, r0, r1, k, TAG_REF, true, keys, vals, at, at + nr);      // forward + reverse FASTA (Q2)
-      at += 2 * nr;
-      emit_set(h, p.reads, r0, r1, k, TAG_CASE, false, keys, vals, at, 0);        // every record, duplicates included (Q3)
-      at += nd;
-      emit_set(h, p.sc, r0, r1, k, TAG_SC, false, keys, vals, at, 0);
-      at += ns;
-      emit_set(h, p.normal, r0, r1, k, TAG_NORMAL, false, keys, vals, at, 0);     // K4
+      emit_set(h, p.reads, r0, r1, k, TAG_CASE, false, keys, vals, 0, 0);         // every record, duplicates included (Q3)
+      emit_set(h, p.sc, r0, r1, k, TAG_SC, false, keys, vals, nd, 0);
+      std::function<void(const ProbeTable&)> probe;
+      if (probe_ref || probe_normal)
+        probe = [&, r0, r1](const ProbeTable& T) {
+          if (probe_ref) emit_set(h, p.ref, r0, r1, k, TAG_REF, true, nullptr, nullptr, 0, 0, &T);
+          if (probe_normal) emit_set(h, p.normal, r0, r1, k, TAG_NORMAL, false, nullptr, nullptr, 0, 0, &T);
+        };
       ChunkOut co;
-      co.so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0, p.use_ref_cache, r0);
+      co.so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0, p.use_ref_cache, r0, probe);
       co.r0 = r0; co.r1 = r1;
       BK_CUDA(cudaMemcpyAsync(seg_counts_all + r0, co.so.seg_counts, (size_t)(r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
       chunks.push_back(co);
     }
+    out->n_sorted_keys = n_sorted;
     if (chunks.size() == 1) {
       S_total = chunks[0].so.n;
       so_mer = chunks[0].so.mers; so_cnt = chunks[0].so.counts;

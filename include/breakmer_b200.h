@@ -137,8 +137,9 @@ typedef struct bk_batch_result {
   /* work counters of this call (for roofline arithmetic) */
   int64_t n_check_align;             /* contig.check_align calls (each = two olc.nw) */
   int64_t n_dp_cells;                /* sum over those of len(contig)*len(read) (one sweep each) */
-  int64_t n_kmer_occurrences;        /* windows emitted by the k-mer stage */
+  int64_t n_kmer_occurrences;        /* k-mer windows of all inputs (reference forward + reverse, reads, soft clips, normal) */
   double  gpu_ms;                    /* device time of the call, CUDA events */
+  int64_t n_sorted_keys;             /* windows that went through the sort (the sample's; the rest are streamed past) */
 } bk_batch_result;
 
 int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out);
