@@ -414,7 +414,7 @@ def gpu_arm(args):
     int_peak_cells = 148 * 4 * 16 * sm_mhz * 1e6 / 8.0
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_*.md); only valid for the default workload
     asm_traffic = 35980288 if (args.workload == "C2" and per_gpu == 500) else None
-    sort_traffic = 460892928 if (args.workload == "C2" and per_gpu == 500) else None
+    sort_traffic = 191033344 if (args.workload == "C2" and per_gpu == 500) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
