@@ -13,3 +13,11 @@ for w in (4, 1):
     h.set_option("spec_width", w)
     o = batch.run(h, batch.PackedBatch(regions))
     print(w, o.n_contigs, o.n_check_align)
+# normal-sample subtraction (probe mode with two streamed sets) and a batch without reference windows
+nregs = list(synth.config_regions("C3", 2))
+o = batch.run(h, batch.PackedBatch(nregs, with_normal=True))
+print("normal", o.n_contigs, int(o.so_off[-1]))
+h.ref_cache_build([r.ref_fwd for r in regions], 15)
+o = batch.run(h, batch.PackedBatch(regions, with_ref=False))
+print("ref cache", o.n_contigs)
+h.ref_cache_clear()
