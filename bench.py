@@ -226,7 +226,7 @@ def gpu_arm(args):
     desc, per_gpu = WORKLOADS[args.workload]
     if args.regions:
         per_gpu = args.regions
-    regions = make_regions(args.workload, per_gpu, rank)
+    regions = make_regions(args.workload, per_gpu, rank + args.slice)
     pk = batch.PackedBatch(regions).pin()        # pinned host buffers for the end-to-end leg
     h = _lib.Handle(local_rank)
     hbm_peak, peak_src = load_peaks()
@@ -568,6 +568,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
     ap.add_argument("--no-ingest-leg", action="store_true")
+    ap.add_argument("--slice", type=int, default=0, help="use the regions rank+SLICE would own (debugging)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
