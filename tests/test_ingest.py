@@ -175,3 +175,24 @@ def test_missing_file_and_flag_override(ing, tmp_path):
     fl = pk.struct().read_flags
     import ctypes
     assert list((ctypes.c_uint8 * 2).from_address(fl)) == [1, 0]
+
+
+def test_parsers_under_address_sanitizer():
+    """tests/sim/ingest_fuzz.cpp: the readers of csrc/ingest.cuh compiled by g++ with ASan + UBSan and driven with
+    random and corrupted texts (layout invariants checked, memory errors abort)."""
+    import shutil
+    import subprocess
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("g++") is None or not os.path.isdir(os.path.join(cuda, "include")):
+        pytest.skip("g++ / CUDA headers not available")
+    sim = os.path.join(HERE, "sim")
+    exe = os.path.join(sim, "ingest_fuzz")
+    src = os.path.join(sim, "ingest_fuzz.cpp")
+    dep = os.path.join(HERE, "..", "breakmer_b200", "csrc", "ingest.cuh")
+    if not os.path.isfile(exe) or max(os.path.getmtime(src), os.path.getmtime(dep)) > os.path.getmtime(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-I", os.path.join(cuda, "include"),
+                               "-o", exe, src, "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lpthread"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe, "1500"], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "parsed" in out.stdout
