@@ -6,8 +6,9 @@
 A "step" is one pass of the whole hot path (target.compare_kmers: k-mer counting,
 sample-only selection, read grouping, init_assembly) over one batch of synthetic
 target regions.  At N=1 the workload is BASELINE.json configs[1]: the 500-target
-gene panel (k=15).  With N ranks every rank owns its own 500 regions of the same
-generator (weak scaling, regions sharded by rank, no data-path collective).
+gene panel (k=15).  With N ranks every rank owns its own batch of 500 regions -- one sample of
+the panel per GPU, the same per-GPU problem on every rank (weak scaling, regions sharded by rank,
+no data-path collective).
 
 One JSON line is printed by rank 0.  `value` is whole-job regions/s with the
 batch already resident in HBM; `e2e` is the same metric through the C-ABI entry
@@ -46,9 +47,13 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_regions(workload, n, rank):
+def make_regions(workload, n, slice_index):
+    """The regions of one GPU.  Weak scaling runs the SAME per-GPU problem on every rank (one sample of the panel per
+    GPU: slice 0 of the generator everywhere), so that the per-N values differ by scaling effects only -- distinct slices
+    of the generator differ by +-5 % in DP work and 15 % in their longest region (profiles/r1_scaling.md); `--slice`
+    selects another one."""
     from breakmer_b200 import synth
-    return list(synth.config_regions(workload, n=n, start=rank * n))
+    return list(synth.config_regions(workload, n=n, start=slice_index * n))
 
 
 # ---------------------------------------------------------------------------------
@@ -226,7 +231,7 @@ def gpu_arm(args):
     desc, per_gpu = WORKLOADS[args.workload]
     if args.regions:
         per_gpu = args.regions
-    regions = make_regions(args.workload, per_gpu, rank + args.slice)
+    regions = make_regions(args.workload, per_gpu, args.slice)
     pk = batch.PackedBatch(regions).pin()        # pinned host buffers for the end-to-end leg
     h = _lib.Handle(local_rank)
     hbm_peak, peak_src = load_peaks()
@@ -420,6 +425,7 @@ def gpu_arm(args):
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "from_files": from_files,
         "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": pk.k, "rc_thresh": pk.rc_thresh,
+                   "per_gpu_problem": "every rank runs its own batch of the same %d regions (generator slice %d)" % (per_gpu, args.slice),
                    "input_bytes_per_gpu": pk.input_bytes, "steps_in_flight": n_fly, "assembler_spec_width": spec_w,
                    "l2": ("256 MB buffer written between timed steps (flush)" if n_fly == 1 else
                           "%d independent batches in flight on separate buffers; the per-step working set (~0.8 GB of "
@@ -568,7 +574,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
     ap.add_argument("--no-ingest-leg", action="store_true")
-    ap.add_argument("--slice", type=int, default=0, help="use the regions rank+SLICE would own (debugging)")
+    ap.add_argument("--slice", type=int, default=0, help="which 500-region slice of the generator every rank runs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
