@@ -509,7 +509,8 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
             refs.append(base + "_ref.fa"); fqs.append(base + "_reads.fastq"); scs.append(base + "_sc.fa")
             nms.append(base + "_normal.fastq" if any_normal else None)
         normal = nms if any_normal else None
-        cores = os.cpu_count() or 1
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        cores = max(1, (os.cpu_count() or 1) // world)     # this rank's share of the host
         per = max(1, cores // n_fly)
         ings = [ingest.Ingest(n_threads=per) for _ in range(n_fly)]
         kw = dict(normal=normal, k=pk.k, rc_thresh=pk.rc_thresh)

@@ -153,7 +153,7 @@ void pipeline_upload(bk_handle_t h, const bk_batch_input* in) {
   h->resident.reset();
   h->pipe.reset(new Pipeline());
   pipeline_upload_into(h, h->resident, in, *h->pipe);
-  BK_CUDA(cudaStreamSynchronize(h->st));
+  BK_CUDA(stream_wait(h));
 }
 
 template <typename T>
@@ -233,7 +233,7 @@ void ref_cache_build(bk_handle_t h, const char* ref_bases, const int64_t* ref_of
   exclusive_scan_u32(seg_counts_all, seg_excl, R, stmp, d_tot, st);
   widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_tot, R, koff);
   BK_CUDA(cudaGetLastError());
-  BK_CUDA(cudaStreamSynchronize(st));
+  BK_CUDA(stream_wait(h));
   h->ref_cache_mers = mers; h->ref_cache_koff = koff; h->ref_cache_regions = R; h->ref_cache_k = k;
 }
 
@@ -301,7 +301,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
       exclusive_scan_u32(flag, u_index, n_rec, stmp, d_total, st);
     }
     const uint32_t* h_total = to_host(h, d_total, 1);
-    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(stream_wait(h));
     NU = *h_total;
     u_rec = h->dev.get<int32_t>(NU);
     u_mult = h->dev.get<uint32_t>(NU);
@@ -392,7 +392,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   // per-region table sizes decide the field widths of the packed sort keys below
   const int64_t* h_so_off = to_host(h, so_off, (size_t)R + 1);
   const int64_t* h_u_off = to_host(h, u_off, (size_t)R + 1);
-  BK_CUDA(cudaStreamSynchronize(st));
+  BK_CUDA(stream_wait(h));
   int64_t max_s = 1, max_u = 1;
   for (int r = 0; r < R; ++r) {
     max_s = std::max<int64_t>(max_s, h_so_off[r + 1] - h_so_off[r]);
@@ -446,7 +446,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
                                                                                (unsigned long long)cap);
     }
     const unsigned long long* h_n = to_host(h, d_n, 1);
-    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(stream_wait(h));
     n_post = (int64_t)*h_n;
     if (n_post > cap) fail(BK_ERR_CAPACITY, "index: posting overflow");
     post_read = h->dev.get<int32_t>(n_post);
@@ -488,7 +488,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
 
   // work order
   const int* h_overflow = to_host(h, d_overflow, 1);
-  BK_CUDA(cudaStreamSynchronize(st));
+  BK_CUDA(stream_wait(h));
   if (*h_overflow) fail(BK_ERR_CAPACITY, "seed order: a k-mer count or region size exceeds 2^24");
   std::vector<int32_t> order(R);
   std::iota(order.begin(), order.end(), 0);
@@ -590,7 +590,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     h_cursor = to_host(h, A.out_cursor, 5);
     h_stats = to_host(h, A.stats, 16);
     h_status = to_host(h, A.region_status, (size_t)(R ? R : 1));
-    BK_CUDA(cudaStreamSynchronize(st));
+    BK_CUDA(stream_wait(h));
     const bool overflow = h_cursor[0] > A.cap_seq || h_cursor[1] > A.cap_cnt || h_cursor[2] > A.cap_reads ||
                           h_cursor[3] > A.cap_kmers || h_cursor[4] > A.cap_ctg;
     if (!overflow) break;
@@ -667,7 +667,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   out->ctg_kmer_pos = to_host(h, A.o_kmer_pos, (size_t)h_cursor[3]);
   const int32_t* h_meta = to_host(h, A.o_kmer_meta, (size_t)h_cursor[3]);
   BK_CUDA(cudaEventRecord(ev1, st));
-  BK_CUDA(cudaStreamSynchronize(st));
+  BK_CUDA(stream_wait(h));
   float ms = 0;
   BK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   out->gpu_ms = ms;
