@@ -293,6 +293,7 @@ int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t
       P.edge_stride = NW_MAX_LEN + 1;
       P.edge = h->dev.get<int2>((size_t)grid * NWB_WARPS * 2 * P.edge_stride);
     }
+    P.lastcol = h->dev.get<uint2>((size_t)grid * NWB_WARPS * (NW_MAX_LEN / 2 + 1));
     P.want_aln = want_aln;
     if (want_aln) {
       P.ptr_scratch = h->dev.get<uint8_t>(ptr_total);

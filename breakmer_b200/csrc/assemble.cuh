@@ -27,6 +27,7 @@ namespace bk {
 constexpr int ASM_CAP = 4096;          // contig / count-vector capacity (NW_MAX_LEN + 1)
 constexpr int ASM_BUF = 3 * ASM_CAP;   // gap buffers: data starts at ASM_CAP, may grow both ways
 constexpr int ASM_KCAP = 2 * ASM_CAP;  // contig k-mer tuple list capacity
+constexpr int ASM_LASTCOL = ASM_CAP / 2 + 1;   // row pairs of one sweep
 constexpr int ORDER_FOR = 0, ORDER_REV = 1, ORDER_MID = 2;
 
 // Speculation width: the next ASM_SPEC_W reads of a contig's read stream are aligned
@@ -119,6 +120,7 @@ struct AsmParams {
   uint64_t* w_wcode;               // ASM_CAP
   int32_t* w_diff;                 // ASM_CAP + 1
   int2* w_edge;                    // 2 * ASM_CAP int2, or null if no read is longer than 256
+  uint2* w_lastcol;                // ASM_LASTCOL uint2 per warp: last DP column of the sweep in flight (nw.cuh)
   // work distribution
   int* work_counter;
   const int32_t* work_order;       // regions, most expensive first
@@ -195,6 +197,7 @@ struct RegionCtx {
   int seed_anchor;                // setup: gap-buffer coordinate of the seed mer in the contig
   int cur_e;                      // grow: entry of the snapshot being committed
   int2* edge_all;                 // ASM_SPEC_W x (2 * ASM_CAP) int2 or null
+  uint2* lastcol;                 // warp 0's last-column scratch
   // contig under construction
   uint8_t* cseq; int c0, clen;
   int32_t* cnt_buf; int cur, k0, klen;
@@ -499,7 +502,8 @@ BK_DEV void spec_stage(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, int
   if (lane() == 0) sp->lr[w] = lr;
   syncwarp();
 }
-BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_contig, const uint8_t* s_pred, int w, int2* edge) {
+BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_contig, const uint8_t* s_pred, int w, int2* edge,
+                    uint2* lastcol) {
   const uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
   const int lr = sp->lr[w];
   const int b = sp->abuf[w];
@@ -507,7 +511,7 @@ BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_con
   const int lc = sp->la[w];
   NwDual r;
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  nw_dual_dispatch(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, r);
+  nw_dual_dispatch(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, lastcol, r);
   if (lane() == 0) { sp->v1[w] = r.b; sp->v2[w] = r.a; }
   syncwarp();
 }
@@ -619,10 +623,10 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
   }
   // 3. every warp aligns its read against its contig
 #ifdef BK_SIM
-  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, w, nullptr);
+  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, w, nullptr, nullptr);
 #else
   if (multi) __syncthreads();
-  spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, 0, c.edge_all);
+  spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol);
   if (multi) __syncthreads();
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
@@ -1119,6 +1123,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.wcode = P.w_wcode + slot * ASM_CAP;
   c.diff = P.w_diff + slot * (ASM_CAP + 1);
   c.edge_all = P.w_edge ? P.w_edge + slot * spec_w * 2 * ASM_CAP : nullptr;
+  c.lastcol = P.w_lastcol ? P.w_lastcol + (size_t)slot * spec_w * ASM_LASTCOL : nullptr;
   c.edge = c.edge_all;
   c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
   c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
@@ -1153,6 +1158,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
   const int warp = threadIdx.x >> 5;
   if (W > 1 && warp > 0) {
     int2* edge = P.w_edge ? P.w_edge + (slot * W + warp) * 2 * ASM_CAP : nullptr;
+    uint2* lastcol = P.w_lastcol + (size_t)(slot * W + warp) * ASM_LASTCOL;
     for (;;) {
       __syncthreads();                                 // command published
       const int n = sp.n;
@@ -1160,7 +1166,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
       if (warp < n) spec_stage(P, &sp, s_reads, warp);
       __syncthreads();                                 // reads staged; warp 0 predicts
       __syncthreads();                                 // predictions published
-      if (warp < n) spec_dp(&sp, s_reads, s_contig, s_pred, warp, edge);
+      if (warp < n) spec_dp(&sp, s_reads, s_contig, s_pred, warp, edge, lastcol);
       __syncthreads();                                 // results published
     }
   }

@@ -21,6 +21,7 @@ struct NwBatchParams {
   int32_t* out;               // n_pairs * 10 : A{prej,j0,prei,i0,score}, B{...}
   int2* edge;                 // per warp 2 * edge_stride int2, or null when no seq1 is longer than 256
   int edge_stride;
+  uint2* lastcol;             // per warp NW_MAX_LEN / 2 + 1 uint2 (last DP column of the sweep in flight)
   int want_aln;
   uint8_t* ptr_scratch;       // sum (n+1)(m+1) bytes
   const int64_t* ptr_off;     // n_pairs
@@ -32,12 +33,12 @@ struct NwBatchParams {
 
 template <bool PTR>
 __device__ __forceinline__ void nw_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1,
-                                            uint8_t* ptrmat, NwDual& out) {
+                                            uint2* lastcol, uint8_t* ptrmat, NwDual& out) {
   if (PTR) {
     if (m <= 128) nw_dual_warp<4, true>(cs, m, rs, n, e0, e1, ptrmat, out);
     else nw_dual_warp<8, true>(cs, m, rs, n, e0, e1, ptrmat, out);
   } else {
-    nw_dual_dispatch(cs, m, rs, n, e0, e1, out);
+    nw_dual_dispatch(cs, m, rs, n, e0, e1, lastcol, out);
   }
 }
 
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
   uint8_t* s2 = smem[w][1];
   int2* e0 = p.edge ? p.edge + (size_t)gw * 2 * p.edge_stride : nullptr;
   int2* e1 = p.edge ? e0 + p.edge_stride : nullptr;
+  uint2* lastcol = p.lastcol + (size_t)gw * (NW_MAX_LEN / 2 + 1);
   for (int64_t pi = gw; pi < p.n_pairs; pi += nw_total) {
     const int ia = p.pair_a[pi], ib = p.pair_b[pi];
     const int64_t oa = p.seq_off[ia], ob = p.seq_off[ib];
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
       for (int i = L; i <= n; i += 32) pm[(size_t)i * (m + 1)] = 1;      // olc.py:56-57
       for (int j = L; j <= m; j += 32) pm[j] = 2;                         // olc.py:58-59
       __syncwarp();
-      nw_dispatch<true>(s1, m, s2, n, e0, e1, pm, r);
+      nw_dispatch<true>(s1, m, s2, n, e0, e1, lastcol, pm, r);
       __syncwarp();
       if (L == 0) {                                                       // olc.py:86-105
         int i = r.a.prei, j = m, len = 0;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
         p.aln_len[pi] = len;       // strings are stored reversed; the host shim flips them
       }
     } else {
-      nw_dispatch<false>(s1, m, s2, n, e0, e1, nullptr, r);
+      nw_dispatch<false>(s1, m, s2, n, e0, e1, lastcol, nullptr, r);
     }
     if (L == 0) {
       int32_t* o = p.out + pi * 10;

@@ -530,6 +530,7 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   A.w_wcode = h->dev.get<uint64_t>((size_t)grid * ASM_CAP);
   A.w_diff = h->dev.get<int32_t>((size_t)grid * (ASM_CAP + 1));
   A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * spec_w * 2 * ASM_CAP) : nullptr;
+  A.w_lastcol = h->dev.get<uint2>((size_t)grid * spec_w * ASM_LASTCOL);
   A.region_status = h->dev.get<int32_t>(R ? R : 1);
   A.region_ncontigs = h->dev.get<int32_t>(R ? R : 1);
   // a mutable copy of the liveness flags per attempt, everything else zeroed
