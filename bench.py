@@ -549,6 +549,18 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
         barrier()
         ff_s = max_over_ranks(local)
         n_contigs = int(box[0].n_contigs)
+        # contig hand-off (row f.3): the contig.setup files of every contig of one batch result, written to tmpfs
+        pk0 = ings[0].files(refs, fqs, scs, **kw)
+        res0 = batch.run(handles[0], pk0, decode=False)
+        hand_s, n_files = [], 0
+        writer = ingest.Ingest(n_threads=cores)
+        for rep in range(3):
+            out_root = os.path.join(d, "handoff%d" % rep)
+            t0 = time.time()
+            n_files = writer.write_contigs(res0, pk0, [os.path.join(out_root, "t%05d" % i, "contigs") for i in range(len(regions))],
+                                            [os.path.join(out_root, "t%05d_clusters.out" % i) for i in range(len(regions))])
+            hand_s.append(time.time() - t0)
+        writer.close()
         for g in ings:
             g.close()
         return {"value": n_regions_total * args.steps / ff_s, "unit": UNIT, "ms_per_step": 1000.0 * ff_s / args.steps,
@@ -556,6 +568,9 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
                 "parse_only": {"ms_per_batch": 1000.0 * parse_s, "regions_per_s": len(regions) / parse_s,
                                "text_MB_per_s": n_bytes / parse_s / 1e6, "host_threads": cores},
                 "python_marshalling_ms_per_batch": 1000.0 * py_s,
+                "handoff": {"ms_per_batch": 1000.0 * min(hand_s), "files_per_batch": n_files, "host_threads": cores,
+                            "what": "bk_write_contigs: <id>.fq + <id>.fa per contig and the cluster file per target "
+                                    "(sv_processor.py:749-782), tmpfs"},
                 "note": "each step parses the targets' FASTA/FASTQ files (tmpfs) with bk_ingest_files into page-locked memory "
                         "and calls bk_compare_kmers_batch; %d ingest threads per in-flight batch" % per}
     finally:

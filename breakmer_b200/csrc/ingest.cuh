@@ -348,6 +348,10 @@ void ingest_texts(Ingest& g, int n, const TextView* ref, const TextView* reads, 
 namespace bk {
 
 inline bool make_dirs(const std::string& path) {
+  if (mkdir(path.c_str(), 0777) == 0 || errno == EEXIST) {           // common case: the parent exists already
+    struct stat st0;
+    return stat(path.c_str(), &st0) == 0 && S_ISDIR(st0.st_mode);
+  }
   std::string cur;
   size_t i = 0;
   while (i <= path.size()) {
