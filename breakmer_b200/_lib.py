@@ -116,7 +116,9 @@ def load():
                                     POINTER(c_char_p), POINTER(BatchInput), POINTER(IngestText)]
     lib.bk_write_contigs.argtypes = [H, POINTER(BatchResult), POINTER(BatchInput), POINTER(IngestText),
                                      POINTER(c_char_p), POINTER(c_char_p), POINTER(c_int64)]
-    for name in ("bk_ingest_create", "bk_ingest_destroy", "bk_ingest_buffers", "bk_ingest_files", "bk_write_contigs"):
+    lib.bk_write_sample_kmers.argtypes = [H, POINTER(BatchResult), c_int32, POINTER(c_char_p), POINTER(c_int64)]
+    for name in ("bk_ingest_create", "bk_ingest_destroy", "bk_ingest_buffers", "bk_ingest_files", "bk_write_contigs",
+                 "bk_write_sample_kmers"):
         getattr(lib, name).restype = c_int
     for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_count_kmers", "bk_sample_only",
                  "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
@@ -131,7 +133,7 @@ EXPORTED_SYMBOLS = (
     "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
     "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear",
     "bk_ingest_create", "bk_ingest_destroy", "bk_ingest_last_error", "bk_ingest_buffers", "bk_ingest_files",
-    "bk_write_contigs")
+    "bk_write_contigs", "bk_write_sample_kmers")
 
 
 def _ptr(a):
@@ -259,3 +261,16 @@ def mer_to_code(mer):
 def code_to_mer(code, k):
     code = int(code)
     return "".join(_BASES[(code >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def codes_to_mers(codes, k):
+    """Vectorised code_to_mer: uint64 array -> list of str (first base most significant)."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    if codes.size == 0:
+        return []
+    shifts = (2 * (k - 1 - np.arange(k))).astype(np.uint64)
+    letters = _ACGT[((codes[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.intp)]
+    return np.ascontiguousarray(letters).view("S%d" % k).ravel().astype("U%d" % k).tolist()

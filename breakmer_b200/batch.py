@@ -119,6 +119,7 @@ class BatchOutput:
         R = res.n_regions
         C = int(res.n_contigs)
         self.k = packed.k
+        self._kmer_str = None
         self.n_regions = R
         self.n_contigs = C
         self.read_ids = packed.read_ids
@@ -157,7 +158,12 @@ class BatchOutput:
 
     def sample_only(self, r):
         a, b = int(self.so_off[r]), int(self.so_off[r + 1])
-        return {_lib.code_to_mer(m, self.k): int(c) for m, c in zip(self.so_mers[a:b], self.so_counts[a:b])}
+        return dict(zip(_lib.codes_to_mers(self.so_mers[a:b], self.k), self.so_counts[a:b].tolist()))
+
+    def _kmer_strings(self):
+        if self._kmer_str is None:                      # all contig k-mers of the batch decoded at once
+            self._kmer_str = _lib.codes_to_mers(self.kmer_mer, self.k)
+        return self._kmer_str
 
     def contig_records(self, r):
         """Contigs of region r in acceptance order, in the canonical comparable form
@@ -168,8 +174,10 @@ class BatchOutput:
             co, cl = self.cnt_off[c]
             ro, nr = self.reads_off[c]
             ko, nk = self.kmers_off[c]
-            kmers = [[_lib.code_to_mer(self.kmer_mer[e], self.k), int(self.kmer_pos[e]), int(self.kmer_lth[e]),
-                      int(self.kmer_dist[e]), ORDER_NAMES[int(self.kmer_order[e])]] for e in range(ko, ko + nk)]
+            ks = self._kmer_strings()
+            kmers = [list(t) for t in zip(ks[ko:ko + nk], self.kmer_pos[ko:ko + nk].tolist(), self.kmer_lth[ko:ko + nk].tolist(),
+                                          self.kmer_dist[ko:ko + nk].tolist(),
+                                          [ORDER_NAMES[o] for o in self.kmer_order[ko:ko + nk].tolist()])]
             out.append({
                 "seq": self.seq[so:so + sl].tobytes().decode(),
                 "indel_only": self.indel_only[co:co + cl].tolist(),

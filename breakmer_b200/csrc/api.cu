@@ -602,4 +602,12 @@ int bk_write_contigs(bk_ingest_t g, const bk_batch_result* res, const bk_batch_i
   });
 }
 
+int bk_write_sample_kmers(bk_ingest_t g, const bk_batch_result* res, int32_t k, const char* const* paths, int64_t* n_files) {
+  return guarded_ingest(g, [&] {
+    if (!res || !paths || k < 1 || k > 31) fail(BK_ERR_ARG, "bk_write_sample_kmers: bad arguments");
+    const int64_t n = write_sample_kmer_files(g->g, res, paths, k);
+    if (n_files) *n_files = n;
+  });
+}
+
 }  // extern "C"

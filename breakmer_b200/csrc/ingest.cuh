@@ -384,6 +384,33 @@ inline void append_mer(std::string& s, uint64_t code, int k) {
   for (int t = k - 1; t >= 0; --t) s.push_back("ACGT"[(code >> (2 * t)) & 3u]);
 }
 
+// "<mer>\t<case count>\n" per sample-only k-mer of a target: the file target.compare_kmers writes
+// (sv_processor.py:625-632).  The reference walks a Python set (arbitrary order); here ascending mer order.
+template <typename Result>
+int64_t write_sample_kmer_files(Ingest& g, const Result* res, const char* const* paths, int k) {
+  const int R = res->n_regions;
+  std::atomic<int64_t> n_files{0};
+  std::atomic<int> failed{-1};
+  g.parallel_for(R, [&](int r) {
+    if (!paths[r] || !paths[r][0]) return;
+    const int64_t a = res->so_off[r], b = res->so_off[r + 1];
+    std::string txt;
+    txt.reserve((size_t)(b - a) * (size_t)(k + 8));
+    char num[16];
+    for (int64_t i = a; i < b; ++i) {
+      append_mer(txt, res->so_mers[i], k);
+      txt.push_back('\t');
+      const int nn = snprintf(num, sizeof num, "%u", res->so_counts[i]);
+      txt.append(num, (size_t)nn);
+      txt.push_back('\n');
+    }
+    if (!write_whole_file(paths[r], txt)) { failed = r; return; }
+    n_files += 1;
+  });
+  if (failed >= 0) fail(BK_ERR_IO, "cannot write %s", paths[failed]);
+  return n_files.load();
+}
+
 template <typename Result, typename BatchInput>
 int64_t write_contig_files(Ingest& g, const Result* res, const BatchInput* in, const IngestText* text,
                            const char* const* contigs_dir, const char* const* cluster_fn, int k) {

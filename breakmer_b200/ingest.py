@@ -192,3 +192,13 @@ class Ingest:
         self._check(self.lib.bk_write_contigs(self.g, byref(res), byref(s), byref(pk._text), arr(contigs_dirs),
                                               arr(cluster_fns), byref(nf)))
         return int(nf.value)
+
+    def write_sample_kmers(self, res, k, paths):
+        """bk_write_sample_kmers: "<mer>\\t<count>" files of every target (sv_processor.py:625-632) from the raw result."""
+        n = int(res.n_regions)
+        a = (c_char_p * max(n, 1))()
+        for i, p in enumerate(paths):
+            a[i] = p.encode() if p else None
+        nf = ctypes.c_int64(0)
+        self._check(self.lib.bk_write_sample_kmers(self.g, byref(res), int(k), a, byref(nf)))
+        return int(nf.value)

@@ -128,19 +128,24 @@ def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False)
         _get_ingest().write_contigs(res, pk, [t.paths['contigs'] for t in targets],
                                     [os.path.join(t.paths['kmers'], t.name + "_sample_kmers_merged.out") for t in targets])
     out = batch.BatchOutput(res, pk)
+    for trgt in targets:
+        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
+    if ingest == "native":
+        # the "<mer>\t<count>" files of all targets in one multi-threaded sweep (bk_write_sample_kmers)
+        _get_ingest().write_sample_kmers(res, pk.k, [t.files['sample_kmers'] for t in targets])
     for i, trgt in enumerate(targets):
         if out.region_status[i] != 0:
             raise RuntimeError("compare_kmers: device capacity exceeded for target %s" % trgt.name)
-        only = out.sample_only(i)
-        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
-        with open(trgt.files['sample_kmers'], 'w') as f:
-            for mer, cnt in only.items():
-                f.write("\t".join([mer, str(cnt)]) + "\n")
+        n_only = int(out.so_off[i + 1] - out.so_off[i])
+        if ingest != "native":
+            with open(trgt.files['sample_kmers'], 'w') as f:
+                for mer, cnt in out.sample_only(i).items():
+                    f.write("\t".join([mer, str(cnt)]) + "\n")
         for key in ('ref', 'case', 'case_sc'):
             trgt.kmers[key] = {}
         logger = getattr(trgt, "logger", None)
         if logger is not None:
-            logger.info('Writing %d sample-only kmers to file %s' % (len(only), trgt.files['sample_kmers']))
+            logger.info('Writing %d sample-only kmers to file %s' % (n_only, trgt.files['sample_kmers']))
         trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
         ctgs = []
         for j, rec in enumerate(out.contig_records(i)):

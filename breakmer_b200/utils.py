@@ -106,8 +106,8 @@ def run_jellyfish(fa_fn, jellyfish, kmer_size):
         logger.info('Counting %d-mers of %s on the GPU' % (kmer_size, fa_fn))
         mers, counts = get_handle().count_kmers(read_sequences(fa_fn), int(kmer_size))
         with open(dump_fn, "w") as out:
-            for m, c in zip(mers, counts):
-                out.write("%s %d\n" % (_lib.code_to_mer(m, int(kmer_size)), int(c)))
+            for m, c in zip(_lib.codes_to_mers(mers, int(kmer_size)), counts):
+                out.write("%s %d\n" % (m, int(c)))
         open(dump_marker_fn, "a").close()
         logger.info('Completed k-mer dump %s, touching marker file %s' % (dump_fn, dump_marker_fn))
     else:

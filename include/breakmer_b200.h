@@ -217,6 +217,9 @@ int bk_ingest_files(bk_ingest_t g, int32_t n_regions, const char* const* ref_fa,
  * order (the reference iterates a Python set: no defined order). */
 int bk_write_contigs(bk_ingest_t g, const bk_batch_result* res, const bk_batch_input* in, const bk_ingest_text* text,
                      const char* const* contigs_dir, const char* const* cluster_fn, int64_t* n_files);
+/* The "<name>_sample_kmers.out" file of every target (sv_processor.py:625-632): "<mer>\t<case count>\n" per
+ * sample-only k-mer, ascending mer order (the reference walks a Python set).  paths[r] NULL/"" skips region r. */
+int bk_write_sample_kmers(bk_ingest_t g, const bk_batch_result* res, int32_t k, const char* const* paths, int64_t* n_files);
 
 #ifdef __cplusplus
 }
