@@ -165,9 +165,10 @@ class BatchOutput:
             self._kmer_str = _lib.codes_to_mers(self.kmer_mer, self.k)
         return self._kmer_str
 
-    def contig_records(self, r):
+    def contig_records(self, r, with_reads=True):
         """Contigs of region r in acceptance order, in the canonical comparable form
-        (same shape as oracle.assembler_py.contig_record)."""
+        (same shape as oracle.assembler_py.contig_record).  with_reads=False leaves "reads" out (callers that map
+        ctg_reads to their own read objects do not need the sorted id list)."""
         out = []
         for c in range(int(self.ctg_reg_off[r]), int(self.ctg_reg_off[r + 1])):
             so, sl = self.seq_off[c]
@@ -182,7 +183,7 @@ class BatchOutput:
                 "seq": self.seq[so:so + sl].tobytes().decode(),
                 "indel_only": self.indel_only[co:co + cl].tolist(),
                 "others": self.others[co:co + cl].tolist(),
-                "reads": sorted(self.read_ids[int(i)] for i in self.reads[ro:ro + nr]),
+                "reads": sorted(self.read_ids[int(i)] for i in self.reads[ro:ro + nr]) if with_reads else None,
                 "kmers": kmers,
                 "kmer_locs": self.kmer_locs[so:so + sl].tolist(),
             })

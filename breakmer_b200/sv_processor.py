@@ -148,7 +148,7 @@ def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False)
             logger.info('Writing %d sample-only kmers to file %s' % (n_only, trgt.files['sample_kmers']))
         trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
         ctgs = []
-        for j, rec in enumerate(out.contig_records(i)):
+        for j, rec in enumerate(out.contig_records(i, with_reads=False)):
             cidx = int(out.ctg_reg_off[i]) + j
             ro, nr = out.reads_off[cidx]
             ctgs.append(contig(rec, [objs[int(r)] for r in out.reads[ro:ro + nr]], inputs[i].k))
