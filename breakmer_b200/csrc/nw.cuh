@@ -320,9 +320,11 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
           for (int c = 0; c < C; ++c) {
             const int vA = colA[c], vB = colB[c];
             const int s = (ch[c] == rc0) ? NW_D_MATCH : NW_D_MISM;
+            // the horizontal input (hA / hB) is the only one that depends on the previous column of this row:
+            // it goes last, so the dependent chain along a row is one max + the tag clear per cell
             int tA = dA + s;
-            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
             tA = __viaddmax_s32(vA, NW_GAP_LO, tA);
+            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
             int tB = dB + s;
             tB = __viaddmax_s32(vB, NW_GAP_HI, tB);
             tB = __viaddmax_s32(hB, NW_GAP_LO, tB);
@@ -338,9 +340,11 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
           for (int c = 0; c < C; ++c) {
             const int vA = r0A[c], vB = r0B[c];
             const int s = (ch[c] == rc1) ? NW_D_MATCH : NW_D_MISM;
+            // the horizontal input (hA / hB) is the only one that depends on the previous column of this row:
+            // it goes last, so the dependent chain along a row is one max + the tag clear per cell
             int tA = dA + s;
-            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
             tA = __viaddmax_s32(vA, NW_GAP_LO, tA);
+            tA = __viaddmax_s32(hA, NW_GAP_HI, tA);
             int tB = dB + s;
             tB = __viaddmax_s32(vB, NW_GAP_HI, tB);
             tB = __viaddmax_s32(hB, NW_GAP_LO, tB);
