@@ -43,3 +43,15 @@ def test_known_answers():
         assert digest(sorted(ref.items())) == case["ref_sha256"]
         assert digest(sorted(cs.items())) == case["case_sha256"]
         assert [list(x) for x in sorted(only.items())] == case["sample_only"]
+
+
+def test_vectorised_mer_decoding_matches_scalar():
+    import random
+    import numpy as np
+    from breakmer_b200 import _lib
+    rng = random.Random(5)
+    for k in (1, 2, 11, 15, 21, 25, 31):
+        codes = np.array([rng.getrandbits(2 * k) for _ in range(300)] + [0, (1 << (2 * k)) - 1], dtype=np.uint64)
+        assert _lib.codes_to_mers(codes, k) == [_lib.code_to_mer(c, k) for c in codes]
+        assert [_lib.mer_to_code(m) for m in _lib.codes_to_mers(codes, k)] == codes.tolist()
+    assert _lib.codes_to_mers(np.zeros(0, np.uint64), 15) == []
