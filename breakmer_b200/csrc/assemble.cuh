@@ -1135,9 +1135,6 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 // every speculation round; warps 1..W-1 only align.  W = 4 minimises the latency of a
 // region (used when a batch runs alone on the device), W = 1 spends no work on
 // speculation and packs more regions per SM (used when several batches are in flight).
-// `pad_smem` bytes of dynamic shared memory do nothing but bound the CTAs resident per
-// SM, so that the short k-mer stage kernels of other in-flight batches can still get
-// registers while long assemblies occupy the machine.
 // dynamic shared memory of one CTA: W read buffers, the contig, W-1 predicted contigs,
 // the mer hash, the round mailbox (then padding, see above)
 template <int W>

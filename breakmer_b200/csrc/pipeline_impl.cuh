@@ -517,11 +517,13 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   int ctas_per_sm = spec_w == 8 ? 1 : (spec_w == 4 ? 3 : (spec_w == 2 ? 6 : 8));
   if (const char* e = getenv("BK_ASM_CTAS_PER_SM")) ctas_per_sm = std::max(1, atoi(e));
   int grid = std::min<int64_t>(R, (int64_t)h->sm_count * ctas_per_sm);
-  // dynamic shared memory: what the kernel needs, padded to 1/ctas_per_sm of the SM so residency is bounded
+  // dynamic shared memory: exactly what the kernel needs.  (An earlier version padded it to 1/ctas_per_sm of the SM to bound
+  // residency; that pushed the shared-memory carve-out to the maximum and left the assembler's bookkeeping -- dependent
+  // loads of per-region tables -- ~29 KB of L1: 15 % slower.  BK_ASM_PAD=1 restores it for experiments.)
   const size_t need_smem = spec_w == 8 ? assemble_smem_bytes<8>() : (spec_w == 4 ? assemble_smem_bytes<4>() :
                            (spec_w == 2 ? assemble_smem_bytes<2>() : assemble_smem_bytes<1>()));
-  int dyn_smem = (int)((227 * 1024) / ctas_per_sm) - 1024;
-  if (dyn_smem < (int)need_smem || getenv("BK_ASM_NO_PAD")) dyn_smem = (int)need_smem;
+  int dyn_smem = (int)need_smem;
+  if (getenv("BK_ASM_PAD")) dyn_smem = std::max(dyn_smem, (int)((227 * 1024) / ctas_per_sm) - 1024);
   if (grid < 1) grid = 1;
   A.w_cseq = h->dev.get<uint8_t>((size_t)grid * ASM_BUF);
   A.w_cnt = h->dev.get<int32_t>((size_t)grid * 4 * ASM_BUF);
@@ -573,17 +575,25 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
     if (S_total) BK_CUDA(cudaMemcpyAsync(alive_run, m_alive, S_total, cudaMemcpyDeviceToDevice, st));
     if (R > 0) {
       TimedLaunch t(h->timers, st, KF_ASSEMBLE);
+      // shared-memory carve-out: just enough for the resident CTAs, the rest of the 256 KB stays L1
+      int carve = (int)((100 * (size_t)ctas_per_sm * ((size_t)dyn_smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+      if (const char* e = getenv("BK_ASM_CARVEOUT")) carve = atoi(e);
+      carve = std::min(100, std::max(0, carve));
+      auto prep = [&](const void* fn) {
+        BK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        BK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      };
       if (spec_w == 8) {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        prep((const void*)assemble_kernel<8>);
         assemble_kernel<8><<<grid, 256, dyn_smem, st>>>(A);
       } else if (spec_w == 4) {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        prep((const void*)assemble_kernel<4>);
         assemble_kernel<4><<<grid, 128, dyn_smem, st>>>(A);
       } else if (spec_w == 2) {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        prep((const void*)assemble_kernel<2>);
         assemble_kernel<2><<<grid, 64, dyn_smem, st>>>(A);
       } else {
-        BK_CUDA(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        prep((const void*)assemble_kernel<1>);
         assemble_kernel<1><<<grid, 32, dyn_smem, st>>>(A);
       }
     }
