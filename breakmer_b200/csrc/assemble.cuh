@@ -76,6 +76,7 @@ struct AsmParams {
   int n_regions;
   int k;
   int rc_thresh;
+  int read_cap;                    // bytes of one staged-read buffer in shared memory: >= longest read + 2, multiple of 16
   // reads: raw records + unique-read table (fq_recs, utils.py:239-244, Q28)
   const uint8_t* rbases;
   const int64_t* roff;             // n_rec + 1
@@ -496,15 +497,15 @@ BK_DEV void spec_stage(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, int
   const int rec = P.u_rec[gu0 + sp->u[w]];
   const int64_t a = P.roff[rec];
   const int lr = (int)(P.roff[rec + 1] - a);
-  uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
+  uint8_t* rd = s_reads + (size_t)w * P.read_cap;
   const uint8_t* src = P.rbases + a;
   for (int x = lane(); x < lr; x += WARP) rd[x] = src[x];
   if (lane() == 0) sp->lr[w] = lr;
   syncwarp();
 }
-BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, const uint8_t* s_contig, const uint8_t* s_pred, int w, int2* edge,
-                    uint2* lastcol) {
-  const uint8_t* rd = s_reads + (size_t)w * ASM_CAP;
+BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, int read_cap, const uint8_t* s_contig, const uint8_t* s_pred, int w,
+                    int2* edge, uint2* lastcol) {
+  const uint8_t* rd = s_reads + (size_t)w * read_cap;
   const int lr = sp->lr[w];
   const int b = sp->abuf[w];
   const uint8_t* ct = b == 0 ? s_contig : s_pred + (size_t)(b - 1) * ASM_CAP;
@@ -613,7 +614,7 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
       int anchor_buf;
       const int mer_s = slot_mer(c, pos + w - 1, &anchor_buf);
       const int hint = shift >= 0x40000000 ? -1 : anchor_buf - c.c0 + shift;
-      const int nl = predict_contig(c, src, la, c.s_reads + (size_t)(w - 1) * ASM_CAP, sp->lr[w - 1], c.hit_pos[pos + w - 1],
+      const int nl = predict_contig(c, src, la, c.s_reads + (size_t)(w - 1) * c.P->read_cap, sp->lr[w - 1], c.hit_pos[pos + w - 1],
                                     mer_s, hint, dst, &same, &shift);
       if (!same) { buf = w; la = nl; src = dst; }
       if (lane() == 0) { sp->abuf[w] = buf; sp->la[w] = la; }
@@ -623,10 +624,10 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
   }
   // 3. every warp aligns its read against its contig
 #ifdef BK_SIM
-  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, w, nullptr, nullptr);
+  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, w, nullptr, nullptr);
 #else
   if (multi) __syncthreads();
-  spec_dp(sp, c.s_reads, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol);
+  spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol);
   if (multi) __syncthreads();
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
@@ -705,7 +706,7 @@ BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
   const int w = pos - c.rnd_base;
   const int u = c.hit_u[pos];
   const NwOut v1 = c.sp->v1[w], v2 = c.sp->v2[w];
-  const bool match = apply_align(c, u, seed_s, grow, c.s_reads + (size_t)w * ASM_CAP, c.sp->lr[w], v1, v2);
+  const bool match = apply_align(c, u, seed_s, grow, c.s_reads + (size_t)w * c.P->read_cap, c.sp->lr[w], v1, v2);
   if (match) {
     if (lane() == 0) { c.r_used[u] = 1; c.r_inreads[u] = c.serial; }  // committed by the finalize that follows
   } else if (c.cnt[seed_s] > 2 && !c.r_used[u]) {
@@ -1135,11 +1136,10 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
 // every speculation round; warps 1..W-1 only align.  W = 4 minimises the latency of a
 // region (used when a batch runs alone on the device), W = 1 spends no work on
 // speculation and packs more regions per SM (used when several batches are in flight).
-// dynamic shared memory of one CTA: W read buffers, the contig, W-1 predicted contigs,
+// dynamic shared memory of one CTA: W read buffers (sized by the longest read of the batch), the contig, W-1 predicted contigs,
 // the mer hash, the round mailbox (then padding, see above)
-template <int W>
-constexpr size_t assemble_smem_bytes() {
-  return (size_t)W * ASM_CAP + ASM_CAP + (size_t)(W - 1) * ASM_CAP + MER_HASH_SIZE * sizeof(int32_t) +
+inline size_t assemble_smem_bytes(int W, int read_cap) {
+  return (size_t)W * read_cap + ASM_CAP + (size_t)(W - 1) * ASM_CAP + MER_HASH_SIZE * sizeof(int32_t) +
          ((sizeof(SpecShared) + 15) & ~size_t(15));
 }
 
@@ -1147,7 +1147,7 @@ template <int W>
 __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : ASM_W1_CTAS)))) assemble_kernel(AsmParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* s_reads = smem_raw;
-  uint8_t* s_contig = s_reads + (size_t)W * ASM_CAP;
+  uint8_t* s_contig = s_reads + (size_t)W * P.read_cap;
   uint8_t* s_pred = s_contig + ASM_CAP;
   int32_t* s_hash = reinterpret_cast<int32_t*>(s_pred + (size_t)(W - 1) * ASM_CAP);
   SpecShared& sp = *reinterpret_cast<SpecShared*>(s_hash + MER_HASH_SIZE);
@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
       if (warp < n) spec_stage(P, &sp, s_reads, warp);
       __syncthreads();                                 // reads staged; warp 0 predicts
       __syncthreads();                                 // predictions published
-      if (warp < n) spec_dp(&sp, s_reads, s_contig, s_pred, warp, edge, lastcol);
+      if (warp < n) spec_dp(&sp, s_reads, P.read_cap, s_contig, s_pred, warp, edge, lastcol);
       __syncthreads();                                 // results published
     }
   }

@@ -520,8 +520,8 @@ void pipeline_run(bk_handle_t h, const bk_batch_input* in, bool resident, bk_bat
   // dynamic shared memory: exactly what the kernel needs.  (An earlier version padded it to 1/ctas_per_sm of the SM to bound
   // residency; that pushed the shared-memory carve-out to the maximum and left the assembler's bookkeeping -- dependent
   // loads of per-region tables -- ~29 KB of L1: 15 % slower.  BK_ASM_PAD=1 restores it for experiments.)
-  const size_t need_smem = spec_w == 8 ? assemble_smem_bytes<8>() : (spec_w == 4 ? assemble_smem_bytes<4>() :
-                           (spec_w == 2 ? assemble_smem_bytes<2>() : assemble_smem_bytes<1>()));
+  A.read_cap = (int)std::min<int64_t>(ASM_CAP, std::max<int64_t>(64, (p.max_read_len + 2 + 15) / 16 * 16));
+  const size_t need_smem = assemble_smem_bytes(spec_w, A.read_cap);
   int dyn_smem = (int)need_smem;
   if (getenv("BK_ASM_PAD")) dyn_smem = std::max(dyn_smem, (int)((227 * 1024) / ctas_per_sm) - 1024);
   if (grid < 1) grid = 1;

@@ -25,7 +25,7 @@ extern "C" int sim_assemble_region(
     uint64_t* stats_out) {
   AsmParams P;
   memset(&P, 0, sizeof P);
-  P.n_regions = 1; P.k = k; P.rc_thresh = rc_thresh;
+  P.n_regions = 1; P.k = k; P.rc_thresh = rc_thresh; P.read_cap = ASM_CAP;
   P.rbases = rbases; P.roff = roff;
   int64_t u_off[2] = {0, n_reads};
   std::vector<int32_t> u_rec(n_reads);
