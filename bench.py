@@ -418,7 +418,7 @@ def gpu_arm(args):
     # INT32 ALU-pipe ceiling of the DP: 8 alu-pipe instructions per cell (nw.cuh), 16 lanes/clk/SMSP (B300_MICROARCH.md)
     int_peak_cells = 148 * 4 * 16 * sm_mhz * 1e6 / 8.0
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_*.md); only valid for the default workload
-    asm_traffic = 35980288 if (args.workload == "C2" and per_gpu == 500) else None
+    asm_traffic = 34850560 if (args.workload == "C2" and per_gpu == 500) else None
     sort_traffic = 191033344 if (args.workload == "C2" and per_gpu == 500) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
