@@ -263,13 +263,12 @@ def gpu_arm(args):
     # regions with long serial chains -- overlaps the bulk of the next.  inflight=1 is the strictly sequential mode.
     n_fly = max(1, min(args.inflight, args.steps))
     # one host thread per in-flight batch waits on its stream; when the ranks of this box have fewer cores than such threads,
-    # let them sleep on a blocking event instead of spinning (library knob BK_BLOCKING_SYNC, read at handle creation)
+    # let them sleep on a blocking event instead of spinning (bk_set_option "blocking_sync")
     cores_per_rank = max(1, (os.cpu_count() or 1) // max(1, world))
-    if n_fly > cores_per_rank and "BK_BLOCKING_SYNC" not in os.environ and not os.environ.get("BK_BENCH_SPIN"):
-        os.environ["BK_BLOCKING_SYNC"] = "1"
-        h.close()
-        h = _lib.Handle(local_rank)
+    blocking = (n_fly > cores_per_rank and not os.environ.get("BK_BENCH_SPIN")) or bool(os.environ.get("BK_BLOCKING_SYNC"))
     handles = [h] + [_lib.Handle(local_rank) for _ in range(n_fly - 1)]
+    for hh in handles:
+        hh.set_option("blocking_sync", 1 if blocking else 0)
     for hh in handles:
         batch.upload(hh, pk)
     for _ in range(args.warmup):                # W untimed warm-up steps on every handle (arenas reach steady state)
@@ -434,7 +433,7 @@ def gpu_arm(args):
         "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": pk.k, "rc_thresh": pk.rc_thresh,
                    "per_gpu_problem": "every rank runs its own batch of the same %d regions (generator slice %d)" % (per_gpu, args.slice),
                    "input_bytes_per_gpu": pk.input_bytes, "steps_in_flight": n_fly, "assembler_spec_width": spec_w,
-                   "host_cores_per_rank": cores_per_rank, "host_wait": "blocking" if os.environ.get("BK_BLOCKING_SYNC") else "spin",
+                   "host_cores_per_rank": cores_per_rank, "host_wait": "blocking" if blocking else "spin",
                    "l2": ("256 MB buffer written between timed steps (flush)" if n_fly == 1 else
                           "%d independent batches in flight on separate buffers; the per-step working set (~0.8 GB of "
                           "key/value, scratch and state arrays) exceeds the 126 MB L2" % n_fly),

@@ -458,6 +458,8 @@ int bk_set_option(bk_handle_t h, const char* name, int64_t value) {
     if (strcmp(name, "spec_width") == 0) {
       if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) fail(BK_ERR_ARG, "spec_width must be 0 (auto), 1, 2, 4 or 8");
       h->spec_width = (int)value;
+    } else if (strcmp(name, "blocking_sync") == 0) {
+      h->spin_sync = value == 0;
     } else {
       fail(BK_ERR_ARG, "bk_set_option: unknown option %s", name);
     }

@@ -162,7 +162,9 @@ int bk_ref_cache_clear(bk_handle_t h);
 
 /* Tuning knobs.  "spec_width" = 0 | 1 | 2 | 4 | 8: warps per region in the assembler (how many
  * reads are aligned speculatively at once).  0 (default) = 4, one aligning warp per SM
- * sub-partition.  Results never depend on it. */
+ * sub-partition.  "blocking_sync" = 0 | 1: host threads waiting for the handle's stream spin (default, lowest
+ * latency) or sleep on a blocking event (for hosts with fewer cores than handles in flight).  Results never
+ * depend on either. */
 int bk_set_option(bk_handle_t h, const char* name, int64_t value);
 int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out);
 int bk_kernel_times(bk_handle_t h, const char** names, const double** ms, const int64_t** launches, int32_t* n);
