@@ -39,11 +39,15 @@ class IngestedBatch:
         if not with_ref:
             s.ref_bases = None
             s.ref_off = None
-        ro = self._view(s.read_off, self.n_reads + 1, np.int64)
-        self.input_bytes = int(ro[-1]) if self.n_reads else 0
-        for ptr in (s.ref_off if with_ref else None, s.sc_off):
-            pass
         self.read_reg_off = self._view(s.read_reg_off, n + 1, np.int64)
+        ro = self._view(s.read_off, self.n_reads + 1, np.int64)
+        self.input_bytes = int(ro[-1]) if self.n_reads else 0          # bases of all inputs, like PackedBatch.input_bytes
+        if with_ref and n:
+            self.input_bytes += int(self._view(s.ref_off, n + 1, np.int64)[-1])
+        for offp, regp in ((s.sc_off, s.sc_reg_off), (s.normal_off, s.normal_reg_off) if has_normal else (None, None)):
+            if offp and regp and n:
+                n_rec = int(self._view(regp, n + 1, np.int64)[-1])
+                self.input_bytes += int(self._view(offp, n_rec + 1, np.int64)[-1])
         self.read_len = self._view(s.read_len, n + 1, np.int32)
         # mutable: the caller may replace the flags parsed from the "_1" header suffix (utils.py:436-443) with its own
         # fq_read.indel_only values (get_fastq_reads takes them from sv_reads, utils.py:215,240)
