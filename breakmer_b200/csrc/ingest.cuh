@@ -71,10 +71,12 @@ struct ParsedSet {               // the records of one input of one region
   std::vector<int32_t> len;
   void add(const char* a, const char* b) { bases.append(a, b); len.push_back((int32_t)(b - a)); }
 };
-struct ParsedReads : ParsedSet {
-  std::string ids, quals;
-  std::vector<int32_t> id_len, qual_len;
-  std::vector<uint8_t> flags;
+// The reads of a region are kept as slices of the source text (which outlives the layout step) and copied ONCE,
+// straight into the batch buffer.
+struct ReadSlice { const char* id; const char* seq; const char* qual; int32_t id_len, seq_len, qual_len; uint8_t flag; };
+struct ParsedReads {
+  std::vector<ReadSlice> recs;
+  int64_t id_bytes = 0, seq_bytes = 0, qual_bytes = 0;
   int32_t max_len = 0;
 };
 
@@ -110,7 +112,7 @@ inline const char* check_fastq_header(const char* a, const char* b) {
 inline void parse_reads_fastq(TextView t, ParsedReads& out, std::string& err) {
   LineReader lr(t);
   int64_t rec = 0;
-  out.bases.reserve(t.n / 2); out.quals.reserve(t.n / 2); out.ids.reserve(t.n / 4);
+  out.recs.reserve(t.n / 200 + 4);
   for (;;) {
     const char *h0, *h1, *s0, *s1, *p0, *p1, *q0, *q1;
     if (!lr.next(h0, h1) || !lr.next(s0, s1) || !lr.next(p0, p1) || !lr.next(q0, q1)) break;
@@ -122,15 +124,13 @@ inline void parse_reads_fastq(TextView t, ParsedReads& out, std::string& err) {
       err = buf;
       return;
     }
-    out.add(s0, s1);
-    out.ids.append(h0, h1); out.id_len.push_back((int32_t)(h1 - h0));
-    out.quals.append(q0, q1); out.qual_len.push_back((int32_t)(q1 - q0));
     // the extraction step writes "@<qname>/<end>_<0|1>", 1 = indel_only (fq_line, utils.py:436-443)
     const char* u = h1;
     while (u > h0 && u[-1] != '_') --u;
     const size_t sl = (size_t)(h1 - u);
     const bool flag = u > h0 && ((sl == 4 && memcmp(u, "True", 4) == 0) || (sl == 1 && *u == '1'));
-    out.flags.push_back(flag ? 1 : 0);
+    out.recs.push_back(ReadSlice{h0, s0, q0, (int32_t)(h1 - h0), (int32_t)(s1 - s0), (int32_t)(q1 - q0), (uint8_t)(flag ? 1 : 0)});
+    out.id_bytes += h1 - h0; out.seq_bytes += s1 - s0; out.qual_bytes += q1 - q0;
     if ((int32_t)(s1 - s0) > out.max_len) out.max_len = (int32_t)(s1 - s0);
   }
 }
@@ -269,11 +269,11 @@ void ingest_texts(Ingest& g, int n, const TextView* ref, const TextView* reads, 
   for (int r = 0; r < n; ++r) {
     const IngestRegion& R = g.regions[r];
     t_ref[r + 1] = {t_ref[r].rec + 1, t_ref[r].bytes + (R.ref.len.empty() ? 0 : R.ref.len[0])};
-    t_rd[r + 1] = {t_rd[r].rec + (int64_t)R.reads.len.size(), t_rd[r].bytes + (int64_t)R.reads.bases.size()};
+    t_rd[r + 1] = {t_rd[r].rec + (int64_t)R.reads.recs.size(), t_rd[r].bytes + R.reads.seq_bytes};
     t_sc[r + 1] = {t_sc[r].rec + (int64_t)R.sc.len.size(), t_sc[r].bytes + (int64_t)R.sc.bases.size()};
     t_nm[r + 1] = {t_nm[r].rec + (int64_t)R.normal.len.size(), t_nm[r].bytes + (int64_t)R.normal.bases.size()};
-    t_id[r + 1] = t_id[r] + (int64_t)R.reads.ids.size();
-    t_q[r + 1] = t_q[r] + (int64_t)R.reads.quals.size();
+    t_id[r + 1] = t_id[r] + R.reads.id_bytes;
+    t_q[r + 1] = t_q[r] + R.reads.qual_bytes;
   }
   const int64_t n_rd = t_rd[n].rec, n_sc = t_sc[n].rec, n_nm = t_nm[n].rec;
   size_t total = 0;
@@ -308,17 +308,21 @@ void ingest_texts(Ingest& g, int n, const TextView* ref, const TextView* reads, 
       for (size_t i = 0; i < S.len.size(); ++i) { off[t0.rec + (int64_t)i] = o; o += S.len[i]; }
       if (!S.bases.empty()) memcpy(base + o_bytes + t0.bytes, S.bases.data(), S.bases.size());
     };
-    put(R.reads, t_rd[r], rd_off, rd_reg, o_rd);
     put(R.sc, t_sc[r], sc_off, sc_reg, o_sc);
     put(R.normal, t_nm[r], nm_off, nm_reg, o_nm);
-    int64_t oi = t_id[r], oq = t_q[r];
-    for (size_t i = 0; i < R.reads.len.size(); ++i) {
-      id_off[t_rd[r].rec + (int64_t)i] = oi; oi += R.reads.id_len[i];
-      q_off[t_rd[r].rec + (int64_t)i] = oq; oq += R.reads.qual_len[i];
-      fl[t_rd[r].rec + (int64_t)i] = R.reads.flags[i];
+    rd_reg[r] = t_rd[r].rec;
+    int64_t os = t_rd[r].bytes, oi = t_id[r], oq = t_q[r];
+    char* d_seq = base + o_rd;
+    char* d_id = base + o_id;
+    char* d_q = base + o_q;
+    for (size_t i = 0; i < R.reads.recs.size(); ++i) {
+      const ReadSlice& x = R.reads.recs[i];
+      const int64_t gi = t_rd[r].rec + (int64_t)i;
+      rd_off[gi] = os; id_off[gi] = oi; q_off[gi] = oq; fl[gi] = x.flag;
+      memcpy(d_seq + os, x.seq, (size_t)x.seq_len);   os += x.seq_len;
+      memcpy(d_id + oi, x.id, (size_t)x.id_len);      oi += x.id_len;
+      memcpy(d_q + oq, x.qual, (size_t)x.qual_len);   oq += x.qual_len;
     }
-    if (!R.reads.ids.empty()) memcpy(base + o_id + t_id[r], R.reads.ids.data(), R.reads.ids.size());
-    if (!R.reads.quals.empty()) memcpy(base + o_q + t_q[r], R.reads.quals.data(), R.reads.quals.size());
     rlen[r] = R.reads.max_len;
   });
   memset(in, 0, sizeof *in);
