@@ -92,6 +92,8 @@ def load():
     lib.bk_last_error.restype = c_char_p
     lib.bk_nw_batch.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.bk_dedup_reads.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_double, c_void_p,
+                                   c_void_p, POINTER(c_int64)]
     lib.bk_count_kmers.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                    POINTER(POINTER(c_uint64)), POINTER(POINTER(c_uint32)), POINTER(c_int64)]
     lib.bk_sample_only.argtypes = [H, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -129,7 +131,7 @@ def load():
 
 
 EXPORTED_SYMBOLS = (
-    "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_count_kmers",
+    "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_dedup_reads", "bk_count_kmers",
     "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
     "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear",
     "bk_ingest_create", "bk_ingest_destroy", "bk_ingest_last_error", "bk_ingest_buffers", "bk_ingest_files",
@@ -200,6 +202,22 @@ class Handle:
         self._check(self.lib.bk_nw_batch(self.h, _ptr(data), _ptr(off), len(seqs), _ptr(pa), _ptr(pb), n, _ptr(out),
                                          0, None, None, None, None))
         return out, None
+
+    # ---- read_batch.check_mer_read over whole batches (sv_assembly_mm2.py:290-355) ----
+    def dedup_reads(self, seqs, mer_pos, batch_off, subseq_frac):
+        """-> (check uint8[n], flags uint8[n], number of alignments computed)"""
+        data, off = concat(seqs)
+        n = len(seqs)
+        mp = np.ascontiguousarray(mer_pos, dtype=np.int32)
+        bo = np.ascontiguousarray(batch_off, dtype=np.int64)
+        if len(mp) != n:
+            raise ValueError("dedup_reads: one mer_pos per read")
+        check = np.zeros(n, dtype=np.uint8)
+        flags = np.zeros(n, dtype=np.uint8)
+        n_pairs = c_int64()
+        self._check(self.lib.bk_dedup_reads(self.h, _ptr(data), _ptr(off), n, _ptr(mp), _ptr(bo), len(bo) - 1,
+                                            float(subseq_frac), _ptr(check), _ptr(flags), byref(n_pairs)))
+        return check, flags, n_pairs.value
 
     # ---- jellyfish count + dump + load_kmers ----------------------------------------
     def count_kmers(self, seqs, k, mult=None):

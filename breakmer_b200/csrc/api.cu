@@ -14,6 +14,7 @@
 #include "scan.cuh"
 #include "pipeline.cuh"
 #include "ingest.cuh"
+#include "dedup.cuh"
 
 using namespace bk;
 
@@ -323,6 +324,54 @@ int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t
         std::reverse(aln2 + aln_off[p], aln2 + aln_off[p] + aln_len[p]);
       }
     }
+  });
+}
+
+// read_batch.check_mer_read of the reference's older assembler variant (sv_assembly_mm2.py:290-355) for whole batches:
+// every ordered pair of a batch goes through nw_batch_kernel in ONE launch (both directions come out of one sweep), then
+// the sequential decision chain is replayed on the host from the score table (csrc/dedup.cuh).
+int bk_dedup_reads(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_reads, const int32_t* mer_pos,
+                   const int64_t* batch_off, int64_t n_batches, double subseq_frac, uint8_t* check, uint8_t* flags,
+                   int64_t* n_pairs_out) {
+  if (!h) return BK_ERR_ARG;
+  std::vector<int32_t> pa, pb, out;
+  std::vector<int64_t> pair_base;
+  int rc = guarded(h, [&] {
+    if (n_reads < 0 || n_batches < 0 || (n_reads > 0 && (!seqs || !seq_off || !mer_pos || !check || !flags)) ||
+        (n_batches > 0 && !batch_off))
+      fail(BK_ERR_ARG, "bk_dedup_reads: null argument");
+    if (!(subseq_frac > 0.0 && subseq_frac <= 1.0)) fail(BK_ERR_ARG, "bk_dedup_reads: subseq_frac must be in (0, 1]");
+    int64_t total = 0;
+    pair_base.resize(n_batches + 1);
+    for (int64_t b = 0; b < n_batches; ++b) {
+      const int64_t lo = batch_off[b], hi = batch_off[b + 1];
+      if (lo < 0 || hi < lo || hi > n_reads || (b == 0 && lo != 0) || (b + 1 == n_batches && hi != n_reads))
+        fail(BK_ERR_ARG, "bk_dedup_reads: batch_off must partition the reads");
+      if (hi == lo) fail(BK_ERR_ARG, "bk_dedup_reads: batch %lld is empty (a batch is opened by its first read)", (long long)b);
+      pair_base[b] = total;
+      total += (hi - lo) * (hi - lo - 1) / 2;
+      if (total > DEDUP_MAX_PAIRS)
+        fail(BK_ERR_CAPACITY, "bk_dedup_reads: more than %lld read pairs in one call", (long long)DEDUP_MAX_PAIRS);
+    }
+    pair_base[n_batches] = total;
+    pa.resize(total); pb.resize(total); out.resize(total * 10);
+    for (int64_t b = 0; b < n_batches; ++b) {
+      const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
+      int64_t p = pair_base[b];
+      for (int64_t j = 1; j < n; ++j)
+        for (int64_t i = 0; i < j; ++i, ++p) { pa[p] = (int32_t)(lo + i); pb[p] = (int32_t)(lo + j); }
+    }
+  });
+  if (rc != BK_OK) return rc;
+  const int64_t total = pair_base.empty() ? 0 : pair_base.back();
+  if (n_pairs_out) *n_pairs_out = total;
+  if (total > 0) {
+    rc = bk_nw_batch(h, seqs, seq_off, n_reads, pa.data(), pb.data(), total, out.data(), 0, nullptr, nullptr, nullptr, nullptr);
+    if (rc != BK_OK) return rc;
+  }
+  return guarded(h, [&] {
+    for (int64_t b = 0; b < n_batches; ++b)
+      dedup_replay(seq_off, mer_pos, batch_off[b], batch_off[b + 1], out.data() + pair_base[b] * 10, subseq_frac, check, flags);
   });
 }
 

@@ -117,6 +117,39 @@ def load():
     return olc, asm
 
 
+def load_mm2():
+    """Return (olc_module, sv_assembly_mm2_module): the reference's older assembler variant
+    (sv_assembly_mm2.py, imported by nothing in the reference), loaded the same way as ``load``.
+    Used to pin the read-redundancy row: ``same_reads``, ``subseq``,
+    ``sim_seqs`` (:64-93) and ``read_batch.check_mer_read`` (:309-355).  Rewrites: the ``__main__``
+    driver (:577-) and ``from utils import *`` are dropped, ``len(seq)/2`` -> ``//`` (:125),
+    ``.items()[0]``/``.keys()[0]`` -> ``list(...)[0]`` (:45,:257); ``map``/``filter``/``zip`` are eager."""
+    fn = os.path.join(REFERENCE_ROOT, "sv_assembly_mm2.py")
+    if not os.path.isfile(fn):
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    olc, _asm = load()
+    with open(fn) as f:
+        src = f.read().expandtabs(8)
+    src = src[:src.index("if __name__ == '__main__'")]
+    src = _must_sub(r"^from utils import \*\s*$", "", src, 1, flags=re.M)
+    src = _must_sub(r"m = len\(seq\)/2", "m = len(seq)//2", src, 1)
+    src = _must_sub(r"akmers\.mers\.items\(\)\[0\]", "list(akmers.mers.items())[0]", src, 1)
+    src = _must_sub(r"self\.contigs\.keys\(\)\[0\]", "list(self.contigs.keys())[0]", src, 1)
+    mm2 = types.ModuleType("sv_assembly_mm2")
+    mm2.__file__ = fn
+    mm2.__dict__.update(map=_eager_map, filter=_eager_filter, zip=_eager_zip, fq_read=fq_read)
+    saved = sys.modules.get("olc")
+    sys.modules["olc"] = olc
+    try:
+        exec(compile(src, fn, "exec"), mm2.__dict__)
+    finally:
+        if saved is None:
+            del sys.modules["olc"]
+        else:
+            sys.modules["olc"] = saved
+    return olc, mm2
+
+
 def load_readers():
     """Namespace holding the reference's own ``fq_read``, ``FastqFile`` and
     ``get_fastq_reads`` (utils.py:203-246, 681-720), used to pin the ingest row

@@ -1,0 +1,126 @@
+"""Read-redundancy row on the CPU: the oracle restatement against the golden
+vectors generated from the reference's own same_reads / subseq / sim_seqs / read_batch.check_mer_read
+(oracle/make_golden_redundancy.py), and the host replay of bk_dedup_reads (csrc/dedup.cuh, compiled
+for the host with the score table supplied by the oracle's nw) against the same vectors."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from oracle import nw_py, redundancy_py as R
+
+G = golden("redundancy_cases.json")
+
+
+def test_pairs_against_reference():
+    for c in G["pairs"]:
+        a, b = c["seq1"], c["seq2"]
+        assert R.same_reads(a, b) == c["same_reads"] == c["same_reads_mm2"]
+        assert list(R.subseq(a, b, R.SUBSEQ_FRAC_LIVE)) == c["subseq_live"]
+        assert list(R.subseq(a, b, R.SUBSEQ_FRAC_MM2)) == c["subseq_mm2"]
+        got = []
+        for red in (False, True):
+            br = R.b_read("x", b)
+            br.redundant = red
+            got.append(R.sim_seqs(a, br))
+        assert got == c["sim_seqs"]
+
+
+def test_sim_seqs_is_true_for_unrelated_reads():
+    # the tuple-truthiness quirk (R1): pinned by the golden file, stated here explicitly
+    assert any(c["sim_seqs"][0] and not c["same_reads"] and not c["subseq_mm2"][0] for c in G["pairs"])
+    assert all(c["sim_seqs"] == [True, False] for c in G["pairs"])
+
+
+def test_pure_python_nw_gives_the_same_predicates():
+    for c in G["pairs"][:12]:
+        assert list(R.subseq(c["seq1"], c["seq2"], nw=nw_py.nw)) == c["subseq_mm2"]
+        assert R.same_reads(c["seq1"], c["seq2"], nw=nw_py.nw) == c["same_reads"]
+
+
+def test_batches_against_reference():
+    for b in G["batches"]:
+        checks, kept, redundant, deleted = R.dedup_batch([tuple(r) for r in b["reads"]])
+        assert checks == b["checks"]
+        assert kept == b["kept"]
+        assert redundant == b["redundant"]
+        assert deleted == b["deleted"]
+
+
+def test_empty_sequence_raises_like_the_reference():
+    with pytest.raises(NameError):
+        R.dedup_batch([("a", "ACGT", 0), ("b", "", 1)])
+
+
+# ---- the product's host replay (csrc/dedup.cuh), with the oracle's nw standing in for the kernel ----------
+
+@pytest.fixture(scope="module")
+def sim():
+    so = os.path.join(ROOT, "tests", "sim", "libdedup_sim.so")
+    src = os.path.join(ROOT, "tests", "sim", "dedup_sim.cpp")
+    deps = [src, os.path.join(ROOT, "breakmer_b200", "csrc", "dedup.cuh"), os.path.join(ROOT, "include", "breakmer_b200.h")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+def replay(sim, reads, frac):
+    """reads: [(id, seq, pos)] of ONE batch -> (checks, kept, redundant, deleted) through dedup_replay."""
+    n = len(reads)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(r[1]) for r in reads], out=off[1:])
+    pos = np.array([r[2] for r in reads], dtype=np.int32)
+    tab = np.zeros((max(1, n * (n - 1) // 2), 10), dtype=np.int32)
+    for j in range(1, n):
+        for i in range(j):
+            row = tab[j * (j - 1) // 2 + i]
+            row[:5] = nw_py.nw_fast(reads[i][1], reads[j][1])[2:]
+            row[5:] = nw_py.nw_fast(reads[j][1], reads[i][1])[2:]
+    check = np.zeros(n, dtype=np.uint8)
+    flags = np.zeros(n, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    sim.dedup_sim_replay(p(off), p(pos), ctypes.c_int64(0), ctypes.c_int64(n), p(tab), ctypes.c_double(frac), p(check), p(flags))
+    ids = [r[0] for r in reads]
+    return ([bool(c) for c in check], [ids[i] for i in range(n) if flags[i] & 1], [ids[i] for i in range(n) if flags[i] & 2],
+            sorted(ids[i] for i in range(n) if flags[i] & 4))
+
+
+def test_host_replay_against_reference(sim):
+    for b in G["batches"]:
+        checks, kept, redundant, deleted = replay(sim, [tuple(r) for r in b["reads"]], R.SUBSEQ_FRAC_MM2)
+        assert (checks, kept, redundant, deleted) == (b["checks"], b["kept"], b["redundant"], b["deleted"])
+
+
+def random_batch(rng, n, tag):
+    g = "".join(rng.choice("ACGT") for _ in range(400))
+    reads = []
+    for i in range(n):
+        rl = rng.choice([100, 100, 80, 60, 45])
+        pos = rng.randint(0, rl - 15)
+        seq = list(g[200 - pos:200 - pos + rl])
+        for _ in range(rng.choice([0, 0, 1, 2, 5])):
+            x = rng.randrange(len(seq))
+            seq[x] = rng.choice("ACGTN")
+        if reads and rng.random() < 0.2:
+            prev = reads[-1]
+            cut = rng.randint(0, 6)
+            seq, pos = list(prev[1][cut:len(prev[1]) - rng.randint(0, 6)]), prev[2] + 100 + i    # contained, fresh position
+        reads.append(("%s_%d" % (tag, i), "".join(seq), pos))
+    return reads
+
+
+def test_host_replay_against_oracle_on_random_batches(sim):
+    rng = random.Random(77)
+    seen = set()
+    for t in range(40):
+        reads = random_batch(rng, rng.randint(1, 25), "t%d" % t)
+        for frac in (R.SUBSEQ_FRAC_MM2, R.SUBSEQ_FRAC_LIVE):
+            exp = R.dedup_batch(reads, frac)
+            got = replay(sim, reads, frac)
+            assert got == (exp[0], exp[1], exp[2], exp[3])
+            seen.add((bool(exp[2]), len(exp[3]) > 0))
+    assert (True, True) in seen          # the redundant-flag arm was exercised
