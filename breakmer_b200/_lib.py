@@ -93,7 +93,7 @@ def load():
     lib.bk_nw_batch.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]
     lib.bk_dedup_reads.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_double, c_void_p,
-                                   c_void_p, POINTER(c_int64)]
+                                   c_void_p, POINTER(c_int64), POINTER(c_int32)]
     lib.bk_count_kmers.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                    POINTER(POINTER(c_uint64)), POINTER(POINTER(c_uint32)), POINTER(c_int64)]
     lib.bk_sample_only.argtypes = [H, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
@@ -122,7 +122,7 @@ def load():
     for name in ("bk_ingest_create", "bk_ingest_destroy", "bk_ingest_buffers", "bk_ingest_files", "bk_write_contigs",
                  "bk_write_sample_kmers"):
         getattr(lib, name).restype = c_int
-    for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_count_kmers", "bk_sample_only",
+    for name in ("bk_create", "bk_destroy", "bk_nw_batch", "bk_dedup_reads", "bk_count_kmers", "bk_sample_only",
                  "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
                  "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear"):
         getattr(lib, name).restype = c_int
@@ -131,8 +131,8 @@ def load():
 
 
 EXPORTED_SYMBOLS = (
-    "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_dedup_reads", "bk_count_kmers",
-    "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
+    "bk_version", "bk_device_count", "bk_create", "bk_destroy", "bk_last_error", "bk_nw_batch", "bk_dedup_reads",
+    "bk_count_kmers",    "bk_sample_only", "bk_compare_kmers_batch", "bk_batch_upload", "bk_compare_kmers_resident", "bk_kernel_times",
     "bk_kernel_times_reset", "bk_set_option", "bk_ref_cache_build", "bk_ref_cache_clear",
     "bk_ingest_create", "bk_ingest_destroy", "bk_ingest_last_error", "bk_ingest_buffers", "bk_ingest_files",
     "bk_write_contigs", "bk_write_sample_kmers")
@@ -214,9 +214,11 @@ class Handle:
             raise ValueError("dedup_reads: one mer_pos per read")
         check = np.zeros(n, dtype=np.uint8)
         flags = np.zeros(n, dtype=np.uint8)
-        n_pairs = c_int64()
+        n_pairs, n_launches = c_int64(), c_int32()
         self._check(self.lib.bk_dedup_reads(self.h, _ptr(data), _ptr(off), n, _ptr(mp), _ptr(bo), len(bo) - 1,
-                                            float(subseq_frac), _ptr(check), _ptr(flags), byref(n_pairs)))
+                                            float(subseq_frac), _ptr(check), _ptr(flags), byref(n_pairs),
+                                            byref(n_launches)))
+        self.last_dedup_launches = n_launches.value
         return check, flags, n_pairs.value
 
     # ---- jellyfish count + dump + load_kmers ----------------------------------------

@@ -253,16 +253,33 @@ int bk_destroy(bk_handle_t h) {
 
 const char* bk_last_error(bk_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 
-int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq, const int32_t* pair_a,
-                const int32_t* pair_b, int64_t n_pairs, int32_t* out, int want_aln, char* aln1, char* aln2,
-                const int64_t* aln_off, int32_t* aln_len) {
-  return guarded(h, [&] {
+}  // extern "C"
+
+namespace {
+
+// Sequences and per-warp scratch kept on the device between the launches of one call (bk_dedup_reads aligns the same
+// reads round after round): filled by the first nw_batch_run of the call, reused by the others.
+struct NwResident {
+  const uint8_t* seqs = nullptr;
+  const int64_t* seq_off = nullptr;
+  uint2* lastcol = nullptr;
+  int2* edge = nullptr;
+};
+
+// Body of bk_nw_batch.  keep == nullptr: a self-contained call (arenas reset, everything uploaded).
+void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq, const int32_t* pair_a,
+                  const int32_t* pair_b, int64_t n_pairs, int32_t* out, int want_aln, char* aln1, char* aln2,
+                  const int64_t* aln_off, int32_t* aln_len, NwResident* keep) {
+  {
     if (n_pairs < 0 || n_seq < 0 || (n_pairs > 0 && (!seqs || !seq_off || !pair_a || !pair_b || !out)))
       fail(BK_ERR_ARG, "bk_nw_batch: null argument");
     if (want_aln && (!aln1 || !aln2 || !aln_off || !aln_len)) fail(BK_ERR_ARG, "bk_nw_batch: alignment buffers missing");
     if (n_pairs == 0) return;
-    h->dev.reset();
-    h->pin.reset();
+    const bool first = !keep || !keep->seqs;
+    if (!keep) {
+      h->dev.reset();
+      h->pin.reset();
+    }
     int max_m = 0;
     std::vector<int64_t> ptr_off;
     int64_t ptr_total = 0, aln_total = 0;
@@ -282,19 +299,41 @@ int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t
       }
     }
     NwBatchParams P{};
-    P.seqs = (const uint8_t*)to_device(h, h->dev, seqs, (size_t)seq_off[n_seq]);
-    P.seq_off = to_device(h, h->dev, seq_off, (size_t)n_seq + 1);
+    if (first) {
+      P.seqs = (const uint8_t*)to_device(h, h->dev, seqs, (size_t)seq_off[n_seq]);
+      P.seq_off = to_device(h, h->dev, seq_off, (size_t)n_seq + 1);
+    } else {
+      P.seqs = keep->seqs;
+      P.seq_off = keep->seq_off;
+    }
     P.pair_a = to_device(h, h->dev, pair_a, (size_t)n_pairs);
     P.pair_b = to_device(h, h->dev, pair_b, (size_t)n_pairs);
     P.n_pairs = n_pairs;
     P.out = h->dev.get<int32_t>(n_pairs * 10);
     int64_t want_blocks = (n_pairs + NWB_WARPS - 1) / NWB_WARPS;
     const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)h->sm_count * 8);
-    if (max_m > 256) {
-      P.edge_stride = NW_MAX_LEN + 1;
-      P.edge = h->dev.get<int2>((size_t)grid * NWB_WARPS * 2 * P.edge_stride);
+    if (!keep) {
+      if (max_m > 256) {
+        P.edge_stride = NW_MAX_LEN + 1;
+        P.edge = h->dev.get<int2>((size_t)grid * NWB_WARPS * 2 * P.edge_stride);
+      }
+      P.lastcol = h->dev.get<uint2>((size_t)grid * NWB_WARPS * (NW_MAX_LEN / 2 + 1));
+    } else {
+      if (first) {                                   // scratch for the largest grid and the longest sequence of the call
+        const size_t warps = (size_t)h->sm_count * 8 * NWB_WARPS;
+        int64_t longest = 0;
+        for (int64_t q = 0; q < n_seq; ++q) longest = std::max(longest, seq_off[q + 1] - seq_off[q]);
+        keep->seqs = P.seqs;
+        keep->seq_off = P.seq_off;
+        keep->edge = longest > 256 ? h->dev.get<int2>(warps * 2 * (NW_MAX_LEN + 1)) : nullptr;
+        keep->lastcol = h->dev.get<uint2>(warps * (NW_MAX_LEN / 2 + 1));
+      }
+      if (max_m > 256) {
+        P.edge_stride = NW_MAX_LEN + 1;
+        P.edge = keep->edge;
+      }
+      P.lastcol = keep->lastcol;
     }
-    P.lastcol = h->dev.get<uint2>((size_t)grid * NWB_WARPS * (NW_MAX_LEN / 2 + 1));
     P.want_aln = want_aln;
     if (want_aln) {
       P.ptr_scratch = h->dev.get<uint8_t>(ptr_total);
@@ -324,55 +363,61 @@ int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t
         std::reverse(aln2 + aln_off[p], aln2 + aln_off[p] + aln_len[p]);
       }
     }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq, const int32_t* pair_a,
+                const int32_t* pair_b, int64_t n_pairs, int32_t* out, int want_aln, char* aln1, char* aln2,
+                const int64_t* aln_off, int32_t* aln_len) {
+  return guarded(h, [&] {
+    nw_batch_run(h, seqs, seq_off, n_seq, pair_a, pair_b, n_pairs, out, want_aln, aln1, aln2, aln_off, aln_len, nullptr);
   });
 }
 
 // read_batch.check_mer_read of the reference's older assembler variant (sv_assembly_mm2.py:290-355) for whole batches:
-// every ordered pair of a batch goes through nw_batch_kernel in ONE launch (both directions come out of one sweep), then
-// the sequential decision chain is replayed on the host from the score table (csrc/dedup.cuh).
+// the alignments the decision chains need go through nw_batch_kernel a round at a time for all batches together, and
+// the chains are replayed on the host from the score table (csrc/dedup.cuh).
 int bk_dedup_reads(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_reads, const int32_t* mer_pos,
                    const int64_t* batch_off, int64_t n_batches, double subseq_frac, uint8_t* check, uint8_t* flags,
-                   int64_t* n_pairs_out) {
+                   int64_t* n_pairs_out, int32_t* n_launches_out) {
   if (!h) return BK_ERR_ARG;
-  std::vector<int32_t> pa, pb, out;
-  std::vector<int64_t> pair_base;
   int rc = guarded(h, [&] {
     if (n_reads < 0 || n_batches < 0 || (n_reads > 0 && (!seqs || !seq_off || !mer_pos || !check || !flags)) ||
-        (n_batches > 0 && !batch_off))
+        (n_batches > 0 && !batch_off) || (n_batches == 0 && n_reads != 0))
       fail(BK_ERR_ARG, "bk_dedup_reads: null argument");
     if (!(subseq_frac > 0.0 && subseq_frac <= 1.0)) fail(BK_ERR_ARG, "bk_dedup_reads: subseq_frac must be in (0, 1]");
-    int64_t total = 0;
-    pair_base.resize(n_batches + 1);
+    if (n_reads >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "bk_dedup_reads: more than 2^31 reads in one call");
     for (int64_t b = 0; b < n_batches; ++b) {
       const int64_t lo = batch_off[b], hi = batch_off[b + 1];
       if (lo < 0 || hi < lo || hi > n_reads || (b == 0 && lo != 0) || (b + 1 == n_batches && hi != n_reads))
         fail(BK_ERR_ARG, "bk_dedup_reads: batch_off must partition the reads");
       if (hi == lo) fail(BK_ERR_ARG, "bk_dedup_reads: batch %lld is empty (a batch is opened by its first read)", (long long)b);
-      pair_base[b] = total;
-      total += (hi - lo) * (hi - lo - 1) / 2;
-      if (total > DEDUP_MAX_PAIRS)
-        fail(BK_ERR_CAPACITY, "bk_dedup_reads: more than %lld read pairs in one call", (long long)DEDUP_MAX_PAIRS);
-    }
-    pair_base[n_batches] = total;
-    pa.resize(total); pb.resize(total); out.resize(total * 10);
-    for (int64_t b = 0; b < n_batches; ++b) {
-      const int64_t lo = batch_off[b], n = batch_off[b + 1] - lo;
-      int64_t p = pair_base[b];
-      for (int64_t j = 1; j < n; ++j)
-        for (int64_t i = 0; i < j; ++i, ++p) { pa[p] = (int32_t)(lo + i); pb[p] = (int32_t)(lo + j); }
     }
   });
   if (rc != BK_OK) return rc;
-  const int64_t total = pair_base.empty() ? 0 : pair_base.back();
-  if (n_pairs_out) *n_pairs_out = total;
-  if (total > 0) {
-    rc = bk_nw_batch(h, seqs, seq_off, n_reads, pa.data(), pb.data(), total, out.data(), 0, nullptr, nullptr, nullptr, nullptr);
-    if (rc != BK_OK) return rc;
-  }
-  return guarded(h, [&] {
-    for (int64_t b = 0; b < n_batches; ++b)
-      dedup_replay(seq_off, mer_pos, batch_off[b], batch_off[b + 1], out.data() + pair_base[b] * 10, subseq_frac, check, flags);
+  if (n_pairs_out) *n_pairs_out = 0;
+  if (n_launches_out) *n_launches_out = 0;
+  if (n_batches == 0) return BK_OK;
+  int rounds = 0;
+  NwResident keep;                                   // reads uploaded once, reused by every round's launch
+  rc = guarded(h, [&] {
+    h->dev.reset();
+    h->pin.reset();
   });
+  if (rc != BK_OK) return rc;
+  rc = dedup_run(seq_off, mer_pos, batch_off, n_batches, subseq_frac, check, flags, n_pairs_out, &rounds,
+                 [&](const int32_t* pa, const int32_t* pb, int64_t n, int32_t* out) {
+                   return guarded(h, [&] {
+                     nw_batch_run(h, seqs, seq_off, n_reads, pa, pb, n, out, 0, nullptr, nullptr, nullptr, nullptr, &keep);
+                   });
+                 });
+  if (n_launches_out) *n_launches_out = rounds;
+  if (rc == BK_ERR_CAPACITY && h->err.find("nw:") != 0) h->err = "bk_dedup_reads: too many read pairs in one launch";
+  return rc;
 }
 
 int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int64_t n_rec, const uint32_t* rec_mult,

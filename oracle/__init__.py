@@ -12,7 +12,8 @@ golden vectors of its own.  ``oracle/ref_shim.py`` loads the reference's own
 ``/root/reference`` with a minimal Python-3 shim applied in memory, and
 ``oracle/make_golden.py`` uses that to generate the fixtures committed under
 ``tests/golden/``.  The restatements in this package are checked against
-those fixtures (``tests/test_oracle_*.py``).  K-mer counting follows
+those fixtures (``tests/test_oracle_*.py``).  ``ref_shim.load_mm2`` does the same for
+``sv_assembly_mm2.py`` (read-redundancy row, ``redundancy_py.py``).  K-mer counting follows
 jellyfish 1.1.11 (third party, absent from the reference tree): that part is
 "parity unpinned" -- see ``kmers_py.py``.
 """

@@ -68,25 +68,55 @@ def sim():
     return ctypes.CDLL(so)
 
 
-def replay(sim, reads, frac):
-    """reads: [(id, seq, pos)] of ONE batch -> (checks, kept, redundant, deleted) through dedup_replay."""
+ALIGN_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_int64,
+                            ctypes.POINTER(ctypes.c_int32))
+
+
+def replay_many(sim, batches, frac):
+    """batches: [[(id, seq, pos)]] -> ([(checks, kept, redundant, deleted)], alignments, rounds) through dedup_run,
+    with the oracle's nw standing in for the kernel."""
+    reads = [r for b in batches for r in b]
     n = len(reads)
     off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum([len(r[1]) for r in reads], out=off[1:])
     pos = np.array([r[2] for r in reads], dtype=np.int32)
-    tab = np.zeros((max(1, n * (n - 1) // 2), 10), dtype=np.int32)
-    for j in range(1, n):
-        for i in range(j):
-            row = tab[j * (j - 1) // 2 + i]
-            row[:5] = nw_py.nw_fast(reads[i][1], reads[j][1])[2:]
-            row[5:] = nw_py.nw_fast(reads[j][1], reads[i][1])[2:]
-    check = np.zeros(n, dtype=np.uint8)
-    flags = np.zeros(n, dtype=np.uint8)
+    boff = np.zeros(len(batches) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in batches], out=boff[1:])
+    asked = []
+
+    def align(pa, pb, cnt, out):
+        for p in range(cnt):
+            i, j = pa[p], pb[p]
+            assert i < j
+            asked.append((i, j))
+            f = nw_py.nw_fast(reads[i][1], reads[j][1])[2:] + nw_py.nw_fast(reads[j][1], reads[i][1])[2:]
+            for t in range(10):
+                out[p * 10 + t] = f[t]
+        return 0
+
+    check = np.full(n, 7, dtype=np.uint8)
+    flags = np.full(n, 255, dtype=np.uint8)
+    n_pairs, n_rounds = ctypes.c_int64(), ctypes.c_int()
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    sim.dedup_sim_replay(p(off), p(pos), ctypes.c_int64(0), ctypes.c_int64(n), p(tab), ctypes.c_double(frac), p(check), p(flags))
-    ids = [r[0] for r in reads]
-    return ([bool(c) for c in check], [ids[i] for i in range(n) if flags[i] & 1], [ids[i] for i in range(n) if flags[i] & 2],
-            sorted(ids[i] for i in range(n) if flags[i] & 4))
+    sim.dedup_sim_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                  ctypes.POINTER(ctypes.c_int), ALIGN_FN]
+    rc = sim.dedup_sim_run(p(off), p(pos), p(boff), len(batches), frac, p(check), p(flags), ctypes.byref(n_pairs),
+                           ctypes.byref(n_rounds), ALIGN_FN(align))
+    assert rc == 0
+    assert n_pairs.value == len(asked) == len(set(asked))            # no alignment is computed twice
+    out = []
+    for bi, b in enumerate(batches):
+        lo = int(boff[bi])
+        ids = [r[0] for r in b]
+        fl = flags[lo:lo + len(b)]
+        out.append(([bool(c) for c in check[lo:lo + len(b)]], [ids[i] for i in range(len(b)) if fl[i] & 1],
+                    [ids[i] for i in range(len(b)) if fl[i] & 2], sorted(ids[i] for i in range(len(b)) if fl[i] & 4)))
+    return out, n_pairs.value, n_rounds.value
+
+
+def replay(sim, reads, frac):
+    return replay_many(sim, [reads], frac)[0][0]
 
 
 def test_host_replay_against_reference(sim):
@@ -124,3 +154,30 @@ def test_host_replay_against_oracle_on_random_batches(sim):
             assert got == (exp[0], exp[1], exp[2], exp[3])
             seen.add((bool(exp[2]), len(exp[3]) > 0))
     assert (True, True) in seen          # the redundant-flag arm was exercised
+
+
+def test_host_replay_many_batches_in_shared_rounds(sim):
+    """All batches of a call share the launches: the golden batches and random ones in one run, fewer alignments
+    than all ordered pairs, and only a handful of rounds."""
+    rng = random.Random(5)
+    batches = [[tuple(r) for r in b["reads"]] for b in G["batches"]] + [random_batch(rng, 40, "m%d" % t) for t in range(12)]
+    got, n_pairs, n_rounds = replay_many(sim, batches, R.SUBSEQ_FRAC_MM2)
+    for b, g in zip(batches, got):
+        exp = R.dedup_batch(b, R.SUBSEQ_FRAC_MM2)
+        assert g == (exp[0], exp[1], exp[2], exp[3])
+    all_pairs = sum(len(b) * (len(b) - 1) // 2 for b in batches)
+    assert n_pairs < all_pairs // 3
+    assert 1 <= n_rounds <= 8
+
+
+def test_host_replay_long_run_of_dropped_reads(sim):
+    """More reads dropped in a row than the band and the window hold: the chain asks again, round after round."""
+    rng = random.Random(6)
+    s = "".join(rng.choice("ACGT") for _ in range(100))
+    inner = [("in%d" % i, s[1 + i % 3:90 - i % 5], 100 + i) for i in range(30)]       # each inside the opener
+    reads = [("open", s, 0)] + inner + [("tail", "".join(rng.choice("ACGT") for _ in range(80)), 500)]
+    exp = R.dedup_batch(reads, R.SUBSEQ_FRAC_MM2)
+    assert exp[1] == ["open", "tail"]
+    got, n_pairs, n_rounds = replay_many(sim, [reads], R.SUBSEQ_FRAC_MM2)
+    assert got[0] == (exp[0], exp[1], exp[2], exp[3])
+    assert n_rounds >= 4
