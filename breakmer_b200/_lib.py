@@ -144,11 +144,21 @@ def _ptr(a):
 
 def concat(seqs):
     """list of str/bytes -> (uint8 array, int64 offsets[n+1])."""
-    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
-    off = np.zeros(len(bs) + 1, dtype=np.int64)
-    if bs:
+    if not isinstance(seqs, (list, tuple)):
+        seqs = list(seqs)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if not seqs:
+        return np.zeros(0, dtype=np.uint8), off
+    try:
+        joined = "".join(seqs).encode()                  # all str (the usual case): one join, one encode
+        np.cumsum(np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs)), out=off[1:])
+        if len(joined) != off[-1]:                       # a non-ASCII character: byte lengths differ, do it per record
+            raise TypeError
+    except TypeError:
+        bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         np.cumsum([len(b) for b in bs], out=off[1:])
-    data = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, dtype=np.uint8)
+        joined = b"".join(bs)
+    data = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(0, dtype=np.uint8)
     return np.ascontiguousarray(data), off
 
 

@@ -56,3 +56,15 @@ def test_product_package_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "liboracle" not in src, fn
+
+
+def test_concat_str_bytes_and_non_ascii():
+    """The binding's packer: one join for all-str input, per-record encoding otherwise; offsets are byte offsets."""
+    import numpy as np
+    from breakmer_b200._lib import concat
+    for case in ([], ["ACGT", "", "NNA"], [b"AC", b"GT"], ["AC", b"GT"], ["é", "AC"], [""], (s for s in ["A", "CG"])):
+        case = list(case)
+        data, off = concat(iter(case))
+        bs = [s.encode() if isinstance(s, str) else bytes(s) for s in case]
+        assert data.tobytes() == b"".join(bs)
+        assert off.dtype == np.int64 and list(off) == [0] + list(np.cumsum([len(b) for b in bs]))
