@@ -8,6 +8,7 @@ sv_assembly.py:67-98):
     subseq(seq1, seq2)                :74-85    (bool, None | score); threshold SUBSEQ_FRAC
     sim_seqs(seq1, b_read)            :88-94    bool
     b_read, read_batch                :281-355  read_batch.check_mer_read(pos, read) one read at a time
+                                                (called from contig.check_read, :478; batch opened at :368)
 
 and adds the batched entry the GPU wants:
 

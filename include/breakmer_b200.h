@@ -62,19 +62,20 @@ int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t
                 int want_aln, char* aln1, char* aln2, const int64_t* aln_off, int32_t* aln_len);
 
 /* ---- read redundancy (sv_assembly_mm2.py:64-94, 290-355) ----------
- * read_batch.check_mer_read for whole batches.  Batch b = reads batch_off[b] .. batch_off[b+1]-1 of
- * the concatenated `seqs`, in the order the assembler meets them; its first read opens the batch
- * (read_batch.__init__, :290-294); mer_pos[r] = offset of the seed k-mer in read r (the `pos`
- * argument of check_mer_read).  subseq_frac = the subseq() identity threshold (0.90 in
- * sv_assembly_mm2.py:77, 0.85 in sv_assembly.py:80).  The alignments the decision chains need are
- * computed ahead of the decisions for all batches together (every read against its 4 predecessors in
- * one olc.nw launch; a further launch per round for chains that dropped more reads in a row), and the
- * chains are replayed on the host.  Outputs (caller-owned,
- * n_reads bytes each): check[r] = what check_mer_read returned for read r (1 for an opener);
- * flags[r] = BK_DEDUP_ADDED (1, appended to batch_reads) | BK_DEDUP_REDUNDANT (2, b_read.redundant)
- * | BK_DEDUP_DELETED (4, id in read_batch.delete).  n_pairs_out / n_launches_out (optional) =
- * alignments computed (each one sweep that yields both directions) and kernel launches made.
- * An empty sequence in a batch of two or more reads -> BK_ERR_EMPTY_SEQ (olc.nw raises NameError). */
+ * read_batch.check_mer_read (call site: contig.check_read, sv_assembly_mm2.py:478) for whole
+ * batches.  Batch b = reads batch_off[b] .. batch_off[b+1]-1 of the concatenated `seqs`, in the
+ * order the assembler meets them; its first read opens the batch (read_batch.__init__, :290-294);
+ * mer_pos[r] = offset of the seed k-mer in read r (the `pos` argument of check_mer_read).
+ * subseq_frac = the subseq() identity threshold (0.90 in sv_assembly_mm2.py:77, 0.85 in
+ * sv_assembly.py:80).  The alignments the decision chains need are computed ahead of the decisions
+ * for all batches together (every read against its 4 predecessors in one olc.nw launch; a further
+ * launch per round for chains that dropped more reads in a row), and the chains are replayed on the
+ * host.  Outputs (caller-owned, n_reads bytes each): check[r] = what check_mer_read returned for
+ * read r (1 for an opener); flags[r] = BK_DEDUP_ADDED (1, appended to batch_reads) |
+ * BK_DEDUP_REDUNDANT (2, b_read.redundant) | BK_DEDUP_DELETED (4, id in read_batch.delete).
+ * n_pairs_out / n_launches_out (optional) = alignments computed (each one sweep that yields both
+ * directions) and kernel launches made.  An empty sequence in a batch of two or more reads ->
+ * BK_ERR_EMPTY_SEQ (olc.nw raises NameError). */
 #define BK_DEDUP_ADDED 1
 #define BK_DEDUP_REDUNDANT 2
 #define BK_DEDUP_DELETED 4
