@@ -405,6 +405,7 @@ int bk_dedup_reads(bk_handle_t h, const char* seqs, const int64_t* seq_off, int6
   int rounds = 0;
   NwResident keep;                                   // reads uploaded once, reused by every round's launch
   rc = guarded(h, [&] {
+    h->err.clear();
     h->dev.reset();
     h->pin.reset();
   });
@@ -416,7 +417,7 @@ int bk_dedup_reads(bk_handle_t h, const char* seqs, const int64_t* seq_off, int6
                    });
                  });
   if (n_launches_out) *n_launches_out = rounds;
-  if (rc == BK_ERR_CAPACITY && h->err.find("nw:") != 0) h->err = "bk_dedup_reads: too many read pairs in one launch";
+  if (rc == BK_ERR_CAPACITY && h->err.empty()) h->err = "bk_dedup_reads: too many read pairs in one launch";
   return rc;
 }
 
