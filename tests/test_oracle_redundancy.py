@@ -181,3 +181,23 @@ def test_host_replay_long_run_of_dropped_reads(sim):
     got, n_pairs, n_rounds = replay_many(sim, [reads], R.SUBSEQ_FRAC_MM2)
     assert got[0] == (exp[0], exp[1], exp[2], exp[3])
     assert n_rounds >= 4
+
+
+def test_invariants_of_a_dedup_result(sim):
+    """Size-independent properties of check_mer_read's bookkeeping, on batches larger than the oracle comparison uses:
+    every read is either appended to the batch or in the delete set (a kept read flagged redundant is in both), the
+    opener is always kept, check is true exactly for the appended reads, and two kept, unflagged reads never share a
+    seed position (the sim_seqs quirk drops the second one)."""
+    rng = random.Random(11)
+    batches = [random_batch(rng, rng.randint(50, 200), "p%d" % t) for t in range(10)]
+    got, n_pairs, n_rounds = replay_many(sim, batches, R.SUBSEQ_FRAC_MM2)
+    for b, (checks, kept, redundant, deleted) in zip(batches, got):
+        ids = [r[0] for r in b]
+        pos = {r[0]: r[2] for r in b}
+        assert kept[0] == ids[0] and checks[0]
+        assert [i for i, c in zip(ids, checks) if c] == kept
+        assert set(kept) | set(deleted) == set(ids)
+        assert set(kept) & set(deleted) == set(redundant)
+        live = [pos[i] for i in kept if i not in set(redundant)]
+        assert len(live) == len(set(live))
+    assert n_pairs < sum(len(b) * (len(b) - 1) // 2 for b in batches) // 5
