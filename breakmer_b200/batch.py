@@ -151,6 +151,7 @@ class BatchOutput:
         self.kmer_dist = _arr(res.ctg_kmer_dist, n_km, np.int32)
         self.kmer_order = _arr(res.ctg_kmer_order, n_km, np.int32)
         self.region_status = _arr(res.region_status, R, np.int32)
+        self.region_dp_cells = _arr(res.region_dp_cells, R, np.int64)
         self.n_check_align = int(res.n_check_align)
         self.n_dp_cells = int(res.n_dp_cells)
         self.n_kmer_occurrences = int(res.n_kmer_occurrences)
@@ -198,6 +199,25 @@ def run(handle, packed, resident=False, decode=True):
     else:
         s = packed.struct()
         handle._check(handle.lib.bk_compare_kmers_batch(handle.h, ctypes.byref(s), ctypes.byref(res)))
+    if not decode:
+        return res
+    return BatchOutput(res, packed)
+
+
+def submit(handle, packed=None):
+    """bk_batch_submit: enqueue the device pass of `packed` (None: the batch uploaded with `upload`) and return.
+    `packed` must stay alive until `wait` has returned."""
+    if packed is None:
+        handle._check(handle.lib.bk_batch_submit(handle.h, None))
+    else:
+        s = packed.struct()
+        handle._check(handle.lib.bk_batch_submit(handle.h, ctypes.byref(s)))
+
+
+def wait(handle, packed=None, decode=True):
+    """bk_batch_wait: block until the submitted batch is done; BatchResult, or BatchOutput if decode."""
+    res = _lib.BatchResult()
+    handle._check(handle.lib.bk_batch_wait(handle.h, ctypes.byref(res)))
     if not decode:
         return res
     return BatchOutput(res, packed)

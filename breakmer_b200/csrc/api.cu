@@ -35,6 +35,8 @@ struct bk_handle_s {
   KernelTimers timers;
   std::string err;
   std::unique_ptr<Pipeline> pipe;
+  PendingBatch pending;            // the batch between bk_batch_submit and bk_batch_wait
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of a batch
   // bk_kernel_times result storage
   double kt_ms[KF_COUNT_];
   int64_t kt_launches[KF_COUNT_];
@@ -88,12 +90,12 @@ int bits_for(uint64_t n_values) {   // bits needed to represent 0 .. n_values-1
   return b;
 }
 
-// sort + run-length select + compaction on keys already emitted on the device.
-// Returns n_selected; device outputs through the pointers.
+// sort + run-length select + compaction on keys already emitted on the device.  Nothing here waits for the device: the
+// number of selected k-mers stays in device memory (d_n) and every output is allocated for its upper bound `sel_cap`.
 struct SelectOut {
-  uint64_t* mers;
+  uint64_t* mers;         // device, written at [base, base + *d_n) where base = *dst_base_dev (or 0)
   uint32_t* counts;
-  int64_t n;
+  uint32_t* d_n;          // device: number of k-mers selected by this call
   uint32_t* seg_counts;   // device, n_seg (or null)
 };
 
@@ -101,20 +103,35 @@ struct SelectOut {
 struct ProbeTable {
   const uint64_t* keys;
   const uint32_t* idx;
-  uint64_t mask;
+  const uint64_t* mask_dev;
   uint8_t* dead;
 };
 
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// sel_cap: upper bound of the number of selected runs (the caller knows one: every selected sample-only run holds a
+// soft-clip window; SELECT_ALL selects at most n).  dst_*: optional destination shared by several calls (region chunks),
+// each call writing at *dst_base_dev.
 SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int seg_bits, int mode,
-                          int64_t n_seg, bool use_ref_cache = false, int seg_shift = 0,
-                          const std::function<void(const ProbeTable&)>& probe = nullptr) {
-  SelectOut o{nullptr, nullptr, 0, nullptr};
+                          int64_t n_seg, int64_t sel_cap, bool use_ref_cache = false, int seg_shift = 0,
+                          const std::function<void(const ProbeTable&)>& probe = nullptr, uint64_t* dst_mers = nullptr,
+                          uint32_t* dst_counts = nullptr, const uint32_t* dst_base_dev = nullptr) {
+  SelectOut o{dst_mers, dst_counts, nullptr, nullptr};
   cudaStream_t st = h->st;
   if (n_seg > 0) {
     o.seg_counts = h->dev.get<uint32_t>(n_seg);
     BK_CUDA(cudaMemsetAsync(o.seg_counts, 0, n_seg * sizeof(uint32_t), st));
   }
-  if (n == 0) return o;
+  if (sel_cap > n) sel_cap = n;
+  if (!o.mers) {
+    o.mers = h->dev.get<uint64_t>(sel_cap ? sel_cap : 1);
+    o.counts = h->dev.get<uint32_t>(sel_cap ? sel_cap : 1);
+  }
+  o.d_n = h->dev.get<uint32_t>(1);
+  if (n == 0 || sel_cap == 0) {
+    BK_CUDA(cudaMemsetAsync(o.d_n, 0, sizeof(uint32_t), st));
+    return o;
+  }
   const int64_t tiles = rs_num_tiles(n);
   RadixSortScratch sc;
   sc.keys_alt = h->dev.get<uint64_t>(n);
@@ -131,70 +148,73 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
   rp.flags = h->dev.get<uint32_t>(n);
   rp.run_count = h->dev.get<uint32_t>(n);
   uint32_t* pos = h->dev.get<uint32_t>(n);
-  uint32_t* d_total = h->dev.get<uint32_t>(1);
   uint32_t* scan_tmp = h->dev.get<uint32_t>(scan_tmp_elems(n));
-  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const unsigned blocks = blocks_for(n, 256);
   {
     TimedLaunch t(h->timers, st, KF_RUN_SELECT);
     run_select_kernel<<<blocks, 256, 0, st>>>(rp);
   }
   {
     TimedLaunch t(h->timers, st, KF_SCAN, 3);
-    exclusive_scan_u32(rp.flags, pos, n, scan_tmp, d_total, st);
+    exclusive_scan_u32(rp.flags, pos, n, scan_tmp, o.d_n, st);
   }
-  uint32_t* h_total = h->pin.get<uint32_t>(1);
-  BK_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  BK_CUDA(stream_wait(h));
-  o.n = *h_total;
-  o.mers = h->dev.get<uint64_t>(o.n ? o.n : 1);
-  o.counts = h->dev.get<uint32_t>(o.n ? o.n : 1);
-  rp.pos = pos; rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts;
-  if (!probe || o.n == 0) {
+  rp.pos = pos;
+  if (!probe) {
+    rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts; rp.out_base_dev = dst_base_dev;
     TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
     run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
     BK_CUDA(cudaGetLastError());
     return o;
   }
   // ---- probe mode: the selected runs are only candidates; the caller streams further windows past them -----------
-  const int64_t n_cand = o.n;
-  uint32_t* cand_seg = h->dev.get<uint32_t>(n_cand);
-  rp.seg_counts = nullptr; rp.out_seg = cand_seg;
+  uint64_t* cand_mers = h->dev.get<uint64_t>(sel_cap);
+  uint32_t* cand_counts = h->dev.get<uint32_t>(sel_cap);
+  uint32_t* cand_seg = h->dev.get<uint32_t>(sel_cap);
+  rp.out_mers = cand_mers; rp.out_counts = cand_counts; rp.seg_counts = nullptr; rp.out_seg = cand_seg; rp.out_base_dev = nullptr;
   uint64_t cap = 1024;
-  while (cap < 2 * (uint64_t)n_cand) cap <<= 1;
+  while (cap < 2 * (uint64_t)sel_cap) cap <<= 1;           // worst case; the used size (mask + 1) is decided on the device
   uint64_t* tkeys = h->dev.get<uint64_t>(cap);
   uint32_t* tidx = h->dev.get<uint32_t>(cap);
-  uint8_t* dead = h->dev.get<uint8_t>(n_cand);
-  BK_CUDA(cudaMemsetAsync(tkeys, 0xFF, cap * sizeof(uint64_t), st));
-  BK_CUDA(cudaMemsetAsync(dead, 0, n_cand, st));
+  uint8_t* dead = h->dev.get<uint8_t>(sel_cap);
+  uint64_t* mask_dev = h->dev.get<uint64_t>(1);
+  BK_CUDA(cudaMemsetAsync(dead, 0, sel_cap, st));
   {
-    TimedLaunch t(h->timers, st, KF_RUN_SCATTER, 2);
+    TimedLaunch t(h->timers, st, KF_RUN_SCATTER, 4);
+    cand_table_size_kernel<<<1, 1, 0, st>>>(o.d_n, cap, mask_dev);
+    cand_table_clear_kernel<<<(unsigned)std::min<uint64_t>(cap / 256, (uint64_t)h->sm_count * 8), 256, 0, st>>>(tkeys, mask_dev);
     run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
-    cand_insert_kernel<<<blocks, 256, 0, st>>>(rp, tkeys, tidx, cap - 1);
+    cand_insert_kernel<<<blocks, 256, 0, st>>>(rp, tkeys, tidx, mask_dev);
   }
-  probe(ProbeTable{tkeys, tidx, cap - 1, dead});
-  uint32_t* flags2 = h->dev.get<uint32_t>(n_cand);
-  uint32_t* pos2 = h->dev.get<uint32_t>(n_cand);
-  uint32_t* scan_tmp2 = h->dev.get<uint32_t>(scan_tmp_elems(n_cand));
-  const unsigned blocks2 = (unsigned)((n_cand + 255) / 256);
+  probe(ProbeTable{tkeys, tidx, mask_dev, dead});
+  uint32_t* flags2 = h->dev.get<uint32_t>(sel_cap);
+  uint32_t* pos2 = h->dev.get<uint32_t>(sel_cap);
+  uint32_t* scan_tmp2 = h->dev.get<uint32_t>(scan_tmp_elems(sel_cap));
+  uint32_t* d_n2 = h->dev.get<uint32_t>(1);
+  const unsigned blocks2 = blocks_for(sel_cap, 256);
   {
     TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
-    survivor_flag_kernel<<<blocks2, 256, 0, st>>>(dead, n_cand, flags2);
+    survivor_flag_kernel<<<blocks2, 256, 0, st>>>(dead, o.d_n, sel_cap, flags2);
   }
   {
     TimedLaunch t(h->timers, st, KF_SCAN, 3);
-    exclusive_scan_u32(flags2, pos2, n_cand, scan_tmp2, d_total, st);
+    exclusive_scan_u32(flags2, pos2, sel_cap, scan_tmp2, d_n2, st);
   }
-  BK_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  BK_CUDA(stream_wait(h));
-  SelectOut f{nullptr, nullptr, (int64_t)*h_total, o.seg_counts};
-  f.mers = h->dev.get<uint64_t>(f.n ? f.n : 1);
-  f.counts = h->dev.get<uint32_t>(f.n ? f.n : 1);
   {
     TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
-    survivor_scatter_kernel<<<blocks2, 256, 0, st>>>(flags2, pos2, n_cand, o.mers, o.counts, cand_seg, f.mers, f.counts, f.seg_counts);
+    survivor_scatter_kernel<<<blocks2, 256, 0, st>>>(flags2, pos2, sel_cap, cand_mers, cand_counts, cand_seg, o.mers, o.counts,
+                                                     o.seg_counts, dst_base_dev);
   }
   BK_CUDA(cudaGetLastError());
-  return f;
+  o.d_n = d_n2;
+  return o;
+}
+
+// number of k-mers a finished select produced (host round trip; used by the small entry points only)
+int64_t select_count(bk_handle_t h, const SelectOut& so) {
+  uint32_t* hn = h->pin.get<uint32_t>(1);
+  BK_CUDA(cudaMemcpyAsync(hn, so.d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+  BK_CUDA(stream_wait(h));
+  return (int64_t)*hn;
 }
 
 }  // namespace
@@ -232,6 +252,12 @@ int bk_create(int device, bk_handle_t* out) {
     h->sync_ev = nullptr;
   }
   h->spin_sync = getenv("BK_BLOCKING_SYNC") == nullptr;
+  if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamDestroy(h->st);
+    delete h;
+    return BK_ERR_CUDA;
+  }
   *out = h;
   return BK_OK;
 }
@@ -241,6 +267,8 @@ int bk_destroy(bk_handle_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->st);
   if (h->sync_ev) cudaEventDestroy(h->sync_ev);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   h->pipe.reset();
   h->dev.release();
   h->pin.release();
@@ -458,15 +486,16 @@ int bk_count_kmers(bk_handle_t h, const char* bases, const int64_t* rec_off, int
       TimedLaunch t(h->timers, h->st, KF_EMIT);
       kmer_emit_kernel<<<(unsigned)((n_bases + EMIT_TILE - 1) / EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
     }
-    SelectOut so = sort_and_select(h, E.keys, E.vals, n_bases, k, 0, SELECT_ALL, 0);
-    uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
-    uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
-    if (so.n) {
-      BK_CUDA(cudaMemcpyAsync(hm, so.mers, so.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
-      BK_CUDA(cudaMemcpyAsync(hc, so.counts, so.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    SelectOut so = sort_and_select(h, E.keys, E.vals, n_bases, k, 0, SELECT_ALL, 0, n_bases);
+    const int64_t n_sel = select_count(h, so);
+    uint64_t* hm = h->pin.get<uint64_t>(n_sel ? n_sel : 1);
+    uint32_t* hc = h->pin.get<uint32_t>(n_sel ? n_sel : 1);
+    if (n_sel) {
+      BK_CUDA(cudaMemcpyAsync(hm, so.mers, n_sel * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(hc, so.counts, n_sel * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     }
     BK_CUDA(stream_wait(h));
-    *mers = hm; *counts = hc; *n_out = so.n;
+    *mers = hm; *counts = hc; *n_out = n_sel;
   });
 }
 
@@ -498,23 +527,50 @@ int bk_sample_only(bk_handle_t h, int k, const uint64_t* case_mers, const uint32
     for (int64_t i = 0; i < n_normal; ++i, ++w) { hk[w] = normal_mers[i]; hv[w] = 1u | ((uint32_t)TAG_NORMAL << 30); }
     uint64_t* dk = to_device(h, h->dev, hk, (size_t)n);
     uint32_t* dv = to_device(h, h->dev, hv, (size_t)n);
-    SelectOut so = sort_and_select(h, dk, dv, n, k, 0, SELECT_SAMPLE_ONLY, 0);
-    uint64_t* hm = h->pin.get<uint64_t>(so.n ? so.n : 1);
-    uint32_t* hc = h->pin.get<uint32_t>(so.n ? so.n : 1);
-    if (so.n) {
-      BK_CUDA(cudaMemcpyAsync(hm, so.mers, so.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
-      BK_CUDA(cudaMemcpyAsync(hc, so.counts, so.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
+    SelectOut so = sort_and_select(h, dk, dv, n, k, 0, SELECT_SAMPLE_ONLY, 0, n_case);
+    const int64_t n_sel = select_count(h, so);
+    uint64_t* hm = h->pin.get<uint64_t>(n_sel ? n_sel : 1);
+    uint32_t* hc = h->pin.get<uint32_t>(n_sel ? n_sel : 1);
+    if (n_sel) {
+      BK_CUDA(cudaMemcpyAsync(hm, so.mers, n_sel * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->st));
+      BK_CUDA(cudaMemcpyAsync(hc, so.counts, n_sel * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->st));
     }
     BK_CUDA(stream_wait(h));
-    *mers = hm; *counts = hc; *n_out = so.n;
+    *mers = hm; *counts = hc; *n_out = n_sel;
   });
 }
 
+// On a failed submit the stream may hold work that uses the arenas: drain it so that the handle is reusable.
+static int submit_guarded(bk_handle_t h, const bk_batch_input* in) {
+  if (h && h->pending.active) {                     // refused without touching the batch that is in flight
+    h->err = "a batch is already in flight on this handle (call bk_batch_wait first)";
+    return BK_ERR_ARG;
+  }
+  const int rc = guarded(h, [&] { pipeline_submit(h, in); });
+  if (rc != BK_OK && h) { cudaStreamSynchronize(h->st); cudaGetLastError(); h->pending.active = false; }
+  return rc;
+}
+static int wait_guarded(bk_handle_t h, bk_batch_result* out) {
+  if (h && !h->pending.active) { h->err = "bk_batch_wait: no batch in flight on this handle"; return BK_ERR_ARG; }
+  const int rc = guarded(h, [&] { pipeline_wait(h, out); });
+  if (rc != BK_OK && h) { cudaStreamSynchronize(h->st); cudaGetLastError(); h->pending.active = false; }
+  return rc;
+}
+
+int bk_batch_submit(bk_handle_t h, const bk_batch_input* in) {
+  if (h && !in && !h->pipe) { h->err = "bk_batch_submit: null input and no batch uploaded"; return BK_ERR_ARG; }
+  return submit_guarded(h, in);
+}
+
+int bk_batch_wait(bk_handle_t h, bk_batch_result* out) {
+  if (h && !out) { h->err = "bk_batch_wait: null argument"; return BK_ERR_ARG; }
+  return wait_guarded(h, out);
+}
+
 int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out) {
-  return guarded(h, [&] {
-    if (!in || !out) fail(BK_ERR_ARG, "bk_compare_kmers_batch: null argument");
-    pipeline_run(h, in, /*resident=*/false, out);
-  });
+  if (h && (!in || !out)) { h->err = "bk_compare_kmers_batch: null argument"; return BK_ERR_ARG; }
+  const int rc = submit_guarded(h, in);
+  return rc != BK_OK ? rc : wait_guarded(h, out);
 }
 
 int bk_batch_upload(bk_handle_t h, const bk_batch_input* in) {
@@ -525,10 +581,10 @@ int bk_batch_upload(bk_handle_t h, const bk_batch_input* in) {
 }
 
 int bk_compare_kmers_resident(bk_handle_t h, bk_batch_result* out) {
-  return guarded(h, [&] {
-    if (!out) fail(BK_ERR_ARG, "bk_compare_kmers_resident: null argument");
-    pipeline_run(h, nullptr, /*resident=*/true, out);
-  });
+  if (h && !out) { h->err = "bk_compare_kmers_resident: null argument"; return BK_ERR_ARG; }
+  if (h && !h->pipe) { h->err = "bk_compare_kmers_resident: no batch uploaded"; return BK_ERR_ARG; }
+  const int rc = submit_guarded(h, nullptr);
+  return rc != BK_OK ? rc : wait_guarded(h, out);
 }
 
 int bk_ref_cache_build(bk_handle_t h, const char* ref_bases, const int64_t* ref_off, int32_t n_regions, int32_t k) {

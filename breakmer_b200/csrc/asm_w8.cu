@@ -1,0 +1,14 @@
+// assemble_kernel<8> (assemble.cuh) and its launcher.
+#include "assemble.cuh"
+#include "assemble_launch.cuh"
+
+namespace bk {
+cudaError_t launch_assemble_w8(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(assemble_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(assemble_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+  if (e != cudaSuccess) return e;
+  assemble_kernel<8><<<grid, 32 * 8, dyn_smem, st>>>(A);
+  return cudaGetLastError();
+}
+}  // namespace bk

@@ -90,7 +90,6 @@ struct AsmParams {
   const int64_t* so_off;           // n_regions + 1
   const uint64_t* so_mer;
   const uint32_t* so_cnt;
-  const int32_t* seed_order;       // per region: local mer indices by (count, mer) descending (Q7)
   const int64_t* post_off;         // total mers + 1 : k-mer -> read posting lists
   const int32_t* post_read;        // local unique-read index, ascending within a list
   const int32_t* post_pos;         // first position of the mer in that read
@@ -98,7 +97,7 @@ struct AsmParams {
   const int32_t* rk_s;
   const int32_t* rk_pos;           // first position of that mer in the read
   // mutable per-mer / per-read state (zero-initialised except m_alive)
-  uint8_t* m_alive;                // akmers.mers membership (homopolymers start dead, Q5)
+  uint8_t* m_alive;                // akmers.mers membership (set by bind_region: homopolymers start dead, Q5)
   uint8_t* m_used;                 // buffer.used_mers
   uint32_t* m_checked;             // contig serial in whose checked_kmers the mer is
   uint32_t* m_taken;               // finalize serial (check_alt_reads' mer_set)
@@ -136,6 +135,7 @@ struct AsmParams {
                                    //                        reads_off, n_reads, kmers_off, n_kmers
   int32_t* region_status;
   int32_t* region_ncontigs;
+  unsigned long long* region_cells;  // per region: sum over its check_align calls of len(contig) * len(read)
   unsigned long long* stats;       // [0] check_align calls, [1] DP cells, [2] find_reads, [3] seeds, [8..] phase cycles
   unsigned long long* prof_regions; // BK_PHASE_PROF: n_regions x 8 phase cycles (or null)
 };
@@ -175,7 +175,7 @@ struct RegionCtx {
   int region, k;
   // mers
   int S; int64_t gm0;
-  const uint64_t* mer; const uint32_t* cnt; const int32_t* seed_order;
+  const uint64_t* mer; const uint32_t* cnt;
   uint8_t* alive; uint8_t* mused; uint32_t* checked; uint32_t* taken; uint32_t* first;
   int32_t* s_hash; bool hash_on;   // shared-memory hash of the region's mer table (find_mer)
   // reads
@@ -210,6 +210,7 @@ struct RegionCtx {
   int ct_init_read;
   int status;
   int n_out;
+  unsigned long long n_align, n_cells;   // work counters of the region (flushed once at its end)
 #if defined(BK_PHASE_PROF) && !defined(BK_SIM)
   long long ph_cycles[PH_COUNT_];
 #endif
@@ -637,10 +638,8 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
 // ---- contig.check_align (:449-504), decision part: v1/v2 come from the round -------------------------------
 BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2) {
   const int lc = c.clen;
-  if (lane() == 0) {
-    atomic_add(&c.P->stats[0], 1ull);
-    atomic_add(&c.P->stats[1], (unsigned long long)lc * (unsigned long long)lr);
-  }
+  c.n_align += 1ull;
+  c.n_cells += (unsigned long long)lc * (unsigned long long)lr;
   const int s1 = v1.score, s2 = v2.score;
   const int mn = lc < lr ? lc : lr;
   // :459-464 in integers (Q27)
@@ -1063,20 +1062,40 @@ BK_DEV void finish_contig(RegionCtx& c, int rc_thresh, int read_len) {
   emit_contig(c);
 }
 
+// ---- akmers.has_mers + mers.items()[0] (:43-45, :318-322; seed order Q7) ----------------------------------------
+// The reference keeps the mers in an OrderedDict sorted by (count, mer) descending and takes the first remaining one.
+// That is the live mer with the largest (count, local index) -- mers ascend with the index -- found here by a warp
+// arg-max over the region's table (S / 32 steps per seed, a few dozen seeds per region) instead of a global sort.
+// Returns -1 when no live mer with count > 1 is left.
+BK_DEV int next_seed(const RegionCtx& c) {
+  unsigned best_c = 0;
+  int best_s = -1;
+  for (int s = lane(); s < c.S; s += WARP) {
+    if (!c.alive[s]) continue;
+    const unsigned v = c.cnt[s];
+    if (best_s < 0 || v >= best_c) { best_c = v; best_s = s; }       // s ascends within a lane: >= keeps the larger index
+  }
+#ifndef BK_SIM
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+    if (os >= 0 && (best_s < 0 || oc > best_c || (oc == best_c && os > best_s))) { best_c = oc; best_s = os; }
+  }
+#endif
+  return (best_s >= 0 && best_c > 1u) ? best_s : -1;
+}
+
 // ---- init_assembly (:30-63) for one region ------------------------------------------------------------------
 BK_DEV void assemble_region(RegionCtx& c) {
   const AsmParams& P = *c.P;
   const int read_len = P.read_len[c.region];
-  int cursor = 0;
-  c.serial = 0; c.fin_serial = 0; c.status = ST_OK; c.n_out = 0;
+  c.serial = 0; c.fin_serial = 0; c.status = ST_OK; c.n_out = 0; c.n_align = 0; c.n_cells = 0;
   c.q_head = 0; c.q_tail = 0; c.n_alt = 0; c.n_del = 0;
   if (c.S == 0) return;                                              // :33-34
   while (c.status == ST_OK) {
-    // has_mers (:318-322): the first live mer in seed order carries the max count
-    while (cursor < c.S && !c.alive[c.seed_order[cursor]]) ++cursor;
-    if (cursor >= c.S) break;
-    const int seed = c.seed_order[cursor];
-    if (c.cnt[seed] <= 1) break;
+    const int seed = next_seed(c);                                   // has_mers (:318-322): max count must be > 1
+    if (seed < 0) break;
     if (lane() == 0) atomic_add(&P.stats[3], 1ull);
     const bool queued = setup_contigs(c, seed);
     if (queued && c.status == ST_OK) {                               // it is the FIFO head (the queue was empty)
@@ -1107,7 +1126,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.spec_w = spec_w; c.s_pred = s_pred; c.round_seed = -1; c.cur_e = 0; c.rnd_ver = 0;
   c.P = &P; c.region = region; c.k = P.k;
   c.gm0 = P.so_off[region]; c.S = (int)(P.so_off[region + 1] - c.gm0);
-  c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0; c.seed_order = P.seed_order + c.gm0;
+  c.mer = P.so_mer + c.gm0; c.cnt = P.so_cnt + c.gm0;
   c.alive = P.m_alive + c.gm0; c.mused = P.m_used + c.gm0; c.checked = P.m_checked + c.gm0; c.taken = P.m_taken + c.gm0;
   c.first = P.m_first + c.gm0;
   c.gu0 = P.u_off[region]; c.U = (int)(P.u_off[region + 1] - c.gu0);
@@ -1128,6 +1147,14 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.edge = c.edge_all;
   c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
   c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
+  // kmers.add_kmer (:272-278, Q5): a homopolymer (len(set(mer)) == 1) never enters akmers
+  for (int s = lane(); s < c.S; s += WARP) {
+    const uint64_t m = c.mer[s];
+    bool homo = true;
+    for (int t = 1; t < c.k; ++t) homo = homo && (((m >> (2 * t)) & 3ull) == (m & 3ull));
+    c.alive[s] = homo ? 0 : 1;
+  }
+  syncwarp();
   build_mer_hash(c);
 }
 
@@ -1197,7 +1224,12 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
       }
     }
 #endif
-    if (lane() == 0) { P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out; }
+    if (lane() == 0) {
+      P.region_status[region] = c.status; P.region_ncontigs[region] = c.n_out;
+      P.region_cells[region] = c.n_cells;
+      atomicAdd(&P.stats[0], c.n_align);
+      atomicAdd(&P.stats[1], c.n_cells);
+    }
     syncwarp();
   }
   if (W > 1) {

@@ -55,7 +55,7 @@ struct EmitParams {
   // is looked up in the open-addressed candidate table and a hit sets dead[probe_idx[slot]]
   const uint64_t* probe_keys;
   const uint32_t* probe_idx;
-  uint64_t probe_mask;
+  const uint64_t* probe_mask_dev;   // table size - 1, decided on the device from the candidate count
   uint8_t* dead;
 };
 
@@ -66,13 +66,13 @@ __device__ __forceinline__ uint64_t cand_hash(uint64_t x) {
   return x;
 }
 
-__device__ __forceinline__ void probe_candidate(const EmitParams& P, uint64_t key) {
-  uint64_t slot = cand_hash(key) & P.probe_mask;
+__device__ __forceinline__ void probe_candidate(const EmitParams& P, uint64_t mask, uint64_t key) {
+  uint64_t slot = cand_hash(key) & mask;
   for (;;) {
     const uint64_t t = P.probe_keys[slot];
     if (t == key) { P.dead[P.probe_idx[slot]] = 1; return; }
     if (t == KEY_INVALID) return;
-    slot = (slot + 1) & P.probe_mask;
+    slot = (slot + 1) & mask;
   }
 }
 
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
   const int tid = threadIdx.x;
   const int64_t p0 = (int64_t)blockIdx.x * EMIT_TILE;
   const int k = P.k;
+  const uint64_t pmask = P.probe_keys ? *P.probe_mask_dev : 0ull;
   if (tid == 0) {
     // last record whose start is <= p0
     int64_t lo = 0, hi = P.n_rec;           // rec_off[lo] <= p0 < rec_off[hi]
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
     const uint64_t hi = seg << (2 * k);
     if (P.probe_keys) {
       if (ok) {
-        probe_candidate(P, hi | fwd);
-        if (P.emit_rc) probe_candidate(P, hi | rc);
+        probe_candidate(P, pmask, hi | fwd);
+        if (P.emit_rc) probe_candidate(P, pmask, hi | rc);
       }
       continue;
     }
@@ -183,6 +184,7 @@ struct RunParams {
   uint32_t* out_counts;
   uint32_t* seg_counts;       // per region number of selected runs (atomic), may be null
   uint32_t* out_seg;          // region of each selected run, may be null (probe mode)
+  const uint32_t* out_base_dev; // device: where this call's output starts in out_mers / out_counts (null = 0; region chunks)
   // optional persistent reference k-mer cache: sorted mers of region r at ref_mers[ref_koff[r] .. ref_koff[r+1])
   const uint64_t* ref_mers;
   const int64_t* ref_koff;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(RunParams P) {
   if (!P.flags[i]) return;
   const uint64_t g = P.keys[i];
   const uint64_t mer = g & ((P.k == 32) ? ~0ull : ((1ull << (2 * P.k)) - 1ull));
-  const uint32_t dst = P.pos[i];
+  const uint32_t dst = P.pos[i] + (P.out_base_dev ? *P.out_base_dev : 0u);
   P.out_mers[dst] = mer;
   P.out_counts[dst] = P.run_count[i];
   if (P.out_seg) P.out_seg[dst] = (uint32_t)(g >> (2 * P.k));
@@ -249,11 +251,25 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(RunParams P) {
 
 // ---- probe mode: candidate hash table + survivor compaction -------------------------------------------------
 // insert every selected run head [region | mer] -> its compacted index
+// The candidate table is allocated for the worst case (every soft-clip window a candidate) but only its first
+// mask + 1 slots are used: mask is chosen on the device from the actual candidate count (load <= 0.5), so the table
+// stays L2 resident and the host never has to learn the count.
+__global__ void cand_table_size_kernel(const uint32_t* __restrict__ n_cand, uint64_t cap_bound, uint64_t* __restrict__ mask) {
+  uint64_t cap = 1024;
+  while (cap < 2ull * (uint64_t)*n_cand && cap < cap_bound) cap <<= 1;
+  *mask = cap - 1;
+}
+__global__ void __launch_bounds__(256) cand_table_clear_kernel(uint64_t* __restrict__ tkeys, const uint64_t* __restrict__ mask) {
+  const uint64_t n = *mask + 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) tkeys[i] = KEY_INVALID;
+}
+
 __global__ void __launch_bounds__(256) cand_insert_kernel(RunParams P, uint64_t* __restrict__ tkeys,
-                                                          uint32_t* __restrict__ tidx, uint64_t mask) {
+                                                          uint32_t* __restrict__ tidx, const uint64_t* __restrict__ mask_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
   if (!P.flags[i]) return;
+  const uint64_t mask = *mask_dev;
   const uint64_t key = P.keys[i];
   uint64_t slot = cand_hash(key) & mask;
   for (;;) {
@@ -264,10 +280,11 @@ __global__ void __launch_bounds__(256) cand_insert_kernel(RunParams P, uint64_t*
   }
 }
 
-__global__ void __launch_bounds__(256) survivor_flag_kernel(const uint8_t* __restrict__ dead, int64_t n,
-                                                            uint32_t* __restrict__ flags) {
+// n_bound elements are written (the scan that follows covers all of them); candidates are [0, *n_cand)
+__global__ void __launch_bounds__(256) survivor_flag_kernel(const uint8_t* __restrict__ dead, const uint32_t* __restrict__ n_cand,
+                                                            int64_t n_bound, uint32_t* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = dead[i] ? 0u : 1u;
+  if (i < n_bound) flags[i] = (i < (int64_t)*n_cand && !dead[i]) ? 1u : 0u;
 }
 
 __global__ void __launch_bounds__(256) survivor_scatter_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos,
@@ -275,13 +292,18 @@ __global__ void __launch_bounds__(256) survivor_scatter_kernel(const uint32_t* _
                                                                const uint32_t* __restrict__ in_counts,
                                                                const uint32_t* __restrict__ in_seg,
                                                                uint64_t* __restrict__ out_mers, uint32_t* __restrict__ out_counts,
-                                                               uint32_t* __restrict__ seg_counts) {
+                                                               uint32_t* __restrict__ seg_counts,
+                                                               const uint32_t* __restrict__ out_base_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !flags[i]) return;
-  const uint32_t dst = pos[i];
+  const uint32_t dst = pos[i] + (out_base_dev ? *out_base_dev : 0u);
   out_mers[dst] = in_mers[i];
   out_counts[dst] = in_counts[i];
   atomicAdd(&seg_counts[in_seg[i]], 1u);
 }
+
+
+__global__ void set_u32_kernel(uint32_t* __restrict__ dst, uint32_t v) { *dst = v; }
+__global__ void add_u32_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ acc) { *acc += *a; }
 
 }  // namespace bk

@@ -5,9 +5,10 @@
 //                   first occurrence; multiplicity = group size.  Hash every
 //                   record, sort by hash (radix_sort.cuh), resolve runs of equal
 //                   hash by exact byte comparison.
-//   seed order      kmers.get_all_kmer_values (sv_assembly.py:280-285, Q7):
-//                   (count, mer) descending per region, via one global sort;
-//                   homopolymer mers never enter akmers (:277, Q5).
+//   work order      regions ordered by a static cost estimate (unique reads x sample-only mers), most expensive
+//                   first, by one single-block counting sort on the device.  (Seed order -- kmers.get_all_kmer_values,
+//                   sv_assembly.py:280-285, Q7 -- and the homopolymer filter, :277, Q5, are evaluated inside the
+//                   assembler: assemble.cuh next_seed / bind_region.)
 //   inverted index  k-mer -> [(unique read, first position)] in read order; what
 //                   find_reads/read_search (sv_assembly.py:102-122) recompute with
 //                   a regex scan over every read for every k-mer.
@@ -118,30 +119,30 @@ __global__ void __launch_bounds__(256) widen_scan_kernel(const uint32_t* __restr
   if (i == n) out[i] = *total;
 }
 
-// thread per sample-only mer: liveness + seed sort key
-//   key = [ region | 0xFFFFFF - count : 24 | max - local index : idx_bits ]
-// ascending key order == (count, mer) descending within a region (mers ascend with the index)
-__global__ void __launch_bounds__(256) mer_prep_kernel(const uint64_t* __restrict__ mers, const uint32_t* __restrict__ counts,
-                                                        const int64_t* __restrict__ so_off, int n_regions, int64_t n_mers, int k,
-                                                        int idx_bits, uint8_t* __restrict__ alive, uint64_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, int* __restrict__ overflow) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_mers) return;
-  int lo = 0, hi = n_regions;                 // so_off[lo] <= g < so_off[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (so_off[mid] <= g) lo = mid; else hi = mid;
+// Work order of the assembler: regions by descending cost class.  cost = unique reads x sample-only mers (the DP work of a
+// region grows with both); class = floor(8 * log2(cost + 1)) quantises it to 1/8 octave, which is all the longest-first
+// heuristic needs.  One block: histogram, scan, scatter (order inside a class is arbitrary; results never depend on it).
+constexpr int WO_CLASSES = 512;
+__global__ void __launch_bounds__(1024) work_order_kernel(const int64_t* __restrict__ so_off, const int64_t* __restrict__ u_off,
+                                                          int n_regions, int32_t* __restrict__ order) {
+  __shared__ unsigned hist[WO_CLASSES];
+  __shared__ unsigned start[WO_CLASSES];
+  for (int c = threadIdx.x; c < WO_CLASSES; c += blockDim.x) hist[c] = 0;
+  __syncthreads();
+  auto cls = [&](int r) {
+    const float cost = (float)(so_off[r + 1] - so_off[r]) * (float)(u_off[r + 1] - u_off[r]) + 1.0f;
+    int c = (int)(8.0f * __log2f(cost));
+    c = c < 0 ? 0 : (c > WO_CLASSES - 1 ? WO_CLASSES - 1 : c);
+    return WO_CLASSES - 1 - c;                       // ascending class = descending cost
+  };
+  for (int r = threadIdx.x; r < n_regions; r += blockDim.x) atomicAdd(&hist[cls(r)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int c = 0; c < WO_CLASSES; ++c) { start[c] = run; run += hist[c]; }
   }
-  const uint64_t m = mers[g];
-  bool homo = true;                           // len(set(mer)) > 1  (sv_assembly.py:277)
-  for (int t = 1; t < k; ++t) homo = homo && (((m >> (2 * t)) & 3ull) == (m & 3ull));
-  alive[g] = homo ? 0 : 1;
-  const uint64_t local = (uint64_t)(g - so_off[lo]);
-  const uint32_t c = counts[g];
-  const uint64_t imask = (1ull << idx_bits) - 1ull;
-  if (c > 0xFFFFFFu || local > imask) *overflow = 1;
-  keys[g] = ((uint64_t)lo << (24 + idx_bits)) | ((uint64_t)(0xFFFFFFu - (c > 0xFFFFFFu ? 0xFFFFFFu : c)) << idx_bits) | (imask - local);
-  vals[g] = (uint32_t)local;
+  __syncthreads();
+  for (int r = threadIdx.x; r < n_regions; r += blockDim.x) order[atomicAdd(&start[cls(r)], 1u)] = r;
 }
 
 // ---------------------------------------------------------------------------------
@@ -167,15 +168,15 @@ __device__ __forceinline__ bool window_code_dev(const uint8_t* seq, int x, int k
 //   key2 = [ global read index | local mer index : s_bits ], value = position   (read -> k-mers)
 __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
     const uint8_t* __restrict__ rbases, const int64_t* __restrict__ roff, const int64_t* __restrict__ u_off,
-    const int32_t* __restrict__ u_rec, int n_regions, int64_t n_uniq, const int64_t* __restrict__ so_off,
+    const int32_t* __restrict__ u_rec, int n_regions, const uint32_t* __restrict__ n_uniq_dev, const int64_t* __restrict__ so_off,
     const uint64_t* __restrict__ so_mer, int k, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-    uint64_t* __restrict__ keys2, int u_bits, int s_bits, int ws_stride, unsigned long long* __restrict__ n_out,
-    unsigned long long cap) {
+    uint64_t* __restrict__ keys2, uint32_t* __restrict__ vals2, int u_bits, int s_bits, int ws_stride,
+    uint32_t* __restrict__ n_out, uint32_t cap) {
   extern __shared__ int32_t ws_all[];          // IDX_WARPS x ws_stride : local mer index of every window of the warp's read
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   int32_t* ws = ws_all + (size_t)w * ws_stride;
   const int64_t u = (int64_t)blockIdx.x * IDX_WARPS + w;
-  if (u >= n_uniq) return;
+  if (u >= (int64_t)*n_uniq_dev) return;           // the grid covers the record count, an upper bound of the unique reads
   int lo = 0, hi = n_regions;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -213,15 +214,16 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
         if (ws[y] == s) { first = false; break; }
     const unsigned mk = __ballot_sync(0xffffffffu, first);
     if (mk) {
-      unsigned long long base = 0;
-      if (l == 0) base = atomicAdd(n_out, (unsigned long long)__popc(mk));
+      uint32_t base = 0;
+      if (l == 0) base = atomicAdd(n_out, (uint32_t)__popc(mk));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (first) {
-        const unsigned long long dst = base + __popc(mk & ((1u << l) - 1u));
-        if (dst < cap) {
+        const uint32_t dst = base + __popc(mk & ((1u << l) - 1u));
+        if (dst < cap) {                           // cannot overflow: at most one entry per window, cap = read bases
           keys[dst] = ((uint64_t)(gm0 + s) << u_bits) | ulocal;
           keys2[dst] = ((uint64_t)u << s_bits) | (uint64_t)s;
           vals[dst] = (uint32_t)x;
+          vals2[dst] = (uint32_t)x;
         }
       }
     }
@@ -229,10 +231,13 @@ __global__ void __launch_bounds__(32 * IDX_WARPS) index_emit_kernel(
 }
 
 // thread per (group + 1): post_off[g] = lower bound of g << low_bits in the sorted keys
-__global__ void __launch_bounds__(256) post_off_kernel(const uint64_t* __restrict__ keys, int64_t n_post, int64_t n_mers,
-                                                        int low_bits, int64_t* __restrict__ post_off) {
+// (n_post and n_groups live on the device; the grid covers an upper bound of n_groups + 1)
+__global__ void __launch_bounds__(256) post_off_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_post_dev,
+                                                        const uint32_t* __restrict__ n_groups_dev, int low_bits,
+                                                        int64_t* __restrict__ post_off) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > n_mers) return;
+  const int64_t n_post = (int64_t)*n_post_dev;
+  if (g > (int64_t)*n_groups_dev) return;
   const uint64_t target = (uint64_t)g << low_bits;
   int64_t a = 0, b = n_post;
   while (a < b) {
@@ -243,17 +248,12 @@ __global__ void __launch_bounds__(256) post_off_kernel(const uint64_t* __restric
 }
 
 __global__ void __launch_bounds__(256) post_split_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                          int64_t n_post, int low_bits, int32_t* __restrict__ post_read,
-                                                          int32_t* __restrict__ post_pos) {
+                                                          const uint32_t* __restrict__ n_post_dev, int low_bits,
+                                                          int32_t* __restrict__ post_read, int32_t* __restrict__ post_pos) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_post) return;
+  if (i >= (int64_t)*n_post_dev) return;
   post_read[i] = (int32_t)(keys[i] & ((1ull << low_bits) - 1ull));
   post_pos[i] = (int32_t)vals[i];
-}
-
-__global__ void __launch_bounds__(256) unpack_u32_to_i32_kernel(const uint32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (int32_t)in[i];
 }
 
 }  // namespace bk

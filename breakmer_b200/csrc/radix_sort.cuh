@@ -25,9 +25,13 @@ constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // keys per tile
 constexpr int RS_WCHUNK = 32 * RS_ITEMS;             // contiguous keys per warp
 
+// n_dev (optional): the element count lives on the device (n is then only the upper bound the grid was sized for), so
+// that sorts of device-sized arrays need no host round trip.  Tiles past the count write empty histograms / do nothing.
 __global__ void __launch_bounds__(RS_THREADS) rs_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift,
-                                                               uint32_t* __restrict__ table, int64_t n_tiles) {
+                                                               uint32_t* __restrict__ table, int64_t n_tiles,
+                                                               const uint32_t* __restrict__ n_dev) {
   __shared__ uint32_t hist[256];
+  if (n_dev) n = (int64_t)*n_dev;
   hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -47,7 +51,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint64_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int64_t n, int shift,
-                                                                 const uint32_t* __restrict__ table, int64_t n_tiles) {
+                                                                 const uint32_t* __restrict__ table, int64_t n_tiles,
+                                                                 const uint32_t* __restrict__ n_dev) {
+  if (n_dev) n = (int64_t)*n_dev;
+  if ((int64_t)blockIdx.x * RS_TILE >= n) return;
   __shared__ uint32_t wcount[RS_WARPS][256];
   __shared__ uint64_t skeys[RS_TILE];
   __shared__ uint32_t svals[RS_TILE];
@@ -132,11 +139,11 @@ inline int64_t rs_num_tiles(int64_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 // number of passes run.
 inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int key_bits, const RadixSortScratch& s,
                             cudaStream_t st, uint64_t** keys_sorted, uint32_t** vals_sorted, KernelTimers& kt,
-                            bool aux = false) {
+                            bool aux = false, const uint32_t* n_dev = nullptr) {
   uint64_t* ka = keys; uint64_t* kb = s.keys_alt;
   uint32_t* va = vals; uint32_t* vb = s.vals_alt;
   int passes = 0;
-  if (n > 1) {
+  if (n > 1 || (n_dev && n > 0)) {
     const int64_t tiles = rs_num_tiles(n);
     passes = (key_bits + 7) / 8;
     if (passes > 8) passes = 8;
@@ -144,7 +151,7 @@ inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int key_b
       const int shift = 8 * p;
       {
         TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_COUNT);
-        rs_count_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, n, shift, s.table, tiles);
+        rs_count_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, n, shift, s.table, tiles, n_dev);
       }
       {
         TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_SCAN, 3);
@@ -152,7 +159,7 @@ inline int radix_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int key_b
       }
       {
         TimedLaunch t(kt, st, aux ? KF_AUX_SORT : KF_SORT_SCATTER);
-        rs_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, shift, s.table, tiles);
+        rs_scatter_kernel<<<(unsigned)tiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n, shift, s.table, tiles, n_dev);
       }
       uint64_t* tk = ka; ka = kb; kb = tk;
       uint32_t* tv = va; va = vb; vb = tv;

@@ -162,9 +162,21 @@ typedef struct bk_batch_result {
   int64_t n_kmer_occurrences;        /* k-mer windows of all inputs (reference forward + reverse, reads, soft clips, normal) */
   double  gpu_ms;                    /* device time of the call, CUDA events */
   int64_t n_sorted_keys;             /* windows that went through the sort (the sample's; the rest are streamed past) */
+  const int64_t* region_dp_cells;    /* per region: its share of n_dp_cells (cost models for sharding, shard.py) */
 } bk_batch_result;
 
 int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out);
+
+/* The same call in two halves, for callers that keep several batches in flight from ONE host thread (the region loop
+ * of sv_processor.py:185-201 turned into a pipeline; one handle per batch in flight, several handles per GPU):
+ * bk_batch_submit copies the inputs and enqueues the whole device pass on the handle's stream without waiting for
+ * the device at any point (every intermediate size stays in device memory), then returns; bk_batch_wait blocks until
+ * that pass is done and fills `out`.  in == NULL submits the batch uploaded with bk_batch_upload.  The input arrays
+ * must stay valid and unchanged until bk_batch_submit returns (page-locked inputs, e.g. from bk_ingest_*: until
+ * bk_batch_wait returns).  One batch in flight per handle.  A region holding a read longer than 4095 bases is left
+ * out of the device pass and reported through region_status (BK_ERR_CAPACITY); the other regions are unaffected. */
+int bk_batch_submit(bk_handle_t h, const bk_batch_input* in);
+int bk_batch_wait(bk_handle_t h, bk_batch_result* out);
 
 /* ---- timing support for bench.py ------------------------------------------------------
  * bk_batch_upload copies a batch to the device once; bk_compare_kmers_resident then runs

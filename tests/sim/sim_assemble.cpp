@@ -37,21 +37,8 @@ extern "C" int sim_assemble_region(
   P.read_len = &rl;
   int64_t so_off[2] = {0, n_mers};
   P.so_off = so_off; P.so_mer = mers; P.so_cnt = counts;
-  // seed order: (count, mer) descending (kernel: prep); alive: not a homopolymer
-  std::vector<int32_t> order(n_mers);
-  for (int i = 0; i < n_mers; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) {
-    if (counts[a] != counts[b]) return counts[a] > counts[b];
-    return mers[a] > mers[b];
-  });
-  P.seed_order = order.data();
+  // seed order and the homopolymer filter are evaluated inside the assembler (next_seed, bind_region)
   std::vector<uint8_t> alive(n_mers + 1), mused(n_mers + 1, 0);
-  for (int i = 0; i < n_mers; ++i) {
-    uint64_t m = mers[i];
-    bool homo = true;
-    for (int t = 1; t < k; ++t) homo = homo && (((m >> (2 * t)) & 3) == (m & 3));
-    alive[i] = homo ? 0 : 1;
-  }
   // posting lists (kernel: index)
   std::vector<std::vector<std::pair<int, int>>> post(n_mers);
   for (int u = 0; u < n_reads; ++u) {
@@ -120,6 +107,7 @@ extern "C" int sim_assemble_region(
   std::vector<int32_t> s_hash(MER_HASH_SIZE);
   bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), s_pred.data(), s_hash.data(), &sp, spec_w);
   assemble_region(c);
+  stats[0] += c.n_align; stats[1] += c.n_cells;
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];
   return c.status;

@@ -112,15 +112,53 @@ def test_results_do_not_depend_on_speculation_width(handle):
         handle.set_option("spec_width", 0)
 
 
-def test_capacity_error_is_reported_per_call(handle):
+def test_capacity_is_reported_per_region_and_the_rest_of_the_batch_completes(handle):
+    """A region with a read beyond the DP's length limit gets region_status = BK_ERR_CAPACITY; every other region of
+    the same call is processed normally, with read indices in the caller's numbering."""
     from breakmer_b200 import _lib, batch
-    r = synth.Region(name="long", k=15, ref_fwd="ACGT" * 50, reads=[("@a:1:1:1:1/1_0", "ACGT" * 1100, "I" * 4400, False)],
-                     sc_records=[("a", "ACGT" * 10)])
-    with pytest.raises(_lib.BreakmerError) as e:
-        batch.run(handle, batch.PackedBatch([r]))
-    assert e.value.code == _lib.BK_ERR_CAPACITY
-    # the handle stays usable
+    long_r = synth.Region(name="long", k=15, ref_fwd="ACGT" * 50, reads=[("@a:1:1:1:1/1_0", "ACGT" * 1100, "I" * 4400, False)],
+                          sc_records=[("a", "ACGT" * 10)])
+    normal = list(synth.config_regions("C2", n=6, start=3))
+    regions = normal[:2] + [long_r] + normal[2:4] + [long_r] + normal[4:]
+    out = batch.run(handle, batch.PackedBatch(regions))
+    for i, r in enumerate(regions):
+        if r is long_r:
+            assert out.region_status[i] == _lib.BK_ERR_CAPACITY
+            assert out.contig_records(i) == []
+        else:
+            only, ctg = oracle_region(r)
+            assert out.region_status[i] == 0
+            assert out.sample_only(i) == only, r.name
+            assert out.contig_records(i) == ctg, r.name
+    # alone in a call: same report, and the handle stays usable
+    out = batch.run(handle, batch.PackedBatch([long_r]))
+    assert list(out.region_status) == [_lib.BK_ERR_CAPACITY]
     check_batch(handle, [synth.config_region("C2", 7)])
+
+
+def test_submit_and_wait_keep_batches_in_flight_from_one_thread(handle):
+    """bk_batch_submit / bk_batch_wait: three handles, one host thread, results identical to the one-call form."""
+    from breakmer_b200 import _lib, batch
+    sets = [list(synth.config_regions("C2", n=8, start=10 * j)) for j in range(3)]
+    packed = [batch.PackedBatch(s) for s in sets]
+    handles = [_lib.Handle(0) for _ in sets]
+    try:
+        for rep in range(2):
+            for hh, pk in zip(handles, packed):
+                batch.submit(hh, pk)
+            with pytest.raises(_lib.BreakmerError):
+                batch.submit(handles[0], packed[0])          # one batch in flight per handle
+            outs = [batch.wait(hh, pk) for hh, pk in zip(handles, packed)]
+            for regions, pk, out in zip(sets, packed, outs):
+                ref = batch.run(handle, pk)
+                for i in range(len(regions)):
+                    assert out.sample_only(i) == ref.sample_only(i)
+                    assert out.contig_records(i) == ref.contig_records(i)
+        with pytest.raises(_lib.BreakmerError):
+            batch.wait(handles[0])                           # nothing in flight
+    finally:
+        for hh in handles:
+            hh.close()
 
 
 def _mutated(region, fn):
