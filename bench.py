@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
 
-A "step" is one pass of the whole hot path (target.compare_kmers: k-mer counting,
-sample-only selection, read grouping, init_assembly) over one batch of synthetic
-target regions.  At N=1 the workload is BASELINE.json configs[1]: the 500-target
-gene panel (k=15).  With N ranks every rank owns its own batch of 500 regions -- one sample of
-the panel per GPU, the same per-GPU problem on every rank (weak scaling, regions sharded by rank,
-no data-path collective).
+A "step" is one pass of the whole hot path (target.compare_kmers: k-mer counting, sample-only selection, read
+grouping, init_assembly) over the workload's regions.  The default workload is BASELINE.json configs[1], the
+500-target gene panel (k=15).
 
-One JSON line is printed by rank 0.  `value` is whole-job regions/s with the
-batch already resident in HBM; `e2e` is the same metric through the C-ABI entry
-point bk_compare_kmers_batch with HOST buffers (host->device copies and the
-result read-back inside the timed region).
+Multi-GPU (one process per GPU under torchrun): the workload's regions are PARTITIONED BY REGION --
+`shard.assign_lpt` on a static cost model, distinct regions on every rank, no data-path collective -- and the
+per-region results are gathered on the host in target-name order (`shard.gather_by_name`) and compared, by digest,
+with the same regions run on rank 0's GPU alone.
+  * C2 / C3 / C4 scale weakly: N ranks share a panel of N x 500 (N x 100) distinct regions;
+  * C5 scales strongly: the 20,000 exome-scale regions are split over the N ranks, in calls of <= 2,500 regions.
+The default line also carries `c5_strong` and `c3_sharded`: the same measurement for BASELINE.json configs 5 and 3.
+
+One JSON line is printed by rank 0.  `value` is whole-job regions/s with the inputs already resident in HBM; `e2e`
+is the same metric through the C-ABI calls bk_batch_submit / bk_batch_wait with HOST buffers (host->device copies and
+the result read-back inside the timed region).  Each rank drives its GPU from ONE host thread.
 """
 import argparse
 import json
@@ -27,15 +31,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# name -> (description, regions per GPU (weak) or in total (strong), scaling)
 WORKLOADS = {
-    "C1": ("C1: single synthetic 20 kb target region, 100 bp reads at 200x, planted 1.5 kb deletion, k=15", 1),
-    "C2": ("C2: 500-target gene panel, synthetic tumor reads with planted indels/inversions/tandem dups, k=15", 500),
-    "C3": ("C3: tumor/normal pair, 500 targets with normal-k-mer subtraction, k=15", 500),
-    "C4": ("C4: 2000x amplicon-depth panel, 100 amplicons, k=21", 100),
-    "C5": ("C5: exome-scale 20,000 target regions with planted translocations, k=15 (2,500 per GPU)", 2500),
+    "C1": ("C1: single synthetic 20 kb target region, 100 bp reads at 200x, planted 1.5 kb deletion, k=15", 1, "weak"),
+    "C2": ("C2: 500-target gene panel, synthetic tumor reads with planted indels/inversions/tandem dups, k=15", 500, "weak"),
+    "C3": ("C3: tumor/normal pair, 500 targets with normal-k-mer subtraction, k=15", 500, "weak"),
+    "C4": ("C4: 2000x amplicon-depth panel, 100 amplicons, k=21", 100, "weak"),
+    "C5": ("C5: exome-scale 20,000 target regions with planted translocations, k=15, region-sharded", 20000, "strong"),
 }
 METRIC = "target_regions_assembled_per_sec"
 UNIT = "regions/s"
+CALL_REGIONS = 2500          # regions per C-ABI call
+
+
+def config_dict(workload, world, regions_override=0):
+    """The `config` object of the JSON line -- identical in both arms."""
+    desc, n, scaling = WORKLOADS[workload]
+    if regions_override:
+        n = regions_override
+    total = n * world if scaling == "weak" else n
+    return {"workload": desc, "regions_total": total, "regions_per_gpu": total / float(world), "scaling": scaling,
+            "k": 21 if workload == "C4" else 15, "rc_thresh": 2,
+            "sharding": "by region: shard.assign_lpt on static costs, distinct regions per rank, host-side gather by target name"}
 
 
 def load_peaks():
@@ -45,15 +62,6 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def make_regions(workload, n, slice_index):
-    """The regions of one GPU.  Weak scaling runs the SAME per-GPU problem on every rank (one sample of the panel per
-    GPU: slice 0 of the generator everywhere), so that the per-N values differ by scaling effects only -- distinct slices
-    of the generator differ by +-5 % in DP work and 15 % in their longest region (profiles/r1_scaling.md); `--slice`
-    selects another one."""
-    from breakmer_b200 import synth
-    return list(synth.config_regions(workload, n=n, start=slice_index * n))
 
 
 # ---------------------------------------------------------------------------------
@@ -167,8 +175,8 @@ def reference_arm(args):
         return 0
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    desc, per_gpu = WORKLOADS[args.workload]
-    n_total = per_gpu * args.gpus
+    cfg = config_dict(args.workload, args.gpus, args.regions)
+    n_total = cfg["regions_total"]
     per_step = min(2 * cores, n_total)        # two regions per core per step keeps the pool busy past the stragglers
     budget = float(os.environ.get("BK_REF_BUDGET_S", "170"))
     ctx = mp.get_context("fork")
@@ -193,14 +201,14 @@ def reference_arm(args):
             if time.time() - t_start > budget and steps_done >= 1:
                 break
     value = timed_regions / timed_s if timed_s > 0 else 0.0
-    sample = ("%d regions per step (two per host core, dynamic pool) of %s, %d of %d timed steps completed within the %.0f s budget; "
-              "oracle port of the reference's CPython path over multiprocessing" %
-              (per_step, args.workload, steps_done, args.steps, budget))
+    sample = ("each step is a bounded sample of the workload: %d regions (two per host core, dynamic pool), %d of %d timed "
+              "steps completed within the %.0f s budget; oracle port of the reference's CPython path over multiprocessing" %
+              (per_step, steps_done, args.steps, budget))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * timed_s / max(1, steps_done), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": 21 if args.workload == "C4" else 15},
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_only_kmers_per_s": timed_kmers / timed_s if timed_s > 0 else 0.0,
@@ -213,288 +221,473 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------
-def gpu_arm(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+class Dist:
+    """torch.distributed plumbing: barrier + scalar reductions (NCCL) and the host-side object gather."""
 
-    from breakmer_b200 import _lib, batch
-    desc, per_gpu = WORKLOADS[args.workload]
-    if args.regions:
-        per_gpu = args.regions
-    regions = make_regions(args.workload, per_gpu, args.slice)
-    pk = batch.PackedBatch(regions).pin()        # pinned host buffers for the end-to-end leg
-    h = _lib.Handle(local_rank)
-    hbm_peak, peak_src = load_peaks()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (self.world, args.gpus))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
+    def _reduce(self, x, op):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX)
 
-    # ---- resident-input run: `value` -----------------------------------------------------
-    # Steps are independent batches, so the framework keeps `inflight` of them on the device at once (one
-    # handle = one stream + its own buffers each, one host thread per handle): the tail of one batch -- a few
-    # regions with long serial chains -- overlaps the bulk of the next.  inflight=1 is the strictly sequential mode.
-    n_fly = max(1, min(args.inflight, args.steps))
-    # one host thread per in-flight batch waits on its stream; when the ranks of this box have fewer cores than such threads,
-    # let them sleep on a blocking event instead of spinning (bk_set_option "blocking_sync")
-    cores_per_rank = max(1, (os.cpu_count() or 1) // max(1, world))
-    blocking = (n_fly > cores_per_rank and not os.environ.get("BK_BENCH_SPIN")) or bool(os.environ.get("BK_BLOCKING_SYNC"))
-    handles = [h] + [_lib.Handle(local_rank) for _ in range(n_fly - 1)]
-    for hh in handles:
-        hh.set_option("blocking_sync", 1 if blocking else 0)
-    for hh in handles:
-        batch.upload(hh, pk)
-    for _ in range(args.warmup):                # W untimed warm-up steps on every handle (arenas reach steady state)
-        for hh in handles:
-            batch.run(hh, pk, resident=True, decode=False)
-    # per-kernel device times: a short SEQUENTIAL pass on one handle with the library's CUDA-event timers on
-    # (in the pipelined region kernels of different batches share the SMs, so their durations are not comparable)
-    lat_ms = []
-    h.set_option("spec_width", int(os.environ.get("BK_BENCH_SEQ_W", "4")))   # latency-oriented setting for the sequential pass
-    h.kernel_times_reset(True)
-    for _ in range(3):
-        flush.zero_()
-        torch.cuda.synchronize()
-        r = batch.run(h, pk, resident=True, decode=False)
-        lat_ms.append(float(r.gpu_ms))
-    ktimes = h.kernel_times()
-    kt_steps = 3
-    spec_w = args.spec_width if args.spec_width else 4
-    for hh in handles:
-        hh.set_option("spec_width", spec_w)
-        batch.run(hh, pk, resident=True, decode=False)
-        hh.kernel_times_reset(False)             # timers off, launch counters zeroed for the timed region
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    last_box = {}
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM)
 
-    stagger_s = (min(lat_ms) / 1000.0 / n_fly) if (n_fly > 1 and lat_ms) else 0.0
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
-    def worker(j):
-        hh = handles[j]
-        if stagger_s:
-            time.sleep(j * stagger_s)       # spread the batches over one step latency so that tails and bulks overlap
-        for step in range(j, args.steps, n_fly):
-            if n_fly == 1:
-                flush.zero_()               # L2 flush between timed iterations (sequential mode only)
-                torch.cuda.synchronize()
-            res = batch.run(hh, pk, resident=True, decode=False)
-            last_box[j] = (int(res.n_contigs), int(res.n_check_align), int(res.n_dp_cells),
-                           int(res.n_kmer_occurrences), int(res.so_off[res.n_regions]), float(res.gpu_ms),
-                           int(res.n_sorted_keys))
 
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    ev0.record()
-    threads = [threading.Thread(target=worker, args=(j,)) for j in range(n_fly)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    torch.cuda.synchronize()
-    ev1.record()
-    ev1.synchronize()
-    barrier()
-    wall_s = time.time() - t0
-    clocks = sampler.stop()
-    gpu_launches = 0
-    for hh in handles:
-        gpu_launches += int(sum(v[1] for v in hh.kernel_times().values()))
-    dev_s = max_over_ranks(ev0.elapsed_time(ev1) / 1000.0)      # device clock across the K steps, max over ranks
-    step_ms = [1000.0 * dev_s / args.steps] * args.steps
-    n_regions_total = per_gpu * world
-    value = n_regions_total * args.steps / dev_s
-    n_contigs, n_check, n_cells, n_occ, n_only, _, n_sorted = last_box[0]
-    kmers_per_s = sum_over_ranks(float(n_only)) * args.steps / dev_s
+class ShardRun:
+    """One workload, partitioned by region over the ranks; this rank's share as resident / host-buffer passes."""
 
-    # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------------------
-    for hh in handles:
-        batch.run(hh, pk, decode=False)
-    e2e_box = {}
+    def __init__(self, D, workload, total, inflight, spec_width=0, call_regions=CALL_REGIONS):
+        from breakmer_b200 import _lib, batch, shard, synth
+        self.D = D
+        self.workload = workload
+        self.total = total
+        t0 = time.time()
+        # every rank derives the same partition from the same static costs (no communication)
+        self.regions = [synth.config_region(workload, i) for i in range(total)]
+        self.costs = [shard.region_cost(r) for r in self.regions]
+        self.owned = shard.assign_lpt(self.costs, D.world)
+        self.mine = self.owned[D.rank]
+        self.chunks = shard.chunk_indices(self.mine, call_regions)
+        self.packed = [batch.PackedBatch([self.regions[i] for i in c]).pin() for c in self.chunks]
+        self.gen_s = time.time() - t0
+        nc = max(1, len(self.chunks))
+        self.n_handles = nc * ((max(1, inflight) + nc - 1) // nc)      # a multiple of the chunk count
+        self.handles = [_lib.Handle(D.local_rank) for _ in range(self.n_handles)]
+        for h in self.handles:
+            h.set_option("blocking_sync", 1)        # the single host thread of this rank sleeps while it waits
+            if spec_width:
+                h.set_option("spec_width", spec_width)
+        self.k = self.packed[0].k if self.packed else 15
+        self.last = {}
 
-    def e2e_worker(j):
-        hh = handles[j]
-        if stagger_s:
-            time.sleep(j * stagger_s)
-        for step in range(j, args.steps, n_fly):
-            e2e_box[j] = batch.run(hh, pk, decode=False)
+    def warm_passes(self, w=3):
+        """passes that give every handle at least three calls (its arenas are final after the second)"""
+        nc = max(1, len(self.packed))
+        return max(w, (3 * self.n_handles + nc - 1) // nc)
 
-    barrier()
-    t0 = time.time()
-    threads = [threading.Thread(target=e2e_worker, args=(j,)) for j in range(n_fly)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    torch.cuda.synchronize()
-    e2e_local = time.time() - t0
-    barrier()
-    res = e2e_box[0]
-    e2e_s = max_over_ranks(e2e_local)
-    e2e_value = n_regions_total * args.steps / e2e_s
-    h2d = pk.input_bytes + 8 * (len(pk.read_off) + len(pk.sc_off) + len(pk.ref_off)) + len(pk.read_flags)
-    out = batch.BatchOutput(res, pk)
-    d2h = int(out.seq.nbytes + out.kmer_locs.nbytes + out.indel_only.nbytes + out.others.nbytes + out.reads.nbytes +
-              out.kmer_mer.nbytes + 2 * out.kmer_pos.nbytes + out.so_mers.nbytes + out.so_counts.nbytes +
-              out.uniq_rec.nbytes + out.uniq_mult.nbytes)
+    def upload(self):
+        from breakmer_b200 import batch
+        for j, h in enumerate(self.handles):
+            if self.packed:
+                batch.upload(h, self.packed[j % len(self.packed)])
 
-    # ---- same steps with the persistent reference k-mer cache (reported beside the headline, not as it) ----
-    ref_cache = None
-    if not args.no_ref_cache_leg:
-        pk_nr = batch.PackedBatch(regions, with_ref=False).pin()
-        for hh in handles:
-            hh.ref_cache_build([r.ref_fwd for r in regions], pk.k)
-            batch.upload(hh, pk_nr)
-            batch.run(hh, pk_nr, resident=True, decode=False)
+    def run_pass(self, steps, resident, flush=None):
+        """steps passes over this rank's chunks from ONE host thread: bk_batch_submit keeps n_handles batches queued
+        on the device, bk_batch_wait collects them in order.  Returns the results of the last pass per chunk."""
+        from breakmer_b200 import batch
+        nc = len(self.packed)
+        if nc == 0:
+            return
+        H = self.n_handles
+        items = steps * nc
+        t_sub = t_wait = 0.0
+        for t in range(items):
+            h = self.handles[t % H]
+            if t >= H:
+                t0 = time.perf_counter()
+                self.last[(t - H) % nc] = (t % H, batch.wait(h, decode=False))
+                t_wait += time.perf_counter() - t0
+            if flush is not None and H == 1:
+                flush.zero_()                       # sequential mode: flush L2 between timed steps
+            t0 = time.perf_counter()
+            batch.submit(h, None if resident else self.packed[t % nc])
+            t_sub += time.perf_counter() - t0
+        for t in range(max(0, items - H), items):
+            t0 = time.perf_counter()
+            self.last[t % nc] = (t % H, batch.wait(self.handles[t % H], decode=False))
+            t_wait += time.perf_counter() - t0
+        post = [float(r.host_post_ms) for _j, r in self.last.values()]
+        self.host_ms = {"submit_ms_per_call": 1000.0 * t_sub / items, "wait_ms_per_call": 1000.0 * t_wait / items,
+                        "of_which_result_tables_ms": sum(post) / max(1, len(post)),
+                        "note": "host thread: time inside bk_batch_submit (copies + launches) and bk_batch_wait (mostly blocked on the device)"}
 
-        def rc_worker(j):
-            hh = handles[j]
-            if stagger_s:
-                time.sleep(j * stagger_s)
-            for step in range(j, args.steps, n_fly):
-                batch.run(hh, pk_nr, resident=True, decode=False)
-
-        barrier()
+    def timed(self, steps, resident, flush=None):
+        """-> (device seconds by CUDA events, wall seconds), both max over ranks"""
+        torch = self.D.torch
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        self.D.barrier()
+        t0 = time.time()
         ev0.record()
-        threads = [threading.Thread(target=rc_worker, args=(j,)) for j in range(n_fly)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        self.run_pass(steps, resident, flush)
         torch.cuda.synchronize()
         ev1.record()
         ev1.synchronize()
-        barrier()
-        rc_s = max_over_ranks(ev0.elapsed_time(ev1) / 1000.0)
-        ref_cache = {"value": n_regions_total * args.steps / rc_s, "unit": UNIT, "ms_per_step": 1000.0 * rc_s / args.steps,
+        wall = time.time() - t0
+        self.D.barrier()
+        return self.D.max(ev0.elapsed_time(ev1) / 1000.0), self.D.max(wall)
+
+    def counters(self):
+        """work counters of one pass over this rank's chunks (from the last results)"""
+        tot = {"contigs": 0, "check_align": 0, "dp_cells": 0, "kmer_occ": 0, "sorted": 0, "sample_only": 0}
+        for c, (_j, res) in self.last.items():
+            tot["contigs"] += int(res.n_contigs); tot["check_align"] += int(res.n_check_align)
+            tot["dp_cells"] += int(res.n_dp_cells); tot["kmer_occ"] += int(res.n_kmer_occurrences)
+            tot["sorted"] += int(res.n_sorted_keys); tot["sample_only"] += int(res.so_off[res.n_regions])
+        return tot
+
+    def check_against_single_gpu(self):
+        """Host-side gather of the per-region result digests in target-name order; rank 0 runs ALL regions on its own
+        GPU and compares.  Returns (ok, digest of digests, regions) on rank 0, (None, None, n) elsewhere."""
+        from breakmer_b200 import batch, shard
+        local = {}
+        for c, (_j, res) in sorted(self.last.items()):
+            out = batch.BatchOutput(res, self.packed[c])
+            local.update(shard.region_digests(out, self.packed[c]))
+        merged = shard.gather_by_name(local, self.D.rank, self.D.world)
+        ok, dig = None, None
+        if self.D.rank == 0:
+            single = {}
+            for c in shard.chunk_indices(range(self.total), CALL_REGIONS):
+                if self.D.world == 1 and len(self.chunks) == 1 and c == self.chunks[0]:
+                    single.update(local)          # one rank, one call: it IS the single-GPU run
+                    continue
+                pk = batch.PackedBatch([self.regions[i] for i in c])
+                single.update(shard.region_digests(batch.run(self.handles[0], pk), pk))
+            ok = bool(merged == dict(sorted(single.items())) and list(merged) == sorted(r.name for r in self.regions))
+            dig = shard.digest_of_digests(merged)
+        return ok, dig, len(local)
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+        self.handles = []
+
+
+def sharded_summary(D, workload, total, args, steps):
+    """value / e2e / sharding check of one more workload (the c5_strong and c3_sharded keys of the line)."""
+    run = ShardRun(D, workload, total, args.inflight, args.spec_width)
+    try:
+        run.upload()
+        run.run_pass(run.warm_passes(), True)
+        dev_s, _ = run.timed(steps, True)
+        run.run_pass(run.warm_passes(), False)
+        _, e2e_s = run.timed(steps, False)
+        cnt = run.counters()
+        ok, dig, _n = run.check_against_single_gpu()
+        desc, _n0, scaling = WORKLOADS[workload]
+        return {"workload": desc, "regions_total": total, "scaling": scaling, "steps": steps,
+                "value": total * steps / dev_s, "unit": UNIT, "ms_per_pass": 1000.0 * dev_s / steps,
+                "e2e": {"value": total * steps / e2e_s, "unit": UNIT, "ms_per_pass": 1000.0 * e2e_s / steps},
+                "sample_only_kmers_per_s": D.sum(float(cnt["sample_only"])) * steps / dev_s,
+                "regions_per_rank": [len(o) for o in run.owned], "calls_per_pass_this_rank": len(run.chunks),
+                "equal_to_single_gpu_run": ok, "result_digest": dig, "generate_s": round(run.gen_s, 1)}
+    finally:
+        run.close()
+
+
+def gpu_arm(args):
+    D = Dist(args)
+    torch = D.torch
+    from breakmer_b200 import batch
+    desc, n0, scaling = WORKLOADS[args.workload]
+    cfg = config_dict(args.workload, D.world, args.regions)
+    total = cfg["regions_total"]
+    hbm_peak, peak_src = load_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    run = ShardRun(D, args.workload, total, args.inflight, args.spec_width)
+    H = run.n_handles
+    h = run.handles[0]
+
+    # ---- resident-input run: `value` -----------------------------------------------------
+    # Steps are independent batches; the rank's single host thread keeps `inflight` of them queued on the device
+    # (one handle = one stream + its own buffers each), so the tail of one batch -- a few regions with long serial
+    # chains -- overlaps the bulk of the next.  inflight=1 is the strictly sequential mode (L2 flushed between steps).
+    run.upload()
+    run.run_pass(run.warm_passes(args.warmup), True)   # >= W untimed warm-up steps, >= 3 calls on every handle (arenas reach steady state)
+    # per-kernel device times: a short SEQUENTIAL pass on one handle with the library's CUDA-event timers on
+    # (in the pipelined region kernels of different batches share the SMs, so their durations are not comparable)
+    lat_ms = []
+    h.kernel_times_reset(True)
+    kt_steps = 3
+    for _ in range(kt_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        r = batch.run(h, None, resident=True, decode=False)
+        lat_ms.append(float(r.gpu_ms))
+    ktimes = h.kernel_times()
+    for hh in run.handles:
+        hh.kernel_times_reset(False)                # timers off, launch counters zeroed for the timed region
+    sampler = ClockSampler(D.local_rank)
+    sampler.start()
+    dev_s, wall_s = run.timed(args.steps, True, flush)
+    host_resident = run.host_ms
+    clocks = sampler.stop()
+    gpu_launches = 0
+    for hh in run.handles:
+        gpu_launches += int(sum(v[1] for v in hh.kernel_times().values()))
+    value = total * args.steps / dev_s
+    cnt = run.counters()
+    n_cells_rank = cnt["dp_cells"]
+    kmers_per_s = D.sum(float(cnt["sample_only"])) * args.steps / dev_s
+    cells_all = D.sum(float(n_cells_rank))
+
+    # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------------------
+    run.run_pass(run.warm_passes(), False)
+    _, e2e_s = run.timed(args.steps, False)
+    host_e2e = run.host_ms
+    e2e_value = total * args.steps / e2e_s
+    pk0 = run.packed[0]
+    h2d = sum(pk.input_bytes + 8 * (len(pk.read_off) + len(pk.sc_off) + len(pk.ref_off)) + len(pk.read_flags) for pk in run.packed)
+    d2h = 0
+    outs = {c: batch.BatchOutput(res, run.packed[c]) for c, (_j, res) in run.last.items()}
+    for out in outs.values():
+        d2h += int(out.seq.nbytes + out.kmer_locs.nbytes + out.indel_only.nbytes + out.others.nbytes + out.reads.nbytes +
+                   out.kmer_mer.nbytes + 2 * out.kmer_pos.nbytes + out.so_mers.nbytes + out.so_counts.nbytes +
+                   out.uniq_rec.nbytes + out.uniq_mult.nbytes)
+    ok, digest, _nl = run.check_against_single_gpu()
+
+    # ---- same steps with the persistent reference k-mer cache (reported beside the headline, not as it) ----
+    ref_cache = None
+    if not args.no_ref_cache_leg and len(run.packed) == 1:
+        regions_mine = [run.regions[i] for i in run.mine]
+        pk_nr = batch.PackedBatch(regions_mine, with_ref=False).pin()
+        saved = run.packed
+        for hh in run.handles:
+            hh.ref_cache_build([r.ref_fwd for r in regions_mine], pk0.k)
+        run.packed = [pk_nr]
+        run.upload()
+        run.run_pass(run.warm_passes(), True)
+        rc_s, _ = run.timed(args.steps, True)
+        ref_cache = {"value": total * args.steps / rc_s, "unit": UNIT, "ms_per_step": 1000.0 * rc_s / args.steps,
                      "note": "reference k-mers of the targets counted once and kept on the device (bk_ref_cache_build), as the "
                              "reference keeps its reference dumps behind marker files (utils.py:157)"}
-        for hh in handles:
+        for hh in run.handles:
             hh.ref_cache_clear()
+        run.packed = saved
 
     # ---- ingest row (SURVEY.md 8.7 f.1): the same steps starting from FASTA/FASTQ FILES (tmpfs) -------------------
     from_files = None
-    if not args.no_ingest_leg:
-        from_files = ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_ranks, n_regions_total, rank)
+    if not args.no_ingest_leg and len(run.packed) == 1:
+        from_files = ingest_leg(args, D, run, total)
 
-    # ---- roofline of the dominant kernel (the assembler) and of the dominant k-mer stage kernel -----
+    # ---- the Python drop-in a BreaKmer user calls (sv_processor.compare_kmers_batch on target objects) -------------
+    dropin = None
+    if not args.no_dropin_leg and D.rank == 0:
+        dropin = dropin_leg(run, D.local_rank)
+
+    # ---- roofline of the dominant kernel (the assembler) and of the k-mer stage kernels -----------------------------
     asm_ms, asm_n = ktimes["assemble"]
     asm_ms_per_launch = asm_ms / max(1, asm_n)
+    out0 = outs[0]
+    n_only0 = int(out0.so_off[-1])
+    NU = int(out0.uniq_reg_off[-1])
+    read_lens = pk0.read_off[1:] - pk0.read_off[:-1]
+    uniq_bases = int(read_lens[out0.uniq_rec].sum()) if NU else 0
+    d2h0 = int(out0.seq.nbytes + out0.kmer_locs.nbytes + out0.indel_only.nbytes + out0.others.nbytes + out0.reads.nbytes +
+               out0.kmer_mer.nbytes + 2 * out0.kmer_pos.nbytes)
     # algorithmic bytes of one assemble launch (DESIGN.md "A-stage"): every unique read once, the sample-only
-    # table (12 B/mer), the posting lists (8 B/entry), and the contigs written
-    NU = int(out.uniq_reg_off[-1])
-    read_lens = pk.read_off[1:] - pk.read_off[:-1]
-    uniq_bases = int(read_lens[out.uniq_rec].sum()) if NU else 0
-    asm_bytes = uniq_bases + 12 * n_only + d2h
+    # table (12 B/mer), and the contigs written
+    asm_bytes = uniq_bases + 12 * n_only0 + d2h0
     asm_gbs = asm_bytes / (asm_ms_per_launch * 1e-3) / 1e9 if asm_ms_per_launch > 0 else 0.0
-    sc_ms, sc_n = ktimes["sort_scatter"]
-    sort_bytes = 2 * 12 * n_sorted       # one pass: keys+values of the sorted (sample) windows read once, written once
-    sort_gbs = sort_bytes / (sc_ms / max(1, sc_n) * 1e-3) / 1e9 if sc_ms > 0 else 0.0
-    cells_per_s = n_cells * kt_steps / (asm_ms * 1e-3) if asm_ms > 0 else 0.0
+    cells0 = int(out0.n_dp_cells)
+    cells_per_s = cells0 * kt_steps / (asm_ms * 1e-3) if asm_ms > 0 else 0.0
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # INT32 ALU-pipe ceiling of the DP: 8 alu-pipe instructions per cell (nw.cuh), 16 lanes/clk/SMSP (B300_MICROARCH.md)
-    int_peak_cells = 148 * 4 * 16 * sm_mhz * 1e6 / 8.0
-    # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1_*.md); only valid for the default workload
-    asm_traffic = 34850560 if (args.workload == "C2" and per_gpu == 500) else None
-    sort_traffic = 191033344 if (args.workload == "C2" and per_gpu == 500) else None
+    alu = int_peak(sm_mhz)
+    # DRAM traffic per launch from the committed ncu --set full captures; only valid for the default workload on one GPU
+    default_shape = args.workload == "C2" and total == 500 and D.world == 1
+    roof_k = kstage_rooflines(ktimes, kt_steps, pk0, out0, hbm_peak)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic", "from_files": from_files,
-        "config": {"workload": desc, "regions_per_gpu": per_gpu, "k": pk.k, "rc_thresh": pk.rc_thresh,
-                   "per_gpu_problem": "every rank runs its own batch of the same %d regions (generator slice %d)" % (per_gpu, args.slice),
-                   "input_bytes_per_gpu": pk.input_bytes, "steps_in_flight": n_fly, "assembler_spec_width": spec_w,
-                   "host_cores_per_rank": cores_per_rank, "host_wait": "blocking" if blocking else "spin",
-                   "l2": ("256 MB buffer written between timed steps (flush)" if n_fly == 1 else
-                          "%d independent batches in flight on separate buffers; the per-step working set (~0.8 GB of "
-                          "key/value, scratch and state arrays) exceeds the 126 MB L2" % n_fly),
-                   "timing": "CUDA events bracketing the K steps (barrier + synchronize on both sides), max over ranks",
-                   "wall_ms_per_step": 1000.0 * wall_s / args.steps,
-                   "sequential_latency_ms_per_step": (min(lat_ms) if lat_ms else None)},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": cfg,
+        "run": {"batches_in_flight": H, "host_threads_per_rank": 1, "calls_per_step_this_rank": len(run.chunks),
+                "regions_per_rank": [len(o) for o in run.owned], "input_bytes_this_rank": sum(pk.input_bytes for pk in run.packed),
+                "assembler_spec_width": args.spec_width or 4, "host_cores_per_rank": max(1, (os.cpu_count() or 1) // max(1, D.world)),
+                "l2": ("256 MB buffer written between timed steps (flush)" if H == 1 else
+                       "%d independent batches in flight on separate buffers; the per-step working set (~1 GB of "
+                       "key/value, scratch and state arrays per batch) exceeds the 126 MB L2" % H),
+                "timing": "CUDA events bracketing the K steps (barrier + synchronize on both sides), max over ranks",
+                "wall_ms_per_step": 1000.0 * wall_s / args.steps,
+                "sequential_latency_ms_per_step": (min(lat_ms) if lat_ms else None), "generate_s": round(run.gen_s, 1),
+                "host_e2e": host_e2e, "host_resident": host_resident},
+        "sharding_check": {"regions": total, "equal_to_single_gpu_run": ok, "result_digest": digest,
+                           "what": "per-region digests (sample-only table + every contig) gathered by target name from all ranks "
+                                   "vs the same regions run on rank 0's GPU alone"},
         "sample_only_kmers_per_s": kmers_per_s,
-        "with_ref_kmer_cache": ref_cache,
-        "per_step": {"contigs": n_contigs, "check_align_calls": n_check, "dp_cells": n_cells,
-                     "kmer_occurrences": n_occ, "sorted_keys": n_sorted, "sample_only_kmers": n_only},
+        "with_ref_kmer_cache": ref_cache, "from_files": from_files, "e2e_dropin": dropin,
+        "per_step": {"contigs": cnt["contigs"], "check_align_calls": cnt["check_align"], "dp_cells": n_cells_rank,
+                     "kmer_occurrences": cnt["kmer_occ"], "sorted_keys": cnt["sorted"], "sample_only_kmers": cnt["sample_only"],
+                     "note": "this rank's share of one step"},
         "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": asm_gbs / hbm_peak, "traffic": asm_traffic, "peak_source": peak_src,
+                     "frac": asm_gbs / hbm_peak, "traffic": 34850560 if default_shape else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": asm_ms_per_launch,
-                     "share_of_step": asm_ms / (1000.0 * sum(lat_ms) / 1000.0) if lat_ms else None,
+                     "share_of_step": asm_ms / sum(lat_ms) if lat_ms else None,
                      "note": "the dominant kernel is an integer-issue/latency bound DP state machine that moves "
                              "O(m+n) bytes per O(m*n) cell updates; its HBM fraction is small by construction, "
-                             "see roofline_alu and roofline_kstage"},
-        "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": int_peak_cells,
-                         "unit": "DP cell updates/s", "frac": cells_per_s / int_peak_cells if int_peak_cells else None,
-                         "achieved_in_flight": n_cells * args.steps / dev_s,
-                         "frac_in_flight": (n_cells * args.steps / dev_s) / int_peak_cells if int_peak_cells else None,
+                             "see roofline_alu (its real ceiling) and roofline_per_kernel (the HBM-bound k-mer stage)"},
+        "roofline_alu": {"kernel": "assemble_kernel", "bound": "int32 issue", "achieved": cells_per_s, "peak": alu["cells_per_s"],
+                         "unit": "DP cell updates/s", "frac": cells_per_s / alu["cells_per_s"],
+                         "achieved_in_flight": cells_all * args.steps / dev_s,
+                         "frac_in_flight": (cells_all * args.steps / dev_s) / (alu["cells_per_s"] * D.world),
                          "note": "`achieved`/`frac`: one launch alone (sequential pass; bounded by the longest region's serial "
-                                 "chain, most SMs idle in the tail); `*_in_flight`: all DP cells of the timed region / its device "
-                                 "time with %d batches in flight (other stages included)" % n_fly,
-                         "peak_source": "148 SM x 4 SMSP x 16 alu lanes/clk x measured sm clock / 8 alu-pipe instructions per cell; "
-                                        "ncu: pipe_alu 48% busy on active SMs, launch bounded by the longest region (profiles/r1_assemble_kernel.md)"},
-        "roofline_kstage": {"kernel": "rs_scatter_kernel", "bound": "hbm", "achieved": sort_gbs, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": sort_gbs / hbm_peak, "traffic": sort_traffic,
-                            "algorithmic_bytes_per_launch": sort_bytes, "launches": sc_n},
+                                 "chain); `*_in_flight`: all DP cells of the timed region / its device time with %d batches in "
+                                 "flight (other stages included), against the peak of all %d GPUs" % (H, D.world),
+                         "peak_source": alu["source"]},
+        "roofline_per_kernel": roof_k,
         "kernel_ms_per_step": {k: round(v[0] / kt_steps, 4) for k, v in ktimes.items() if v[1]},
         "kernel_timing": "sequential pass of %d steps with L2 flush, CUDA events per kernel on the library stream" % kt_steps,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1000.0 * e2e_s / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1000.0 * e2e_s / args.steps, "bytes_note": "this rank's share of one step"},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(args.workload, regions)
-        line["cpu_baseline"]["value_with_c_nw_for_context"] = cpu_c_nw_single(regions)
-    elif rank == 0:
+    regions0 = run.regions
+    run.close()
+    if not args.no_extra_workloads and args.workload == "C2" and not args.regions:
+        line["c5_strong"] = sharded_summary(D, "C5", args.c5_regions, args, max(2, args.steps // 12))
+        line["c3_sharded"] = sharded_summary(D, "C3", 500 * D.world, args, max(2, args.steps // 4))
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(args.workload, regions0)
+        line["cpu_baseline"]["value_with_c_nw_for_context"] = cpu_c_nw_single(regions0)
+    elif D.rank == 0:
         line["cpu_baseline"] = None
-    if rank == 0:
+    if D.rank == 0:
         print(json.dumps(line))
-    for hh in handles:
-        hh.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 
-def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_ranks, n_regions_total, rank):
+def int_peak(sm_mhz):
+    """Ceiling of the DP in cell updates/s.  Measured: profiles/r2_int_peak.json holds the rate at which the DP's own
+    cell update (the instruction sequence of nw.cuh, registers only, no shuffles) issues on a full B200
+    (tools/int_peak.py).  Fallback: the nominal ALU-pipe arithmetic."""
+    p = os.path.join(ROOT, "profiles", "r2_int_peak.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"cells_per_s": float(d["cells_per_s"]) * sm_mhz / float(d["sm_mhz"]),
+                "source": "measured: %s (tools/int_peak.py, profiles/r2_int_peak.json), scaled to the SM clock of this run" % d["what"]}
+    return {"cells_per_s": 148 * 4 * 16 * sm_mhz * 1e6 / 8.0,
+            "source": "nominal: 148 SM x 4 SMSP x 16 alu lanes/clk x SM clock / 8 alu-pipe instructions per cell"}
+
+
+def kstage_rooflines(ktimes, kt_steps, pk, out, hbm_peak):
+    """HBM roofline of every k-mer stage / prep kernel family: algorithmic bytes per step over its
+    CUDA-event time in the sequential pass."""
+    nd = int(pk.read_bases.size); ns = int(pk.sc_bases.size); nr = int(pk.ref_bases.size); nn = int(pk.normal_bases.size)
+    n_sorted = nd + ns
+    n_only = int(out.so_off[-1])
+    NU = int(out.uniq_reg_off[-1])
+    n_rec = len(pk.read_off) - 1
+    alg = {
+        # G1+G2: 1 B/base in (every input; the reference strand counted once), 12 B per sorted window out
+        "kmer_emit": nd + ns + nr + nn + 12 * n_sorted,
+        # G3 by the survey's definition: one read + one write of (key, value) per occurrence, whatever the pass count
+        "sort_count": 8 * n_sorted, "sort_scan": 0, "sort_scatter": 2 * 12 * n_sorted,
+        "run_select": 12 * n_sorted + 8 * n_sorted,        # keys + values in, flag + count out
+        "run_scatter": 12 * n_only + 8 * n_sorted,
+        "scan": 12 * n_sorted,
+        "group_reads": nd + 12 * n_rec + 13 * NU,
+        "index": nd + 24 * NU,
+        "aux_sort": 0,
+        "prep": 16 * out.n_regions,
+    }
+    res = {}
+    whole_sort_ms = 0.0
+    for name, (ms, n) in ktimes.items():
+        if not n or name in ("assemble", "nw_batch"):
+            continue
+        per_step_ms = ms / kt_steps
+        if name in ("sort_count", "sort_scan", "sort_scatter"):
+            whole_sort_ms += per_step_ms
+        b = alg.get(name, 0)
+        gbs = b / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else 0.0
+        res[name] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": n / kt_steps, "algorithmic_bytes_per_step": int(b),
+                     "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4) if b else None}
+    if whole_sort_ms > 0:
+        gbs = 2 * 12 * n_sorted / (whole_sort_ms * 1e-3) / 1e9
+        res["whole_sort"] = {"ms_per_step": round(whole_sort_ms, 4), "algorithmic_bytes_per_step": 2 * 12 * n_sorted,
+                             "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4),
+                             "note": "count + scan + scatter of all passes against one read + one write per occurrence (SURVEY.md 8.5 G3)"}
+    return res
+
+
+def dropin_leg(run, device):
+    """`e2e_dropin`: breakmer_b200.sv_processor.compare_kmers_batch on target objects shaped like the reference's
+    (what a BreaKmer user calls after extract_bam_reads / clean_reads), files in tmpfs, contigs materialised lazily."""
+    import shutil
+    import tempfile
+    from tools import dropin_profile
+    from breakmer_b200 import sv_processor
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    d = tempfile.mkdtemp(prefix="bk_dropin_", dir=root)
+    try:
+        regions = [run.regions[i] for i in run.mine][:500]
+        targets = [dropin_profile.Target(r, d) for r in regions]
+        best = {}
+        for label, kw in (("python_marshalling", dict(ingest="python")), ("native_ingest", dict(ingest="native"))):
+            for rep in range(3):
+                for t in targets:
+                    t.reset()
+                t0 = time.time()
+                sv_processor.compare_kmers_batch(targets, device=device, **kw)
+                dt = time.time() - t0
+                best[label] = min(best.get(label, dt), dt)
+        # touching what resolve_sv reads from every contig (sv_processor.py:731-746): sequence, counts, reads, k-mers
+        t0 = time.time()
+        n_ctg = 0
+        for t in targets:
+            for c in t.kmers["clusters"]:
+                n_ctg += 1
+                c.get_contig_seq(); c.get_contig_counts().get_total_reads(); len(c.reads); len(c.kmers); c.get_kmer_locs()
+        touch_s = time.time() - t0
+        n = len(targets)
+        return {"value": n / best["native_ingest"], "unit": "targets/s", "targets": n, "contigs": n_ctg,
+                "ms_per_batch_native_ingest": 1000.0 * best["native_ingest"],
+                "ms_per_batch_python_marshalling": 1000.0 * best["python_marshalling"],
+                "ms_to_touch_every_contig_field": 1000.0 * touch_s,
+                "what": "sv_processor.compare_kmers_batch(targets) on %d reference-shaped target objects, best of 3" % n}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def ingest_leg(args, D, run, total):
     """Every step = bk_ingest_files (text of the four files of each target -> page-locked arrays, host threads) followed by
-    bk_compare_kmers_batch.  Files live in tmpfs; writing them is not timed.  Python marshalling of the same regions
-    (batch.PackedBatch) is timed beside it for context."""
+    bk_batch_submit / bk_batch_wait.  Files live in tmpfs; writing them is not timed.  Python marshalling of the same
+    regions (batch.PackedBatch) is timed beside it for context."""
     import shutil
     import tempfile
     import torch
     from breakmer_b200 import batch, ingest
+    regions = [run.regions[i] for i in run.mine]
+    pk = run.packed[0]
+    handles = run.handles
+    H = len(handles)
     root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
-    d = tempfile.mkdtemp(prefix="bk_bench_r%d_" % rank, dir=root)
+    d = tempfile.mkdtemp(prefix="bk_bench_r%d_" % D.rank, dir=root)
     try:
         refs, fqs, scs, nms = [], [], [], []
         any_normal = any(r.normal_reads for r in regions)
@@ -516,46 +709,40 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
             refs.append(base + "_ref.fa"); fqs.append(base + "_reads.fastq"); scs.append(base + "_sc.fa")
             nms.append(base + "_normal.fastq" if any_normal else None)
         normal = nms if any_normal else None
-        world = int(os.environ.get("WORLD_SIZE", "1"))
-        cores = max(1, (os.cpu_count() or 1) // world)     # this rank's share of the host
-        per = max(1, cores // n_fly)
-        ings = [ingest.Ingest(n_threads=per) for _ in range(n_fly)]
+        cores = max(1, (os.cpu_count() or 1) // D.world)     # this rank's share of the host
+        ings = [ingest.Ingest(n_threads=cores) for _ in range(H)]   # one parse at a time (single host thread), all cores each
         kw = dict(normal=normal, k=pk.k, rc_thresh=pk.rc_thresh)
-        # parser alone, all cores on one batch
-        solo = ingest.Ingest(n_threads=cores)
+        solo = ings[0]
         solo.files(refs, fqs, scs, **kw)
         t0 = time.time()
         reps = 5
         for _ in range(reps):
             solo.files(refs, fqs, scs, **kw)
         parse_s = (time.time() - t0) / reps
-        solo.close()
         t0 = time.time()
         batch.PackedBatch(regions)
         py_s = time.time() - t0
-        for j, hh in enumerate(handles):
-            batch.run(hh, ings[j].files(refs, fqs, scs, **kw), decode=False)
-        box = {}
 
-        def worker(j):
-            hh = handles[j]
-            if stagger_s:
-                time.sleep(j * stagger_s)
-            for step in range(j, args.steps, n_fly):
-                box[j] = batch.run(hh, ings[j].files(refs, fqs, scs, **kw), decode=False)
+        def one_pass(steps):
+            last = None
+            for t in range(steps):
+                j = t % H
+                if t >= H:
+                    last = batch.wait(handles[j], decode=False)
+                batch.submit(handles[j], ings[j].files(refs, fqs, scs, **kw))
+            for t in range(max(0, steps - H), steps):
+                last = batch.wait(handles[t % H], decode=False)
+            return last
 
-        barrier()
+        one_pass(H)
+        D.barrier()
         t0 = time.time()
-        threads = [threading.Thread(target=worker, args=(j,)) for j in range(n_fly)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        last = one_pass(args.steps)
         torch.cuda.synchronize()
         local = time.time() - t0
-        barrier()
-        ff_s = max_over_ranks(local)
-        n_contigs = int(box[0].n_contigs)
+        D.barrier()
+        ff_s = D.max(local)
+        n_contigs = int(last.n_contigs)
         # contig hand-off (row f.3): the contig.setup files of every contig of one batch result, written to tmpfs
         pk0 = ings[0].files(refs, fqs, scs, **kw)
         res0 = batch.run(handles[0], pk0, decode=False)
@@ -570,7 +757,7 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
         writer.close()
         for g in ings:
             g.close()
-        return {"value": n_regions_total * args.steps / ff_s, "unit": UNIT, "ms_per_step": 1000.0 * ff_s / args.steps,
+        return {"value": total * args.steps / ff_s, "unit": UNIT, "ms_per_step": 1000.0 * ff_s / args.steps,
                 "text_bytes_per_step": n_bytes, "n_contigs": n_contigs,
                 "parse_only": {"ms_per_batch": 1000.0 * parse_s, "regions_per_s": len(regions) / parse_s,
                                "text_MB_per_s": n_bytes / parse_s / 1e6, "host_threads": cores},
@@ -579,7 +766,7 @@ def ingest_leg(args, regions, pk, handles, n_fly, stagger_s, barrier, max_over_r
                             "what": "bk_write_contigs: <id>.fq + <id>.fa per contig and the cluster file per target "
                                     "(sv_processor.py:749-782), tmpfs"},
                 "note": "each step parses the targets' FASTA/FASTQ files (tmpfs) with bk_ingest_files into page-locked memory "
-                        "and calls bk_compare_kmers_batch; %d ingest threads per in-flight batch" % per}
+                        "and runs bk_batch_submit / bk_batch_wait; %d ingest threads, one driving host thread" % cores}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -591,13 +778,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--regions", type=int, default=0, help="override regions per GPU (debugging)")
+    ap.add_argument("--regions", type=int, default=0, help="override the workload's region count (per GPU if weak; debugging)")
     ap.add_argument("--spec-width", type=int, default=0, help="assembler warps per region (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=6, help="independent batches (steps) kept on the device at once")
+    ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) kept on the device at once")
+    ap.add_argument("--c5-regions", type=int, default=20000, help="size of the c5_strong workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
     ap.add_argument("--no-ingest-leg", action="store_true")
-    ap.add_argument("--slice", type=int, default=0, help="which 500-region slice of the generator every rank runs")
+    ap.add_argument("--no-dropin-leg", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="skip the c5_strong / c3_sharded keys")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -23,13 +23,16 @@ _lock = threading.Lock()
 
 
 def get_handle(device=0):
-    """Process-wide handle (one CUDA device + one stream) for `device`."""
+    """The calling THREAD's handle (one CUDA device + one stream) for `device`.  The C ABI requires that calls on one
+    handle never overlap (every call reuses the handle's arenas, and results live there until the next call), and ctypes
+    releases the GIL during a call, so handles are never shared between threads."""
     from . import _lib
+    key = (device, threading.get_ident())
     with _lock:
-        h = _handles.get(device)
+        h = _handles.get(key)
         if h is None:
             h = _lib.Handle(device)
-            _handles[device] = h
+            _handles[key] = h
         return h
 
 

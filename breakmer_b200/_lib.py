@@ -58,6 +58,7 @@ class BatchResult(Structure):
         ("gpu_ms", c_double),
         ("n_sorted_keys", c_int64),
         ("region_dp_cells", POINTER(c_int64)),
+        ("host_wait_ms", c_double), ("host_post_ms", c_double),
     ]
 
 

@@ -292,6 +292,7 @@ struct NwResident {
   const int64_t* seq_off = nullptr;
   uint2* lastcol = nullptr;
   int2* edge = nullptr;
+  uint8_t* tab = nullptr;
 };
 
 // Body of bk_nw_batch.  keep == nullptr: a self-contained call (arenas reset, everything uploaded).
@@ -340,7 +341,9 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
     P.out = h->dev.get<int32_t>(n_pairs * 10);
     int64_t want_blocks = (n_pairs + NWB_WARPS - 1) / NWB_WARPS;
     const int grid = (int)std::min<int64_t>(want_blocks, (int64_t)h->sm_count * 8);
+    const bool use_tab = !want_aln && !getenv("BK_NW_PACKED");      // score pass + traceback (nw.cuh) where its table fits
     if (!keep) {
+      if (use_tab) P.tab = h->dev.get<uint8_t>((size_t)grid * NWB_WARPS * NW_TAB_BYTES);
       if (max_m > 256) {
         P.edge_stride = NW_MAX_LEN + 1;
         P.edge = h->dev.get<int2>((size_t)grid * NWB_WARPS * 2 * P.edge_stride);
@@ -355,7 +358,9 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
         keep->seq_off = P.seq_off;
         keep->edge = longest > 256 ? h->dev.get<int2>(warps * 2 * (NW_MAX_LEN + 1)) : nullptr;
         keep->lastcol = h->dev.get<uint2>(warps * (NW_MAX_LEN / 2 + 1));
+        keep->tab = use_tab ? h->dev.get<uint8_t>(warps * NW_TAB_BYTES) : nullptr;
       }
+      P.tab = keep->tab;
       if (max_m > 256) {
         P.edge_stride = NW_MAX_LEN + 1;
         P.edge = keep->edge;

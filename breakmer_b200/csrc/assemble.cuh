@@ -121,6 +121,7 @@ struct AsmParams {
   int32_t* w_diff;                 // ASM_CAP + 1
   int2* w_edge;                    // 2 * ASM_CAP int2, or null if no read is longer than 256
   uint2* w_lastcol;                // ASM_LASTCOL uint2 per warp: last DP column of the sweep in flight (nw.cuh)
+  uint8_t* w_tab;                  // NW_TAB_BYTES per warp: low bytes of the score table of the sweep in flight (nw.cuh)
   // work distribution
   int* work_counter;
   const int32_t* work_order;       // regions, most expensive first
@@ -199,6 +200,7 @@ struct RegionCtx {
   int cur_e;                      // grow: entry of the snapshot being committed
   int2* edge_all;                 // ASM_SPEC_W x (2 * ASM_CAP) int2 or null
   uint2* lastcol;                 // warp 0's last-column scratch
+  uint8_t* tab;                   // warp 0's score-table scratch
   // contig under construction
   uint8_t* cseq; int c0, clen;
   int32_t* cnt_buf; int cur, k0, klen;
@@ -505,7 +507,7 @@ BK_DEV void spec_stage(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, int
   syncwarp();
 }
 BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, int read_cap, const uint8_t* s_contig, const uint8_t* s_pred, int w,
-                    int2* edge, uint2* lastcol) {
+                    int2* edge, uint2* lastcol, uint8_t* tab) {
   const uint8_t* rd = s_reads + (size_t)w * read_cap;
   const int lr = sp->lr[w];
   const int b = sp->abuf[w];
@@ -513,7 +515,7 @@ BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, int read_cap, const 
   const int lc = sp->la[w];
   NwDual r;
   // columns = read, rows = contig: dev-frame A = nw(read, contig) = v2, B = nw(contig, read) = v1
-  nw_dual_dispatch(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, lastcol, r);
+  nw_dual_dispatch<true>(rd, lr, ct, lc, edge, edge ? edge + ASM_CAP : nullptr, lastcol, tab, r);
   if (lane() == 0) { sp->v1[w] = r.b; sp->v2[w] = r.a; }
   syncwarp();
 }
@@ -625,10 +627,10 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
   }
   // 3. every warp aligns its read against its contig
 #ifdef BK_SIM
-  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, w, nullptr, nullptr);
+  for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, w, nullptr, nullptr, nullptr);
 #else
   if (multi) __syncthreads();
-  spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol);
+  spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol, c.tab);
   if (multi) __syncthreads();
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
@@ -1144,6 +1146,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.diff = P.w_diff + slot * (ASM_CAP + 1);
   c.edge_all = P.w_edge ? P.w_edge + slot * spec_w * 2 * ASM_CAP : nullptr;
   c.lastcol = P.w_lastcol ? P.w_lastcol + (size_t)slot * spec_w * ASM_LASTCOL : nullptr;
+  c.tab = P.w_tab ? P.w_tab + (size_t)slot * spec_w * NW_TAB_BYTES : nullptr;
   c.edge = c.edge_all;
   c.s_reads = s_reads; c.s_read = s_reads; c.s_contig = s_contig; c.sp = sp;
   c.st_n = 0; c.rnd_base = 0; c.rnd_cnt = 0; c.seq_ver = 0;
@@ -1170,8 +1173,9 @@ inline size_t assemble_smem_bytes(int W, int read_cap) {
          ((sizeof(SpecShared) + 15) & ~size_t(15));
 }
 
-template <int W>
-__global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : ASM_W1_CTAS)))) assemble_kernel(AsmParams P) {
+// CTAS = resident CTAs per SM the register allocation is bounded for (0: the default of the width)
+template <int W, int CTAS = 0>
+__global__ void __launch_bounds__(32 * W, (CTAS > 0 ? CTAS : (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : ASM_W1_CTAS))))) assemble_kernel(AsmParams P) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* s_reads = smem_raw;
   uint8_t* s_contig = s_reads + (size_t)W * P.read_cap;
@@ -1183,6 +1187,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
   if (W > 1 && warp > 0) {
     int2* edge = P.w_edge ? P.w_edge + (slot * W + warp) * 2 * ASM_CAP : nullptr;
     uint2* lastcol = P.w_lastcol + (size_t)(slot * W + warp) * ASM_LASTCOL;
+    uint8_t* tab = P.w_tab ? P.w_tab + (size_t)(slot * W + warp) * NW_TAB_BYTES : nullptr;
     for (;;) {
       __syncthreads();                                 // command published
       const int n = sp.n;
@@ -1190,7 +1195,7 @@ __global__ void __launch_bounds__(32 * W, (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : 
       if (warp < n) spec_stage(P, &sp, s_reads, warp);
       __syncthreads();                                 // reads staged; warp 0 predicts
       __syncthreads();                                 // predictions published
-      if (warp < n) spec_dp(&sp, s_reads, P.read_cap, s_contig, s_pred, warp, edge, lastcol);
+      if (warp < n) spec_dp(&sp, s_reads, P.read_cap, s_contig, s_pred, warp, edge, lastcol, tab);
       __syncthreads();                                 // results published
     }
   }

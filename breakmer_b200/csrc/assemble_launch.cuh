@@ -9,5 +9,7 @@ struct AsmParams;
 cudaError_t launch_assemble_w1(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
 cudaError_t launch_assemble_w2(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
 cudaError_t launch_assemble_w4(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
+cudaError_t launch_assemble_w4c4(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
+cudaError_t launch_assemble_w4c5(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
 cudaError_t launch_assemble_w8(const AsmParams& A, int grid, int dyn_smem, int carveout, cudaStream_t st);
 }  // namespace bk

@@ -44,6 +44,7 @@ struct NwDual {
   NwOut b;   // nw(rowseq, colseq)
 };
 
+constexpr int NW_TAB_BYTES = 160 * 1024;   // per-warp score-table scratch of the score pass + traceback (below)
 constexpr int NW_SHIFT = 18;
 constexpr int NW_BIAS = 32768;
 constexpr int NW_TAG_CLEAR = ~(3 << 16);
@@ -126,7 +127,9 @@ template <int C>
 inline void nw_dual_warp_fast(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, NwDual& out) {
   nw_dual_warp<C, false>(cs, m, rs, n, e0, e1, nullptr, out);
 }
-inline void nw_dual_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, uint2* /*lastcol*/, NwDual& out) {
+template <bool LAZY = false>
+inline void nw_dual_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1, uint2* /*lastcol*/,
+                             uint8_t* /*tab*/, NwDual& out) {
   nw_dual_warp<4, false>(cs, m, rs, n, e0, e1, nullptr, out);
 }
 #else
@@ -415,11 +418,271 @@ __device__ __forceinline__ void nw_dual_warp_fast(const uint8_t* __restrict__ cs
   nw_decode_a(best_a, best_ai, m, out.a);
   nw_decode_b(best_b, best_bj, n, out.b);
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Score pass + warp-parallel traceback (the path almost every alignment of the assembler takes).
+//
+// The packed cell above spends 8 ALU-pipe instructions per cell because both directions carry their traceback origin
+// through EVERY cell.  But the two directions share one score table (observation 1), and the origin is only needed
+// for two cells: the two end cells.  So:
+//
+//   pass 1  computes the score table ONCE, tag-free, in the shifted form  T[i][j] = score[i][j] + 2 (i + j):
+//             diagonal move   T[i-1][j-1] + (match ? 5 : 2)        (+1 / -2, plus the shift of 4)
+//             either gap move T[i][j-1], T[i-1][j] unchanged       (-2, plus the shift of 2)
+//           i.e. one add and one three-way max (VIMNMX3) per cell; T is non-negative, non-decreasing along rows and
+//           columns and differs by at most 5 between neighbours.  The low byte of every T goes to a per-warp scratch
+//           table (L2 resident), laid out by (step, lane) so that each lane's two rows x C columns of a step are one
+//           8- or 16-byte store and a warp's stores are contiguous.
+//   ends    direction A: the last column (kept in full by the lane that owns column m, as before), largest row on
+//           ties; direction B: the last row, largest column on ties (olc.py:79-83 with its `>=`).
+//   pass 2  walks the two tracebacks (olc.py:90-105) from the end cells.  The pointer of a cell is recomputed from
+//           the table: 3 iff T == T_diag + c, else -- direction A -- 2 iff T == T[i][j-1], else 1; direction B is the
+//           transpose, so its second choice is T[i-1][j].  Neighbour differences are < 256, so the low bytes decide
+//           these equalities exactly.  Alignments are long diagonal runs: the 32 lanes test the next 32 cells of the
+//           diagonal at once and the walk jumps to the first cell that is not a diagonal step, so a traceback costs
+//           a handful of warp iterations instead of one step per base.
+//
+// Results are identical to nw_dual_warp_fast (tests/test_gpu_nw.py runs both paths against the reference's outputs).
+// Limits: one column block (m <= 32 C) and (rows / 2 + 32) * 64 C bytes of table <= NW_TAB_BYTES; anything else takes
+// the packed-cell kernel above.
+
+template <int C>
+__device__ __forceinline__ bool nw_trace_fits(int m, int n) {
+  return m <= 32 * C && (size_t)(((n + 1) >> 1) + 32) * 64 * C <= (size_t)NW_TAB_BYTES;
+}
+
+// byte offset of cell (i, j), i >= 1, j >= 1, in the (step, lane) table layout
+template <int C>
+__device__ __forceinline__ unsigned nw_tab_off(int i, int j) {
+  const unsigned Lc = (unsigned)(j - 1) / C, c = (unsigned)(j - 1) % C;
+  const unsigned q = (unsigned)(i - 1) >> 1, r = (unsigned)(i - 1) & 1u;
+  return (((q + Lc) * 32u + Lc) * 2u + r) * C + c;
+}
+// low byte of T at (i, j), boundary included (T[0][j] = 2 j, T[i][0] = 2 i)
+// (branch-free: the load is always issued, from a clamped in-table address, so that the loads of one traceback
+// iteration overlap instead of waiting for each other behind divergent branches)
+template <int C>
+__device__ __forceinline__ unsigned nw_tab_get(const uint8_t* __restrict__ tab, int i, int j) {
+  const bool inside = i >= 1 && j >= 1;
+  const unsigned v = (unsigned)__ldcg(tab + (inside ? nw_tab_off<C>(i, j) : 0u));
+  const unsigned edge = (unsigned)(2 * (i + j)) & 255u;          // T[0][j] = 2 j, T[i][0] = 2 i
+  return inside ? v : edge;
+}
+
+// The traceback(s) of pass 2.  Walks direction A from (ia, ja) and / or direction B from (ib, jb) to the boundary; on
+// return the coordinates are the traceback origins.  Both walks share the loop (their table loads overlap).
+template <int C>
+__device__ __forceinline__ void nw_trace_walk(const uint8_t* __restrict__ cs, const uint8_t* __restrict__ rs,
+                                              const uint8_t* __restrict__ tab, bool goA, bool goB, int& ia, int& ja, int& ib, int& jb) {
+  const unsigned FULL = 0xffffffffu;
+  const int L = lane();
+  while (goA || goB) {
+    bool ndA = true, hA = false, ndB = true, vB = false;
+    {
+      // cells (i - L, j - L) of both walks; lanes past the boundary (and a walk that is over) read clamped cells
+      const int ai = ia - L, aj = ja - L, bi = ib - L, bj = jb - L;
+      const bool okA = goA && ai >= 1 && aj >= 1, okB = goB && bi >= 1 && bj >= 1;
+      const int ai1 = okA ? ai : 1, aj1 = okA ? aj : 1, bi1 = okB ? bi : 1, bj1 = okB ? bj : 1;
+      const unsigned tcA = nw_tab_get<C>(tab, ai1, aj1), tdA = nw_tab_get<C>(tab, ai1 - 1, aj1 - 1), thA = nw_tab_get<C>(tab, ai1, aj1 - 1);
+      const unsigned tcB = nw_tab_get<C>(tab, bi1, bj1), tdB = nw_tab_get<C>(tab, bi1 - 1, bj1 - 1), tvB = nw_tab_get<C>(tab, bi1 - 1, bj1);
+      const unsigned cA = (cs[aj1 - 1] == rs[ai1 - 1]) ? 5u : 2u, cB = (cs[bj1 - 1] == rs[bi1 - 1]) ? 5u : 2u;
+      if (okA) { ndA = ((tcA - tdA - cA) & 255u) != 0u; hA = ((tcA - thA) & 255u) == 0u; }
+      if (okB) { ndB = ((tcB - tdB - cB) & 255u) != 0u; vB = ((tcB - tvB) & 255u) == 0u; }
+    }
+    if (goA) {
+      const unsigned mk = __ballot_sync(FULL, ndA);
+      const int run = mk ? __ffs((int)mk) - 1 : 32;
+      ia -= run; ja -= run;
+      if (ia == 0 || ja == 0) goA = false;
+      else if (run < 32) {
+        if (__shfl_sync(FULL, (int)hA, run)) ja -= 1; else ia -= 1;      // pointer 2: score[i][j-1]; pointer 1: score[i-1][j]
+        if (ia == 0 || ja == 0) goA = false;
+      }
+    }
+    if (goB) {
+      const unsigned mk = __ballot_sync(FULL, ndB);
+      const int run = mk ? __ffs((int)mk) - 1 : 32;
+      ib -= run; jb -= run;
+      if (ib == 0 || jb == 0) goB = false;
+      else if (run < 32) {
+        if (__shfl_sync(FULL, (int)vB, run)) ib -= 1; else jb -= 1;      // transposed: its pointer 2 is the vertical neighbour
+        if (ib == 0 || jb == 0) goB = false;
+      }
+    }
+  }
+}
+
+// LAZY: the caller is contig.check_align (sv_assembly.py:449-504), which reads a direction's traceback origin only
+//   - for the higher-scoring direction, unless its score already fails `score < min_len / 4` (:459-460);
+//   - for the other direction only if the first one fails the identity test (:461-464) or the scores tie.
+// The direction that is not read is typically the one in which the read overhangs the contig: a low-scoring path of
+// dozens of single gap steps, i.e. dozens of dependent table look-ups.  Its origin is left at the end cell.
+#ifdef BK_NW_PROF
+__device__ long long bk_nw_prof[8];
+#define BK_NW_T(i) if (lane() == 0) bk_nw_prof[i] = clock64();
+#else
+#define BK_NW_T(i)
+#endif
+template <int C, int OWN_C, bool LAZY>
+__device__ __forceinline__ void nw_dual_trace(const uint8_t* __restrict__ cs, int m, const uint8_t* __restrict__ rs, int n,
+                                              uint2* __restrict__ lastcol, uint8_t* __restrict__ tab, NwDual& out) {
+  const unsigned FULL = 0xffffffffu;
+  const int L = lane();
+  const int hn = (n + 1) >> 1;                  // row pairs
+  const int jfirst = L * C + 1;                 // 1-based column held in slot 0
+  const int steps = hn + (m + C - 1) / C - 1;   // the sweep ends when the last lane with a real column has done the last pair
+  int col[C], r0[C], ch[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = jfirst + c;
+    col[c] = 2 * j;                             // row 0: score 0
+    r0[c] = 0;
+    ch[c] = (j <= m) ? (int)cs[j - 1] : 0x100;
+  }
+  int diag = 2 * (jfirst - 1);
+  int last0 = 0, last1 = col[C - 1];
+  const bool own = L == (m - 1) / C;
+  int rc0_next = rs[0], rc1_next = rs[1];
+  BK_NW_T(0)
+  // ---- pass 1: scores ----
+  for (int t = 0; t < steps; ++t) {
+    int h0 = __shfl_up_sync(FULL, last0, 1);
+    int h1 = __shfl_up_sync(FULL, last1, 1);
+    const int q = t - L;
+    const bool active = (unsigned)q < (unsigned)hn;
+    if (L == 0) { h0 = 4 * q + 2; h1 = 4 * q + 4; }          // column 0: T[i][0] = 2 i, rows 2q+1 and 2q+2
+    if (active) {
+      const int rc0 = rc0_next, rc1 = rc1_next;
+      {
+        int nx = 2 * q + 2;                                    // row i0 + 2 (0-based index in rs), clamped in bounds
+        nx = nx > NW_MAX_LEN - 2 ? NW_MAX_LEN - 2 : nx;
+        rc0_next = rs[nx]; rc1_next = rs[nx + 1];
+      }
+      {
+        int d = diag, h = h0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int v = col[c];
+          const int tt = __vimax3_s32(d + ((ch[c] == rc0) ? 5 : 2), h, v);
+          d = v; h = tt; r0[c] = tt;
+        }
+      }
+      {
+        int d = h0, h = h1;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int v = r0[c];
+          const int tt = __vimax3_s32(d + ((ch[c] == rc1) ? 5 : 2), h, v);
+          d = v; h = tt; col[c] = tt;
+        }
+      }
+      diag = h1;
+      last0 = r0[C - 1]; last1 = col[C - 1];
+      if (own) lastcol[q] = make_uint2((unsigned)r0[OWN_C], (unsigned)col[OWN_C]);
+      // low bytes of the 2 x C cells of this step -> table[(t, L)]
+      if (C == 4) {
+        const unsigned w0 = __byte_perm(__byte_perm(r0[0], r0[1], 0x0040), __byte_perm(r0[2], r0[3], 0x0040), 0x5410);
+        const unsigned w1 = __byte_perm(__byte_perm(col[0], col[1], 0x0040), __byte_perm(col[2], col[3], 0x0040), 0x5410);
+        reinterpret_cast<uint2*>(tab)[t * 32 + L] = make_uint2(w0, w1);
+      } else {
+        unsigned w[4];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          w[g] = __byte_perm(__byte_perm(r0[4 * g], r0[4 * g + 1], 0x0040), __byte_perm(r0[4 * g + 2], r0[4 * g + 3], 0x0040), 0x5410);
+          w[2 + g] = __byte_perm(__byte_perm(col[4 * g], col[4 * g + 1], 0x0040), __byte_perm(col[4 * g + 2], col[4 * g + 3], 0x0040), 0x5410);
+        }
+        reinterpret_cast<uint4*>(tab)[t * 32 + L] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  BK_NW_T(1)
+  // ---- end cells ----
+  // direction B: last row n (the lane's first row if n is odd, its second if n is even); key = T - 2 j = score + 2 n
+  int best_b = 2 * n, best_bj = 0;              // score[n][0] = 0
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int j = jfirst + c;
+    const int v = ((n & 1) ? r0[c] : col[c]) - 2 * j;
+    if (j <= m && v >= best_b) { best_b = v; best_bj = j; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int ov = __shfl_xor_sync(FULL, best_b, off);
+    const int oj = __shfl_xor_sync(FULL, best_bj, off);
+    if (ov > best_b || (ov == best_b && oj > best_bj)) { best_b = ov; best_bj = oj; }
+  }
+  __syncwarp();                                  // lastcol / table stores of all lanes are visible to the warp
+  // direction A: last column m; key = T - 2 i = score + 2 m; rows ascending, >= keeps the largest row
+  int best_a, best_ai;
+  {
+    const int per = (hn + 31) >> 5;
+    const int q0 = L * per, q1 = (q0 + per) < hn ? (q0 + per) : hn;
+    int ba = (L == 0) ? 2 * m : (int)0x80000000, bi = (L == 0) ? 0 : -1;
+    for (int q = q0; q < q1; ++q) {
+      const uint2 v = lastcol[q];
+      const int i0 = 2 * q + 1;
+      const int k0 = (int)v.x - 2 * i0, k1 = (int)v.y - 2 * (i0 + 1);
+      if (k0 >= ba) { ba = k0; bi = i0; }
+      if (i0 + 1 <= n && k1 >= ba) { ba = k1; bi = i0 + 1; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const int ov = __shfl_xor_sync(FULL, ba, off);
+      const int oi = __shfl_xor_sync(FULL, bi, off);
+      if (ov > ba || (ov == ba && oi > bi)) { ba = ov; bi = oi; }
+    }
+    best_a = ba; best_ai = bi;
+  }
+  out.a.prej = m; out.a.prei = best_ai; out.a.score = best_a - 2 * m;
+  out.b.prej = n; out.b.prei = best_bj; out.b.score = best_b - 2 * n;
+  BK_NW_T(2)
+  // ---- pass 2: traceback(s) ----
+  int ia = best_ai, ja = m, ib = n, jb = best_bj;
+  bool goA = best_ai > 0, goB = best_bj > 0;
+  if (!goA) { ja = m - 1; }                      // pointer[0][m] == 2: one step left (olc.py:58-59, 96-99)
+  if (!goB) { ib = n - 1; }                      // same in the transposed problem
+  if (LAZY) {
+    const int sA = out.a.score, sB = out.b.score, mn = m < n ? m : n;
+    const bool lowA = 4 * sA < mn, lowB = 4 * sB < mn;          // `score < min_len / 4`: fails whatever the span is
+    if (sA != sB) {
+      const bool firstA = sA > sB;
+      if (firstA ? lowA : lowB) {
+        goA = false; goB = false;                                // both directions fail on their scores alone
+      } else {
+        const bool g1A = goA && firstA, g1B = goB && !firstA;
+        nw_trace_walk<C>(cs, rs, tab, g1A, g1B, ia, ja, ib, jb);
+        // identity test of the first direction (:461-464, integer form Q27); the other one is read only if it fails
+        const int span = firstA ? (m - ja) : (n - ib);
+        const int s1 = firstA ? sA : sB;
+        const bool bad1 = 200 * s1 < 179 * span;
+        if (firstA) goA = false; else goB = false;
+        if (!bad1 || (firstA ? lowB : lowA)) { goA = false; goB = false; }
+      }
+    } else if (lowA) {
+      goA = false; goB = false;
+    }
+  }
+  nw_trace_walk<C>(cs, rs, tab, goA, goB, ia, ja, ib, jb);
+  out.a.j0 = ja; out.a.i0 = ia;                  // start in colseq (seq1 of A), start in rowseq
+  out.b.j0 = ib; out.b.i0 = jb;                  // B: seq1 is rowseq
+  __syncwarp();
+  BK_NW_T(3)
+}
+
 // dispatch on the read length: 4 columns per lane up to 128 bases (with the last-column
-// slot resolved at compile time), 8 beyond
+// slot resolved at compile time), 8 beyond; the score pass + traceback when its table fits
+template <bool LAZY = false>
 __device__ __forceinline__ void nw_dual_dispatch(const uint8_t* __restrict__ cs, int m, const uint8_t* __restrict__ rs, int n,
-                                                 int2* e0, int2* e1, uint2* lastcol, NwDual& out) {
+                                                 int2* e0, int2* e1, uint2* lastcol, uint8_t* tab, NwDual& out) {
   if (m <= 128) {
+    if (tab && nw_trace_fits<4>(m, n)) {
+      switch ((m - 1) & 3) {
+        case 0: nw_dual_trace<4, 0, LAZY>(cs, m, rs, n, lastcol, tab, out); break;
+        case 1: nw_dual_trace<4, 1, LAZY>(cs, m, rs, n, lastcol, tab, out); break;
+        case 2: nw_dual_trace<4, 2, LAZY>(cs, m, rs, n, lastcol, tab, out); break;
+        default: nw_dual_trace<4, 3, LAZY>(cs, m, rs, n, lastcol, tab, out); break;
+      }
+      return;
+    }
     switch ((m - 1) & 3) {
       case 0: nw_dual_warp_fast<4, 0>(cs, m, rs, n, e0, e1, lastcol, out); break;
       case 1: nw_dual_warp_fast<4, 1>(cs, m, rs, n, e0, e1, lastcol, out); break;

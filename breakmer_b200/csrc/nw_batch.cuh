@@ -22,6 +22,7 @@ struct NwBatchParams {
   int2* edge;                 // per warp 2 * edge_stride int2, or null when no seq1 is longer than 256
   int edge_stride;
   uint2* lastcol;             // per warp NW_MAX_LEN / 2 + 1 uint2 (last DP column of the sweep in flight)
+  uint8_t* tab;               // per warp NW_TAB_BYTES (score-table scratch of the score pass + traceback), or null
   int want_aln;
   uint8_t* ptr_scratch;       // sum (n+1)(m+1) bytes
   const int64_t* ptr_off;     // n_pairs
@@ -33,12 +34,12 @@ struct NwBatchParams {
 
 template <bool PTR>
 __device__ __forceinline__ void nw_dispatch(const uint8_t* cs, int m, const uint8_t* rs, int n, int2* e0, int2* e1,
-                                            uint2* lastcol, uint8_t* ptrmat, NwDual& out) {
+                                            uint2* lastcol, uint8_t* tab, uint8_t* ptrmat, NwDual& out) {
   if (PTR) {
     if (m <= 128) nw_dual_warp<4, true>(cs, m, rs, n, e0, e1, ptrmat, out);
     else nw_dual_warp<8, true>(cs, m, rs, n, e0, e1, ptrmat, out);
   } else {
-    nw_dual_dispatch(cs, m, rs, n, e0, e1, lastcol, out);
+    nw_dual_dispatch(cs, m, rs, n, e0, e1, lastcol, tab, out);
   }
 }
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
   int2* e0 = p.edge ? p.edge + (size_t)gw * 2 * p.edge_stride : nullptr;
   int2* e1 = p.edge ? e0 + p.edge_stride : nullptr;
   uint2* lastcol = p.lastcol + (size_t)gw * (NW_MAX_LEN / 2 + 1);
+  uint8_t* tab = p.tab ? p.tab + (size_t)gw * NW_TAB_BYTES : nullptr;
   for (int64_t pi = gw; pi < p.n_pairs; pi += nw_total) {
     const int ia = p.pair_a[pi], ib = p.pair_b[pi];
     const int64_t oa = p.seq_off[ia], ob = p.seq_off[ib];
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
       for (int i = L; i <= n; i += 32) pm[(size_t)i * (m + 1)] = 1;      // olc.py:56-57
       for (int j = L; j <= m; j += 32) pm[j] = 2;                         // olc.py:58-59
       __syncwarp();
-      nw_dispatch<true>(s1, m, s2, n, e0, e1, lastcol, pm, r);
+      nw_dispatch<true>(s1, m, s2, n, e0, e1, lastcol, nullptr, pm, r);
       __syncwarp();
       if (L == 0) {                                                       // olc.py:86-105
         int i = r.a.prei, j = m, len = 0;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
         p.aln_len[pi] = len;       // strings are stored reversed; the host shim flips them
       }
     } else {
-      nw_dispatch<false>(s1, m, s2, n, e0, e1, lastcol, nullptr, r);
+      nw_dispatch<false>(s1, m, s2, n, e0, e1, lastcol, tab, nullptr, r);
     }
     if (L == 0) {
       int32_t* o = p.out + pi * 10;

@@ -16,6 +16,8 @@
 // therefore only enqueues (copies + ~60 launches) and returns; wait() blocks once for the counters, checks the output
 // arena, copies the results and blocks a second time.  One host thread can keep several handles (streams) busy.
 #pragma once
+#include <chrono>
+
 #include "pipeline.cuh"
 
 namespace {
@@ -264,6 +266,8 @@ void launch_assembly(bk_handle_t h, PendingBatch& B) {
     if (const char* e = getenv("BK_ASM_CARVEOUT")) carve = atoi(e);
     carve = std::min(100, std::max(0, carve));
     if (B.spec_w == 8) BK_CUDA(launch_assemble_w8(A, B.grid, B.dyn_smem, carve, st));
+    else if (B.spec_w == 4 && B.ctas_per_sm >= 5) BK_CUDA(launch_assemble_w4c5(A, B.grid, B.dyn_smem, carve, st));
+    else if (B.spec_w == 4 && B.ctas_per_sm == 4) BK_CUDA(launch_assemble_w4c4(A, B.grid, B.dyn_smem, carve, st));
     else if (B.spec_w == 4) BK_CUDA(launch_assemble_w4(A, B.grid, B.dyn_smem, carve, st));
     else if (B.spec_w == 2) BK_CUDA(launch_assemble_w2(A, B.grid, B.dyn_smem, carve, st));
     else BK_CUDA(launch_assemble_w1(A, B.grid, B.dyn_smem, carve, st));
@@ -487,6 +491,7 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
   A.w_diff = h->dev.get<int32_t>((size_t)grid * (ASM_CAP + 1));
   A.w_edge = p.max_read_len > 256 ? h->dev.get<int2>((size_t)grid * spec_w * 2 * ASM_CAP) : nullptr;
   A.w_lastcol = h->dev.get<uint2>((size_t)grid * spec_w * ASM_LASTCOL);
+  A.w_tab = getenv("BK_NW_PACKED") ? nullptr : h->dev.get<uint8_t>((size_t)grid * spec_w * NW_TAB_BYTES);   // (env: the packed-cell DP everywhere, for A/B runs)
   A.region_status = h->dev.get<int32_t>(R ? R : 1);
   A.region_ncontigs = h->dev.get<int32_t>(R ? R : 1);
   A.region_cells = h->dev.get<unsigned long long>(R ? R : 1);
@@ -534,8 +539,16 @@ void pipeline_wait(bk_handle_t h, bk_batch_result* out) {
   out->n_regions = R;
   out->n_kmer_occurrences = B.n_keys;
   out->n_sorted_keys = B.n_sorted;
+  const auto t_enter = std::chrono::steady_clock::now();
+  double blocked_ms = 0;
+  auto timed_wait = [&] {
+    const auto a = std::chrono::steady_clock::now();
+    const cudaError_t e = stream_wait(h);
+    blocked_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    return e;
+  };
   for (int attempt = 0;; ++attempt) {
-    BK_CUDA(stream_wait(h));                               // first wait: counters of the whole pass
+    BK_CUDA(timed_wait());                                 // first wait: counters of the whole pass
     const bool overflow = B.h_cursor[0] > A.cap_seq || B.h_cursor[1] > A.cap_cnt || B.h_cursor[2] > A.cap_reads ||
                           B.h_cursor[3] > A.cap_kmers || B.h_cursor[4] > A.cap_ctg;
     if (!overflow) break;
@@ -570,7 +583,7 @@ void pipeline_wait(bk_handle_t h, bk_batch_result* out) {
   out->ctg_kmer_pos = to_host(h, A.o_kmer_pos, (size_t)h_cursor[3]);
   const int32_t* h_meta = to_host(h, A.o_kmer_meta, (size_t)h_cursor[3]);
   BK_CUDA(cudaEventRecord(h->ev1, st));
-  BK_CUDA(stream_wait(h));                                 // second wait: the result arrays
+  BK_CUDA(timed_wait());                                   // second wait: the result arrays
   float ms = 0;
   BK_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->gpu_ms = ms;
@@ -608,6 +621,13 @@ void pipeline_wait(bk_handle_t h, bk_batch_result* out) {
     lth[e] = h_meta[e] & 1; ord[e] = (h_meta[e] >> 1) & 3; dist[e] = h_meta[e] >> 3;
   }
   out->ctg_kmer_lth = lth; out->ctg_kmer_dist = dist; out->ctg_kmer_order = ord;
+  struct HostTimes {                                       // filled on every normal exit
+    bk_batch_result* out; std::chrono::steady_clock::time_point t0; double* blocked;
+    ~HostTimes() {
+      const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      out->host_wait_ms = *blocked; out->host_post_ms = total - *blocked;
+    }
+  } host_times{out, t_enter, &blocked_ms};
   if (!p.region_skipped.empty()) {
     // regions that were left out: report them, and give record indices in the caller's numbering again
     for (int r = 0; r < R; ++r) {

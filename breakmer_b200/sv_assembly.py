@@ -48,19 +48,79 @@ class assembly_seq:
         self.counts = counts
 
 
+class _lazy(object):
+    """Non-data descriptor: computes the attribute on first read and stores it on the instance (so it can also be
+    assigned like a plain attribute, which the reference's downstream code is free to do)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.name = fn.__name__
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            return self
+        v = obj.__dict__[self.name] = self.fn(obj)
+        return v
+
+
 class contig:
-    def __init__(self, rec, reads, kmer_len):
-        self.reads = set(reads)
-        self.aseq = assembly_seq(rec["seq"], assembly_counts(rec["indel_only"], rec["others"]))
-        self.kmer_locs = list(rec["kmer_locs"])
-        self.kmers = [tuple(t) for t in rec["kmers"]]
+    """What the rest of BreaKmer reads from an sv_assembly.contig.  The Python lists, tuples and
+    fq_read objects are built from the batch's result arrays on FIRST ACCESS of each attribute: resolve_sv touches few of
+    them per contig, and building all of them eagerly costs 12x the device time of the batch."""
+
+    def __init__(self, out, cidx, objs, kmer_len, rec=None):
+        self._out = out
+        self._c = int(cidx)
+        self._objs = objs
         self.kmer_len = kmer_len
         self.setup = True
+        if rec is not None:                                       # eager construction from a decoded record
+            self.__dict__["reads"] = set(objs)
+            self.__dict__["aseq"] = assembly_seq(rec["seq"], assembly_counts(rec["indel_only"], rec["others"]))
+            self.__dict__["kmer_locs"] = list(rec["kmer_locs"])
+            self.__dict__["kmers"] = [tuple(t) for t in rec["kmers"]]
+
+    @_lazy
+    def reads(self):
+        o = self._out
+        ro, nr = o.reads_off[self._c]
+        objs = self._objs
+        return set(objs[int(r)] for r in o.reads[ro:ro + nr])
+
+    @_lazy
+    def aseq(self):
+        o = self._out
+        so, sl = o.seq_off[self._c]
+        co, cl = o.cnt_off[self._c]
+        return assembly_seq(o.seq[so:so + sl].tobytes().decode(),
+                            assembly_counts(o.indel_only[co:co + cl].tolist(), o.others[co:co + cl].tolist()))
+
+    @_lazy
+    def kmer_locs(self):
+        o = self._out
+        so, sl = o.seq_off[self._c]
+        return o.kmer_locs[so:so + sl].tolist()
+
+    @_lazy
+    def kmers(self):
+        o = self._out
+        ko, nk = o.kmers_off[self._c]
+        from . import _lib
+        from .batch import ORDER_NAMES
+        mers = _lib.codes_to_mers(o.kmer_mer[ko:ko + nk], o.k)
+        return list(zip(mers, o.kmer_pos[ko:ko + nk].tolist(), o.kmer_lth[ko:ko + nk].tolist(),
+                        o.kmer_dist[ko:ko + nk].tolist(), [ORDER_NAMES[x] for x in o.kmer_order[ko:ko + nk].tolist()]))
 
     def get_total_read_support(self):
+        o = self._out
+        if "aseq" not in self.__dict__ and o is not None:         # straight from the arrays
+            co, cl = o.cnt_off[self._c]
+            return int(o.indel_only[co:co + cl].max()) + int(o.others[co:co + cl].max())
         return self.aseq.counts.get_total_reads()
 
     def get_contig_len(self):
+        if "aseq" not in self.__dict__ and self._out is not None:
+            return int(self._out.seq_off[self._c][1])
         return len(self.aseq.seq)
 
     def get_kmer_locs(self):
@@ -91,31 +151,47 @@ class _AssemblyInput:
                 self.objs.append(fr)
 
 
-def init_assembly_batch(calls, device=0):
+def _clean_mers(mers, kmer_len):
+    """The reference takes any {str: int}: a mer that is not kmer_len upper-case ACGT characters can never be found in a
+    read by str.find on upper-case reads... except that it CAN if reads hold the same odd characters.  Those exotic mers
+    are not representable in the 2-bit table, so they are rejected loudly rather than silently dropped."""
+    for m in mers:
+        if len(m) != kmer_len:
+            raise ValueError("init_assembly: mer %r does not have kmer_len=%d characters" % (m, kmer_len))
+        if m.strip("ACGT"):
+            raise ValueError("init_assembly: mer %r holds characters other than upper-case A, C, G, T" % (m,))
+    return mers
+
+
+def init_assembly_batch(calls, device=0, on_capacity="raise"):
     """calls: [(mers, fq_recs, kmer_len, rc_thresh, read_len), ...] with one common
-    kmer_len and rc_thresh -> list (per call) of contig lists.  One GPU launch."""
+    kmer_len and rc_thresh -> list (per call) of contig lists.  One GPU pass.
+
+    A call whose region exceeds a device limit (a read longer than 4095 bases) does not disturb the others:
+    with on_capacity="raise" (default) a RuntimeError naming those calls is raised after every other call was completed
+    and stored in the exception's `.results`; with on_capacity="none" their entry in the returned list is None."""
     import numpy as np
     if not calls:
         return []
     inputs = [_AssemblyInput("r%d" % i, c[1], c[2], c[3]) for i, c in enumerate(calls)]
     pk = batch.PackedBatch(inputs, rc_thresh=int(calls[0][3]))
-    pk.set_mers([c[0] for c in calls])
+    pk.set_mers([_clean_mers(c[0], int(c[2])) for c in calls])
     pk.read_len = np.array([int(c[4]) for c in calls] + [0], dtype=np.int32)
     out = batch.run(get_handle(device), pk)
-    bad = [i for i, s in enumerate(out.region_status) if s != 0]
-    if bad:
-        raise RuntimeError("init_assembly: device capacity exceeded in call(s) %s (contig longer than 4095 bases)" % bad)
     objs = [o for inp in inputs for o in inp.objs]
     result = []
+    bad = []
     for i, c in enumerate(calls):
-        recs = out.contig_records(i)
-        ctgs = []
-        for j, rec in enumerate(recs):
-            cidx = int(out.ctg_reg_off[i]) + j
-            ro, nr = out.reads_off[cidx]
-            reads = [objs[int(r)] for r in out.reads[ro:ro + nr]]
-            ctgs.append(contig(rec, reads, int(c[2])))
-        result.append(ctgs)
+        if out.region_status[i] != 0:
+            bad.append(i)
+            result.append(None)
+            continue
+        result.append([contig(out, cidx, objs, int(c[2])) for cidx in range(int(out.ctg_reg_off[i]), int(out.ctg_reg_off[i + 1]))])
+    if bad and on_capacity == "raise":
+        err = RuntimeError("init_assembly: device capacity exceeded in call(s) %s (a read or contig longer than 4095 bases); "
+                           "the other calls completed (see .results)" % bad)
+        err.results = result
+        raise err
     return result
 
 

@@ -30,6 +30,7 @@ normal_fq) are parsed by the library's host threads straight into page-locked me
 (bk_ingest_files).  The reads of the returned contigs are then
 fresh fq_read objects built from the parsed records (same .id/.seq/.qual/.indel_only as the
 caller's; of these the rest of the reference only reads .id/.seq/.qual).
+`devices=[0, 1, ...]` shards the targets by region over several GPUs (no collective, host-side gather by name).
 `write_contigs=True` additionally writes, for every contig of every target, the files
 contig.setup writes before blat (sv_processor.py:749-782) under target.paths['contigs'], on the
 library's host threads (bk_write_contigs).
@@ -60,31 +61,40 @@ class _TargetInput:
 
 
 class _LazyReads:
-    """objs[i] for the native ingest: fq_read of record i, built on first use."""
+    """objs[i] for the native ingest: fq_read of record i, built on first use.  The raw record text (ids, bases,
+    qualities, flags) is copied out of the ingest buffer up front -- a few memcpys -- because that buffer is reused by
+    the next batch; strings are only decoded for the records somebody asks for."""
 
     def __init__(self, pk):
-        self._pk = pk
         self._cache = {}
-        self._cols = None
+        t, s, n = pk._text, pk._s, pk.n_reads
+        view = pk._view
+        self._id_off = view(t.id_off, n + 1, "int64").copy()
+        self._q_off = view(t.qual_off, n + 1, "int64").copy()
+        self._s_off = view(s.read_off, n + 1, "int64").copy()
+        self._ids = view(t.id_bytes, int(self._id_off[-1]) if n else 0, "uint8").tobytes()
+        self._quals = view(t.qual_bytes, int(self._q_off[-1]) if n else 0, "uint8").tobytes()
+        self._seqs = view(s.read_bases, int(self._s_off[-1]) if n else 0, "uint8").tobytes()
+        self._flags = pk.read_flags.copy()
 
     def __getitem__(self, i):
         fr = self._cache.get(i)
         if fr is None:
-            if self._cols is None:
-                self._cols = (self._pk.read_ids, self._pk.read_seqs(), self._pk.read_quals())
-            ids, seqs, quals = self._cols
-            fr = self._cache[i] = utils.fq_read(ids[i], seqs[i], quals[i], bool(self._pk.read_flags[i]))
+            fr = self._cache[i] = utils.fq_read(self._ids[self._id_off[i]:self._id_off[i + 1]].decode(),
+                                                self._seqs[self._s_off[i]:self._s_off[i + 1]].decode(),
+                                                self._quals[self._q_off[i]:self._q_off[i + 1]].decode(),
+                                                bool(self._flags[i]))
         return fr
 
 
 _ingests = {}
 
 
-def _get_ingest():
+def _get_ingest(slot=0):
     import threading
     from . import ingest as _ingest
-    key = threading.get_ident()                    # an ingest object's buffer is reused call to call: one per thread
-    if key not in _ingests:
+    key = (threading.get_ident(), slot)            # an ingest object's buffer is reused call to call: one per thread
+    if key not in _ingests:                        # (and per batch that thread keeps in flight)
         _ingests[key] = _ingest.Ingest()
     return _ingests[key]
 
@@ -94,67 +104,184 @@ class _K:
         self.k = k
 
 
-def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False):
+class CapacityError(RuntimeError):
+    """Some targets exceeded a device limit (a read or contig longer than 4095 bases).  Every other target of the
+    batch was completed; `.targets` lists the ones that were not (their state is untouched, so the reference's own
+    compare_kmers() can still be run on them)."""
+
+    def __init__(self, names):
+        RuntimeError.__init__(self, "compare_kmers: device capacity exceeded for target(s) %s; all other targets completed"
+                              % ", ".join(names))
+        self.targets = list(names)
+
+
+def _apply_chunk(targets, pk, res, inputs_k, objs, ingest, write_contigs, failed):
+    """Results of one device call -> the state target.compare_kmers leaves behind, for the targets of that call."""
+    status = [int(res.region_status[i]) for i in range(len(targets))]
+    ok = [st == 0 for st in status]
+    if ingest == "native":
+        ing = _get_ingest()
+        if write_contigs:
+            # contig.setup's files for every contig of every completed target in one pass (sv_processor.py:749-782,
+            # bk_write_contigs); the reference-side contig.__init__ then skips its own setup() call (INTEGRATION.md)
+            ing.write_contigs(res, pk, [t.paths['contigs'] if g else None for t, g in zip(targets, ok)],
+                              [os.path.join(t.paths['kmers'], t.name + "_sample_kmers_merged.out") if g else None
+                               for t, g in zip(targets, ok)])
+        # the "<mer>\t<count>" files of the completed targets in one multi-threaded sweep (bk_write_sample_kmers)
+        ing.write_sample_kmers(res, pk.k, [os.path.join(t.paths['kmers'], t.name + "_sample_kmers.out") if g else None
+                                           for t, g in zip(targets, ok)])
+    out = batch.BatchOutput(res, pk)
+    ctg_reg_off = out.ctg_reg_off.tolist()
+    so_off = out.so_off.tolist()
+    for i, trgt in enumerate(targets):
+        if not ok[i]:
+            failed.append(trgt.name)
+            continue
+        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
+        if ingest != "native":
+            with open(trgt.files['sample_kmers'], 'w') as f:
+                for mer, cnt in out.sample_only(i).items():
+                    f.write("\t".join([mer, str(cnt)]) + "\n")
+        kmers = trgt.kmers
+        kmers['ref'] = {}; kmers['case'] = {}; kmers['case_sc'] = {}
+        logger = getattr(trgt, "logger", None)
+        if logger is not None and logger.isEnabledFor(20):
+            logger.info('Writing %d sample-only kmers to file %s' % (so_off[i + 1] - so_off[i], trgt.files['sample_kmers']))
+        trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
+        k = inputs_k[i]
+        kmers['clusters'] = [contig(out, c, objs, k) for c in range(ctg_reg_off[i], ctg_reg_off[i + 1])]
+        trgt.cleaned_read_recs = None
+        kmers['case_only'] = {}
+
+
+def _pack_targets(targets, ingest, slot=0):
+    """-> (packed batch, per-target k, record index -> fq_read)"""
     import numpy as np
-    if not targets:
-        return
     if ingest == "native":
         get = lambda t, key: (t.files.get(key) if hasattr(t.files, "get") else None)   # noqa: E731
         k = int(targets[0].params.get_kmer_size())
         if any(int(t.params.get_kmer_size()) != k for t in targets):
             raise ValueError("one k per batch")
         nfq = [get(t, 'normal_fq') for t in targets]
-        pk = _get_ingest().files([t.files['target_ref_fn'][0] for t in targets], [t.files['cleaned_fq'] for t in targets],
+        pk = _get_ingest(slot).files([t.files['target_ref_fn'][0] for t in targets], [t.files['cleaned_fq'] for t in targets],
                                  [t.files['sv_sc_unmapped_fa'] for t in targets], normal=nfq if any(nfq) else None,
                                  k=k, rc_thresh=int(targets[0].params.get_sr_thresh('min')),
                                  names=[t.name for t in targets])
         for i, t in enumerate(targets):             # target.read_len is what get_fastq_reads returned (utils.py:236,246)
             pk.read_len[i] = int(t.read_len)
-        inputs = [_K(k)] * len(targets)
-        objs = _LazyReads(pk)
-    elif ingest == "python":
+        return pk, [k] * len(targets), _LazyReads(pk)
+    if ingest == "python":
         inputs = [_TargetInput(t) for t in targets]
         pk = batch.PackedBatch(inputs, rc_thresh=inputs[0].rc_thresh)
         pk.read_len = np.array([inp.read_len for inp in inputs] + [0], dtype=np.int32)
-        objs = [o for inp in inputs for o in inp.objs]
-    else:
-        raise ValueError("ingest must be 'python' or 'native'")
+        return pk, [inp.k for inp in inputs], [o for inp in inputs for o in inp.objs]
+    raise ValueError("ingest must be 'python' or 'native'")
+
+
+def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False, devices=None, max_targets=2048):
+    """target.compare_kmers() for many targets: one device pass (or, with `devices=[0, 1, ...]`, the targets sharded by
+    region over several GPUs of the box: breakmer_b200.shard, one host thread per device, chunks of at most max_targets
+    handed out largest-first, no collective; results are applied to the targets in name order).
+
+    Targets that exceed a device limit do not disturb the others: everything else completes, then CapacityError lists
+    them (their state is untouched)."""
+    if not targets:
+        return
     if write_contigs and ingest != "native":
         raise ValueError("write_contigs needs ingest='native' (the writer reads the parsed record text)")
-    res = batch.run(get_handle(device), pk, decode=False)
-    if write_contigs:
-        # contig.setup's files for every contig of every target in one pass (sv_processor.py:749-782, bk_write_contigs);
-        # the reference-side contig.__init__ then skips its own setup() call
-        _get_ingest().write_contigs(res, pk, [t.paths['contigs'] for t in targets],
-                                    [os.path.join(t.paths['kmers'], t.name + "_sample_kmers_merged.out") for t in targets])
-    out = batch.BatchOutput(res, pk)
-    for trgt in targets:
-        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
-    if ingest == "native":
-        # the "<mer>\t<count>" files of all targets in one multi-threaded sweep (bk_write_sample_kmers)
-        _get_ingest().write_sample_kmers(res, pk.k, [t.files['sample_kmers'] for t in targets])
-    for i, trgt in enumerate(targets):
-        if out.region_status[i] != 0:
-            raise RuntimeError("compare_kmers: device capacity exceeded for target %s" % trgt.name)
-        n_only = int(out.so_off[i + 1] - out.so_off[i])
-        if ingest != "native":
-            with open(trgt.files['sample_kmers'], 'w') as f:
-                for mer, cnt in out.sample_only(i).items():
-                    f.write("\t".join([mer, str(cnt)]) + "\n")
-        for key in ('ref', 'case', 'case_sc'):
-            trgt.kmers[key] = {}
-        logger = getattr(trgt, "logger", None)
-        if logger is not None:
-            logger.info('Writing %d sample-only kmers to file %s' % (n_only, trgt.files['sample_kmers']))
-        trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
-        ctgs = []
-        for j, rec in enumerate(out.contig_records(i, with_reads=False)):
-            cidx = int(out.ctg_reg_off[i]) + j
-            ro, nr = out.reads_off[cidx]
-            ctgs.append(contig(rec, [objs[int(r)] for r in out.reads[ro:ro + nr]], inputs[i].k))
-        trgt.kmers['clusters'] = ctgs
-        trgt.cleaned_read_recs = None
-        trgt.kmers['case_only'] = {}
+    if ingest not in ("python", "native"):
+        raise ValueError("ingest must be 'python' or 'native'")
+    failed = []
+    if devices is None or len(devices) <= 1:
+        dev = device if not devices else devices[0]
+        for a in range(0, len(targets), max_targets):
+            chunk = targets[a:a + max_targets]
+            pk, ks, objs = _pack_targets(chunk, ingest)
+            res = batch.run(get_handle(dev), pk, decode=False)
+            _apply_chunk(chunk, pk, res, ks, objs, ingest, write_contigs, failed)
+    else:
+        _sharded(targets, list(devices), ingest, write_contigs, max_targets, failed)
+    if failed:
+        raise CapacityError(sorted(failed))
+
+
+def _sharded(targets, devices, ingest, write_contigs, max_targets, failed):
+    """Region-sharded multi-GPU pass: sv_processor.py:185-201 over `devices` (see shard.run_sharded)."""
+    import threading
+    from . import shard
+    costs = [_target_cost(t) for t in targets]
+    order = sorted(range(len(targets)), key=lambda i: (-costs[i], i))
+    n_chunks = max(len(devices), (len(targets) + max_targets - 1) // max_targets)
+    per = (len(targets) + n_chunks - 1) // n_chunks
+    by_name = sorted(range(len(targets)), key=lambda i: targets[i].name)           # sv_processor.py:175-176
+    rank_of = {i: r for r, i in enumerate(by_name)}
+    chunks = [sorted(order[a:a + per], key=lambda i: rank_of[i]) for a in range(0, len(order), per)]
+    lock = threading.Lock()
+    cursor = [0]
+    errors = []
+
+    def take():
+        with lock:
+            if cursor[0] >= len(chunks):
+                return None
+            c = chunks[cursor[0]]
+            cursor[0] += 1
+            return c
+
+    def worker(dev):
+        pipe = None
+        n_sub = 0
+        try:
+            pipe = shard.DevicePipeline(dev, inflight=2)
+
+            def drain_one():
+                res, pk, tag = pipe.pop(decode=False)
+                chunk, ks, objs = tag
+                mine = []
+                _apply_chunk(chunk, pk, res, ks, objs, ingest, write_contigs, mine)
+                with lock:
+                    failed.extend(mine)
+
+            while True:
+                idx = take()
+                if idx is None:
+                    break
+                chunk = [targets[i] for i in idx]
+                if pipe.full():
+                    drain_one()
+                # (a native ingest buffer is reused call to call: two of them alternate under the two batches in flight)
+                pk, ks, objs = _pack_targets(chunk, ingest, slot=n_sub % 2)
+                n_sub += 1
+                pipe.submit(pk, (chunk, ks, objs))
+            while pipe.pending():
+                drain_one()
+        except Exception as e:                           # noqa: BLE001 -- re-raised on the calling thread
+            errors.append(e)
+        finally:
+            if pipe is not None:
+                pipe.close()
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in devices]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
+def _target_cost(trgt):
+    """Static cost of a target before the device pass (shard.region_cost on what the target object knows)."""
+    from . import shard
+    recs = getattr(trgt, "cleaned_read_recs", None)
+    n = sum(len(g) for g in recs.values()) if recs else 0
+    nbytes = 0
+    for key in ('cleaned_fq', 'sv_sc_unmapped_fa'):
+        try:
+            nbytes += os.path.getsize(trgt.files[key])
+        except (OSError, KeyError, TypeError):
+            pass
+    return shard.COST_CELLS_PER_READ2 * n * n + shard.COST_CELLS_PER_READ * n + shard.COST_CELLS_PER_BYTE * nbytes + 1.0
 
 
 def compare_kmers(target, device=0, ingest="python"):

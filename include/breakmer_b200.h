@@ -163,6 +163,8 @@ typedef struct bk_batch_result {
   double  gpu_ms;                    /* device time of the call, CUDA events */
   int64_t n_sorted_keys;             /* windows that went through the sort (the sample's; the rest are streamed past) */
   const int64_t* region_dp_cells;    /* per region: its share of n_dp_cells (cost models for sharding, shard.py) */
+  double host_wait_ms;               /* bk_batch_wait: time blocked on the device ... */
+  double host_post_ms;               /* ... and time spent building the result tables on the host */
 } bk_batch_result;
 
 int bk_compare_kmers_batch(bk_handle_t h, const bk_batch_input* in, bk_batch_result* out);

@@ -7,6 +7,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
 
@@ -29,6 +31,9 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0
+    # both arms describe the workload with the same config object
+    import bench
+    assert d["config"] == bench.config_dict("C1", 1)
 
 
 @pytest.mark.gpu
@@ -44,3 +49,6 @@ def test_gpu_arm_line():
     assert d["from_files"]["value"] > 0 and d["from_files"]["n_contigs"] > 0
     assert d["with_ref_kmer_cache"]["value"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["sharding_check"]["equal_to_single_gpu_run"] is True and d["sharding_check"]["regions"] == 60
+    assert d["e2e_dropin"]["value"] > 0 and d["run"]["host_threads_per_rank"] == 1
+    assert all(v["frac"] is None or v["frac"] >= 0 for v in d["roofline_per_kernel"].values())

@@ -200,3 +200,92 @@ def test_ingested_batch_equals_packed_batch(tmp_path):
     assert [(got.sample_only(i), got.contig_records(i)) for i in range(len(regions))] == want_rec
     assert sum(len(c) for _s, c in want_rec) > 0
     g.close()
+
+
+def test_sharded_compare_kmers_batch_over_devices(tmp_path):
+    """compare_kmers_batch(targets, devices=[...]): region-sharded multi-GPU entry (one host thread + its own handles
+    per device entry, chunks handed out dynamically).  Two workers on device 0 exercise the same code on a one-GPU box."""
+    from breakmer_b200 import sv_processor
+    regions = list(synth.config_regions("C2", 14, start=60)) + list(synth.config_regions("C5", 30, start=90))
+    d1, d2 = os.path.join(str(tmp_path), "a"), os.path.join(str(tmp_path), "b")
+    os.makedirs(d1); os.makedirs(d2)
+    single = [_Target(r, d1) for r in regions]
+    sharded = [_Target(r, d2) for r in regions]
+    sv_processor.compare_kmers_batch(single, ingest="native")
+    sv_processor.compare_kmers_batch(sharded, ingest="native", devices=[0, 0], max_targets=7)
+    n_ctg = 0
+    for a, b in zip(single, sharded):
+        with open(a.files["sample_kmers"]) as fa, open(b.files["sample_kmers"]) as fb:
+            assert fa.read() == fb.read()
+        assert len(a.kmers["clusters"]) == len(b.kmers["clusters"])
+        for x, y in zip(a.kmers["clusters"], b.kmers["clusters"]):
+            assert x.get_contig_seq() == y.get_contig_seq() and x.kmers == y.kmers and x.get_kmer_locs() == y.get_kmer_locs()
+            assert x.get_contig_counts().indel_only == y.get_contig_counts().indel_only
+            assert sorted(r.id for r in x.reads) == sorted(r.id for r in y.reads)
+            n_ctg += 1
+        assert b.cleaned_read_recs is None
+    assert n_ctg > 10
+    # python marshalling through the same sharded path
+    third = [_Target(r, d2) for r in regions[:10]]
+    sv_processor.compare_kmers_batch(third, devices=[0, 0], max_targets=3)
+    for a, b in zip(single, third):
+        assert [c.get_contig_seq() for c in a.kmers["clusters"]] == [c.get_contig_seq() for c in b.kmers["clusters"]]
+
+
+def test_run_sharded_matches_one_call():
+    from breakmer_b200 import _lib, batch, shard
+    regions = list(synth.config_regions("C2", 20, start=200))
+    h = _lib.Handle(0)
+    try:
+        pk = batch.PackedBatch(regions)
+        want = shard.region_digests(batch.run(h, pk), pk)
+    finally:
+        h.close()
+    chunks = {}
+
+    def on_result(idx, out, packed):
+        chunks[tuple(idx)] = shard.region_digests(out, packed)
+
+    got = shard.run_sharded(regions, devices=(0, 0), max_regions=6, inflight=2, on_result=on_result)
+    assert list(got) == sorted(r.name for r in regions)
+    assert sorted(i for idx in chunks for i in idx) == list(range(len(regions))) and len(chunks) >= 4
+    merged = {}
+    for d in chunks.values():
+        merged.update(d)
+    assert merged == want
+    assert shard.digest_of_digests(merged) == shard.digest_of_digests(want)
+    for name, (out, j) in got.items():
+        assert out.region_status[j] == 0
+
+
+def test_one_target_over_the_limit_does_not_disturb_the_batch(tmp_path):
+    from breakmer_b200 import sv_processor
+    regions = list(synth.config_regions("C2", 5, start=30))
+    long_r = synth.Region(name="zz_long", k=15, ref_fwd="ACGT" * 50, reads=[("@a:1:1:1:1/1_0", "ACGT" * 1100, "I" * 4400, False)],
+                          sc_records=[("a", "ACGT" * 10)])
+    targets = [_Target(r, str(tmp_path)) for r in regions[:2] + [long_r] + regions[2:]]
+    for ingest in ("python", "native"):
+        for t, r in zip(targets, regions[:2] + [long_r] + regions[2:]):
+            t.cleaned_read_recs = _fq_recs(r)
+            t.kmers = {}
+        with pytest.raises(sv_processor.CapacityError) as e:
+            sv_processor.compare_kmers_batch(targets, ingest=ingest)
+        assert e.value.targets == ["zz_long"]
+        for t in targets:
+            if t.name == "zz_long":
+                assert t.cleaned_read_recs is not None and "clusters" not in t.kmers     # untouched
+            else:
+                r = next(x for x in regions if x.name == t.name)
+                _a, _b, _c, only = oracle_sample_only(r)
+                exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
+                assert [c.get_contig_seq() for c in t.kmers["clusters"]] == [x["seq"] for x in exp]
+                assert t.cleaned_read_recs is None
+
+
+def test_init_assembly_rejects_mers_it_cannot_represent():
+    from breakmer_b200 import sv_assembly
+    r = synth.config_region("C2", 3)
+    with pytest.raises(ValueError):
+        sv_assembly.init_assembly({"ACGTN" * 3: 3}, _fq_recs(r), 15, 2, 100)
+    with pytest.raises(ValueError):
+        sv_assembly.init_assembly({"ACGT": 3}, _fq_recs(r), 15, 2, 100)

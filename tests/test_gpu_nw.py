@@ -80,3 +80,48 @@ def test_max_length_and_limits(handle):
     with pytest.raises(_lib.BreakmerError) as e:
         _run(handle, [("", "ACGT")])
     assert e.value.code == _lib.BK_ERR_EMPTY_SEQ      # the reference raises NameError here
+
+
+def test_score_pass_traceback_equals_packed_cell_kernel(handle, monkeypatch):
+    """Both DP kernels of nw.cuh on the same pairs: the score pass + warp-parallel traceback (default where its table
+    fits) and the packed-cell kernel that carries origins forward (BK_NW_PACKED=1 forces it everywhere)."""
+    rng = random.Random(29)
+    pairs = []
+    for t in range(1500):
+        la = rng.randint(1, 128)                       # columns: the trace path takes one column block of 4 per lane
+        lb = rng.choice([1, 2, 5, 40, 99, 100, 101, 160, 230, 400, 800, 1216, 1217, 1300])
+        g = "".join(rng.choice("ACGT") for _ in range(la + lb + 50))
+        mode = t % 5
+        if mode == 0:                                  # suffix of b overlaps prefix of a
+            ov = rng.randint(1, min(la, lb))
+            b = (g[la:la + lb - ov] + g[:ov])[:lb]
+            a = g[:la]
+        elif mode == 1:                                # contained
+            a = g[10:10 + la]; b = g[:lb] if lb > la + 10 else g[:la + 20]
+        elif mode == 2:                                # low-complexity / repeats: many ties
+            unit = "".join(rng.choice("AC") for _ in range(rng.randint(1, 4)))
+            a = (unit * 200)[:la]; b = (unit * 700)[:lb]
+        elif mode == 3:                                # unrelated
+            a = g[:la]; b = "".join(rng.choice("ACGTN") for _ in range(lb))
+        else:                                          # overlap with indels
+            a = g[:la]
+            b = list(g[max(0, la - 60):][:lb])
+            for _ in range(rng.randint(0, 4)):
+                if b:
+                    p = rng.randrange(len(b))
+                    if rng.random() < 0.5:
+                        del b[p]
+                    else:
+                        b.insert(p, rng.choice("ACGT"))
+            b = "".join(b) or "A"
+        if rng.random() < 0.3:
+            b = "".join(c if rng.random() > 0.03 else rng.choice("ACGTN") for c in b)
+        pairs.append((a, b))
+    fast, _ = _run(handle, pairs)
+    monkeypatch.setenv("BK_NW_PACKED", "1")
+    packed, _ = _run(handle, pairs)
+    monkeypatch.delenv("BK_NW_PACKED")
+    assert np.array_equal(fast, packed)
+    for (a, b), o in list(zip(pairs, fast))[::7]:
+        assert list(o[:5]) == list(nw_py.nw_fast(a, b)[2:]), (a, b)
+        assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (a, b)

@@ -33,3 +33,19 @@ def test_two_ranks_gloo():
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok"] and res["n"] == 46 and sum(res["sizes"]) == 46 and min(res["sizes"]) > 0
+
+
+def test_chunks_cover_the_shard_and_respect_the_call_limit():
+    assert shard.chunk_indices([], 5) == []
+    idx = list(range(0, 46, 2))
+    chunks = shard.chunk_indices(idx, 5)
+    assert [i for c in chunks for i in c] == idx and max(len(c) for c in chunks) <= 5
+    assert max(len(c) for c in chunks) - min(len(c) for c in chunks) <= 4
+    assert shard.chunk_indices(idx, 1000) == [idx]
+
+
+def test_static_cost_grows_with_reads_and_bytes():
+    from breakmer_b200 import synth
+    small = synth.config_region("C5", 1)
+    big = synth.config_region("C2", 1)
+    assert shard.region_cost(big) > shard.region_cost(small) > 0
