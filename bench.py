@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.1)     # NVML queries contend with kernel launches of every process on the box: keep them sparse
 
     def stop(self):
         self._stop_evt.set()
@@ -259,6 +259,14 @@ class Dist:
     def sum(self, x):
         return self._reduce(x, self.dist.ReduceOp.SUM)
 
+    def gather_floats(self, x):
+        if self.world == 1:
+            return [x]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = x
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def close(self):
         if self.world > 1:
             self.dist.barrier()
@@ -268,7 +276,7 @@ class Dist:
 class ShardRun:
     """One workload, partitioned by region over the ranks; this rank's share as resident / host-buffer passes."""
 
-    def __init__(self, D, workload, total, inflight, spec_width=0, call_regions=CALL_REGIONS):
+    def __init__(self, D, workload, total, inflight, spec_width=0, call_regions=CALL_REGIONS, replicate=False):
         from breakmer_b200 import _lib, batch, shard, synth
         self.D = D
         self.workload = workload
@@ -278,6 +286,8 @@ class ShardRun:
         self.regions = [synth.config_region(workload, i) for i in range(total)]
         self.costs = [shard.region_cost(r) for r in self.regions]
         self.owned = shard.assign_lpt(self.costs, D.world)
+        if replicate:                               # diagnostic: every rank runs the regions rank 0 owns (system effects only)
+            self.owned = [self.owned[0]] * D.world
         self.mine = self.owned[D.rank]
         self.chunks = shard.chunk_indices(self.mine, call_regions)
         self.packed = [batch.PackedBatch([self.regions[i] for i in c]).pin() for c in self.chunks]
@@ -347,7 +357,8 @@ class ShardRun:
         ev1.synchronize()
         wall = time.time() - t0
         self.D.barrier()
-        return self.D.max(ev0.elapsed_time(ev1) / 1000.0), self.D.max(wall)
+        self.last_local_dev_s = ev0.elapsed_time(ev1) / 1000.0
+        return self.D.max(self.last_local_dev_s), self.D.max(wall)
 
     def counters(self):
         """work counters of one pass over this rank's chunks (from the last results)"""
@@ -388,7 +399,8 @@ class ShardRun:
 
 def sharded_summary(D, workload, total, args, steps):
     """value / e2e / sharding check of one more workload (the c5_strong and c3_sharded keys of the line)."""
-    run = ShardRun(D, workload, total, args.inflight, args.spec_width)
+    # (C5 calls have long tails -- 2 % of the regions carry all the assembly work -- so more of them are kept in flight)
+    run = ShardRun(D, workload, total, max(args.inflight, 8) if workload == "C5" else args.inflight, args.spec_width)
     try:
         run.upload()
         run.run_pass(run.warm_passes(), True)
@@ -417,7 +429,7 @@ def gpu_arm(args):
     total = cfg["regions_total"]
     hbm_peak, peak_src = load_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    run = ShardRun(D, args.workload, total, args.inflight, args.spec_width)
+    run = ShardRun(D, args.workload, total, args.inflight, args.spec_width, replicate=args.replicate)
     H = run.n_handles
     h = run.handles[0]
 
@@ -441,10 +453,12 @@ def gpu_arm(args):
     for hh in run.handles:
         hh.kernel_times_reset(False)                # timers off, launch counters zeroed for the timed region
     sampler = ClockSampler(D.local_rank)
-    sampler.start()
+    if not args.no_clock_sampler and D.rank == 0:   # the line is rank 0's: its GPU is the one sampled
+        sampler.start()
     dev_s, wall_s = run.timed(args.steps, True, flush)
     host_resident = run.host_ms
     clocks = sampler.stop()
+    rank_ms = D.gather_floats(1000.0 * run.last_local_dev_s / args.steps)
     gpu_launches = 0
     for hh in run.handles:
         gpu_launches += int(sum(v[1] for v in hh.kernel_times().values()))
@@ -467,7 +481,7 @@ def gpu_arm(args):
         d2h += int(out.seq.nbytes + out.kmer_locs.nbytes + out.indel_only.nbytes + out.others.nbytes + out.reads.nbytes +
                    out.kmer_mer.nbytes + 2 * out.kmer_pos.nbytes + out.so_mers.nbytes + out.so_counts.nbytes +
                    out.uniq_rec.nbytes + out.uniq_mult.nbytes)
-    ok, digest, _nl = run.check_against_single_gpu()
+    ok, digest, _nl = (None, None, 0) if args.replicate else run.check_against_single_gpu()
 
     # ---- same steps with the persistent reference k-mer cache (reported beside the headline, not as it) ----
     ref_cache = None
@@ -530,7 +544,8 @@ def gpu_arm(args):
                        "%d independent batches in flight on separate buffers; the per-step working set (~1 GB of "
                        "key/value, scratch and state arrays per batch) exceeds the 126 MB L2" % H),
                 "timing": "CUDA events bracketing the K steps (barrier + synchronize on both sides), max over ranks",
-                "wall_ms_per_step": 1000.0 * wall_s / args.steps,
+                "wall_ms_per_step": 1000.0 * wall_s / args.steps, "device_ms_per_step_by_rank": [round(v, 3) for v in rank_ms],
+                "replicated_regions_diagnostic": bool(args.replicate),
                 "sequential_latency_ms_per_step": (min(lat_ms) if lat_ms else None), "generate_s": round(run.gen_s, 1),
                 "host_e2e": host_e2e, "host_resident": host_resident},
         "sharding_check": {"regions": total, "equal_to_single_gpu_run": ok, "result_digest": digest,
@@ -782,6 +797,8 @@ def main():
     ap.add_argument("--spec-width", type=int, default=0, help="assembler warps per region (0 = auto)")
     ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) kept on the device at once")
     ap.add_argument("--c5-regions", type=int, default=20000, help="size of the c5_strong workload")
+    ap.add_argument("--replicate", action="store_true", help="diagnostic: every rank runs rank 0's regions (not the headline)")
+    ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
     ap.add_argument("--no-ingest-leg", action="store_true")
