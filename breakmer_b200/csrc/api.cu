@@ -9,6 +9,7 @@
 
 #include "host_util.cuh"
 #include "kmers.cuh"
+#include "region_kmers.cuh"
 #include "nw_batch.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -99,24 +100,12 @@ struct SelectOut {
   uint32_t* seg_counts;   // device, n_seg (or null)
 };
 
-// candidate hash table handed to the caller's probe callback (kmers.cuh, probe mode)
-struct ProbeTable {
-  const uint64_t* keys;
-  const uint32_t* idx;
-  const uint64_t* mask_dev;
-  uint8_t* dead;
-};
-
 inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-// sel_cap: upper bound of the number of selected runs (the caller knows one: every selected sample-only run holds a
-// soft-clip window; SELECT_ALL selects at most n).  dst_*: optional destination shared by several calls (region chunks),
-// each call writing at *dst_base_dev.
+// sel_cap: upper bound of the number of selected runs (SELECT_ALL selects at most n; a sample-only run holds a case k-mer).
 SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t n, int k, int seg_bits, int mode,
-                          int64_t n_seg, int64_t sel_cap, bool use_ref_cache = false, int seg_shift = 0,
-                          const std::function<void(const ProbeTable&)>& probe = nullptr, uint64_t* dst_mers = nullptr,
-                          uint32_t* dst_counts = nullptr, const uint32_t* dst_base_dev = nullptr) {
-  SelectOut o{dst_mers, dst_counts, nullptr, nullptr};
+                          int64_t n_seg, int64_t sel_cap) {
+  SelectOut o{nullptr, nullptr, nullptr, nullptr};
   cudaStream_t st = h->st;
   if (n_seg > 0) {
     o.seg_counts = h->dev.get<uint32_t>(n_seg);
@@ -144,7 +133,6 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
   radix_sort_pairs(keys, vals, n, key_bits, sc, st, &sk, &sv, h->timers);
   RunParams rp{};
   rp.keys = sk; rp.vals = sv; rp.n = n; rp.k = k; rp.mode = mode;
-  if (use_ref_cache) { rp.ref_mers = h->ref_cache_mers; rp.ref_koff = h->ref_cache_koff; rp.seg_shift = seg_shift; }
   rp.flags = h->dev.get<uint32_t>(n);
   rp.run_count = h->dev.get<uint32_t>(n);
   uint32_t* pos = h->dev.get<uint32_t>(n);
@@ -159,53 +147,10 @@ SelectOut sort_and_select(bk_handle_t h, uint64_t* keys, uint32_t* vals, int64_t
     exclusive_scan_u32(rp.flags, pos, n, scan_tmp, o.d_n, st);
   }
   rp.pos = pos;
-  if (!probe) {
-    rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts; rp.out_base_dev = dst_base_dev;
-    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
-    run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
-    BK_CUDA(cudaGetLastError());
-    return o;
-  }
-  // ---- probe mode: the selected runs are only candidates; the caller streams further windows past them -----------
-  uint64_t* cand_mers = h->dev.get<uint64_t>(sel_cap);
-  uint32_t* cand_counts = h->dev.get<uint32_t>(sel_cap);
-  uint32_t* cand_seg = h->dev.get<uint32_t>(sel_cap);
-  rp.out_mers = cand_mers; rp.out_counts = cand_counts; rp.seg_counts = nullptr; rp.out_seg = cand_seg; rp.out_base_dev = nullptr;
-  uint64_t cap = 1024;
-  while (cap < 2 * (uint64_t)sel_cap) cap <<= 1;           // worst case; the used size (mask + 1) is decided on the device
-  uint64_t* tkeys = h->dev.get<uint64_t>(cap);
-  uint32_t* tidx = h->dev.get<uint32_t>(cap);
-  uint8_t* dead = h->dev.get<uint8_t>(sel_cap);
-  uint64_t* mask_dev = h->dev.get<uint64_t>(1);
-  BK_CUDA(cudaMemsetAsync(dead, 0, sel_cap, st));
-  {
-    TimedLaunch t(h->timers, st, KF_RUN_SCATTER, 4);
-    cand_table_size_kernel<<<1, 1, 0, st>>>(o.d_n, cap, mask_dev);
-    cand_table_clear_kernel<<<(unsigned)std::min<uint64_t>(cap / 256, (uint64_t)h->sm_count * 8), 256, 0, st>>>(tkeys, mask_dev);
-    run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
-    cand_insert_kernel<<<blocks, 256, 0, st>>>(rp, tkeys, tidx, mask_dev);
-  }
-  probe(ProbeTable{tkeys, tidx, mask_dev, dead});
-  uint32_t* flags2 = h->dev.get<uint32_t>(sel_cap);
-  uint32_t* pos2 = h->dev.get<uint32_t>(sel_cap);
-  uint32_t* scan_tmp2 = h->dev.get<uint32_t>(scan_tmp_elems(sel_cap));
-  uint32_t* d_n2 = h->dev.get<uint32_t>(1);
-  const unsigned blocks2 = blocks_for(sel_cap, 256);
-  {
-    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
-    survivor_flag_kernel<<<blocks2, 256, 0, st>>>(dead, o.d_n, sel_cap, flags2);
-  }
-  {
-    TimedLaunch t(h->timers, st, KF_SCAN, 3);
-    exclusive_scan_u32(flags2, pos2, sel_cap, scan_tmp2, d_n2, st);
-  }
-  {
-    TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
-    survivor_scatter_kernel<<<blocks2, 256, 0, st>>>(flags2, pos2, sel_cap, cand_mers, cand_counts, cand_seg, o.mers, o.counts,
-                                                     o.seg_counts, dst_base_dev);
-  }
+  rp.out_mers = o.mers; rp.out_counts = o.counts; rp.seg_counts = o.seg_counts;
+  TimedLaunch t(h->timers, st, KF_RUN_SCATTER);
+  run_scatter_kernel<<<blocks, 256, 0, st>>>(rp);
   BK_CUDA(cudaGetLastError());
-  o.d_n = d_n2;
   return o;
 }
 

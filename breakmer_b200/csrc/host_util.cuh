@@ -92,10 +92,10 @@ class Arena {
 
 enum KernelFamily : int {
   KF_NW_BATCH = 0, KF_EMIT, KF_SORT_COUNT, KF_SORT_SCAN, KF_SORT_SCATTER, KF_RUN_SELECT, KF_RUN_SCATTER, KF_SCAN,
-  KF_GROUP, KF_INDEX, KF_PREP, KF_ASSEMBLE, KF_AUX_SORT, KF_COUNT_
+  KF_GROUP, KF_INDEX, KF_PREP, KF_ASSEMBLE, KF_AUX_SORT, KF_REGION_KMERS, KF_COUNT_
 };
 static const char* const kKernelFamilyNames =
-    "nw_batch;kmer_emit;sort_count;sort_scan;sort_scatter;run_select;run_scatter;scan;group_reads;index;prep;assemble;aux_sort";
+    "nw_batch;kmer_emit;sort_count;sort_scan;sort_scatter;run_select;run_scatter;scan;group_reads;index;prep;assemble;aux_sort;region_kmers";
 
 struct KernelTimers {
   bool enabled = false;

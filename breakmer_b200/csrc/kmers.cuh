@@ -16,11 +16,9 @@
 //                      set they came from, so (case & case_sc) - ref [- normal]
 //                      is a property of the run.
 //   run_scatter_kernel compaction of the selected runs to (mer, count) arrays.
-//   probe mode         the batched pipeline does not sort the reference (or normal) windows at all: it sorts only
-//                      the sample's windows, selects case & case_sc, puts those candidates in a hash table
-//                      (cand_insert_kernel) and streams the reference / normal windows past it with
-//                      kmer_emit_kernel in probe mode -- a hit marks the candidate dead -- then compacts the
-//                      survivors (survivor_* kernels).  Same set algebra, ~4x fewer keys through the sort.
+//
+// These kernels back bk_count_kmers, bk_sample_only and the reference k-mer cache (sorted outputs over arbitrary
+// inputs).  The batched pipeline itself counts per region in shared-memory hash tables: region_kmers.cuh.
 //
 // Key layout:    [ 0 | region | mer (2k bits) ]          (one spare top bit: the all-ones invalid key sorts last)
 // Value layout:  [ set tag : 2 | multiplicity : 30 ]
@@ -51,12 +49,6 @@ struct EmitParams {
   uint64_t* keys;             // [out_base + p] forward, [out_base_rc + p] reverse complement
   uint32_t* vals;
   int64_t out_base, out_base_rc;
-  // probe mode (probe_keys != null): nothing is written; every valid window (and its reverse complement if emit_rc)
-  // is looked up in the open-addressed candidate table and a hit sets dead[probe_idx[slot]]
-  const uint64_t* probe_keys;
-  const uint32_t* probe_idx;
-  const uint64_t* probe_mask_dev;   // table size - 1, decided on the device from the candidate count
-  uint8_t* dead;
 };
 
 __device__ __forceinline__ uint64_t cand_hash(uint64_t x) {
@@ -66,23 +58,12 @@ __device__ __forceinline__ uint64_t cand_hash(uint64_t x) {
   return x;
 }
 
-__device__ __forceinline__ void probe_candidate(const EmitParams& P, uint64_t mask, uint64_t key) {
-  uint64_t slot = cand_hash(key) & mask;
-  for (;;) {
-    const uint64_t t = P.probe_keys[slot];
-    if (t == key) { P.dead[P.probe_idx[slot]] = 1; return; }
-    if (t == KEY_INVALID) return;
-    slot = (slot + 1) & mask;
-  }
-}
-
 __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
   __shared__ uint8_t code[EMIT_TILE + 32];
   __shared__ int64_t s_rfirst;
   const int tid = threadIdx.x;
   const int64_t p0 = (int64_t)blockIdx.x * EMIT_TILE;
   const int k = P.k;
-  const uint64_t pmask = P.probe_keys ? *P.probe_mask_dev : 0ull;
   if (tid == 0) {
     // last record whose start is <= p0
     int64_t lo = 0, hi = P.n_rec;           // rec_off[lo] <= p0 < rec_off[hi]
@@ -150,13 +131,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) kmer_emit_kernel(EmitParams P) {
       if (P.rec_mult) mult = P.rec_mult[rec];
     }
     const uint64_t hi = seg << (2 * k);
-    if (P.probe_keys) {
-      if (ok) {
-        probe_candidate(P, pmask, hi | fwd);
-        if (P.emit_rc) probe_candidate(P, pmask, hi | rc);
-      }
-      continue;
-    }
     const uint32_t v = (mult & 0x3FFFFFFFu) | ((uint32_t)P.tag << 30);
     P.keys[P.out_base + p] = ok ? (hi | fwd) : KEY_INVALID;
     P.vals[P.out_base + p] = v;
@@ -183,12 +157,6 @@ struct RunParams {
   uint64_t* out_mers;
   uint32_t* out_counts;
   uint32_t* seg_counts;       // per region number of selected runs (atomic), may be null
-  uint32_t* out_seg;          // region of each selected run, may be null (probe mode)
-  const uint32_t* out_base_dev; // device: where this call's output starts in out_mers / out_counts (null = 0; region chunks)
-  // optional persistent reference k-mer cache: sorted mers of region r at ref_mers[ref_koff[r] .. ref_koff[r+1])
-  const uint64_t* ref_mers;
-  const int64_t* ref_koff;
-  int seg_shift;              // region id in the key + seg_shift = region id of the cache
 };
 
 __global__ void __launch_bounds__(256) run_select_kernel(RunParams P) {
@@ -216,17 +184,6 @@ __global__ void __launch_bounds__(256) run_select_kernel(RunParams P) {
         // (case & case_sc) - ref - normal ; reported count is the case count (sv_processor.py:621-631)
         bool sel = (seen & (1u << TAG_CASE)) && (seen & (1u << TAG_SC)) && !(seen & (1u << TAG_REF)) &&
                    !(seen & (1u << TAG_NORMAL));
-        if (sel && P.ref_mers) {
-          // the reference set was counted once and cached: membership by binary search in the region's sorted mers
-          const uint64_t mer = key & ((P.k == 32) ? ~0ull : ((1ull << (2 * P.k)) - 1ull));
-          const int64_t seg = (int64_t)(key >> (2 * P.k)) + P.seg_shift;
-          int64_t lo = P.ref_koff[seg], hi = P.ref_koff[seg + 1];
-          while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (P.ref_mers[mid] < mer) lo = mid + 1; else hi = mid;
-          }
-          if (lo < P.ref_koff[seg + 1] && P.ref_mers[lo] == mer) sel = false;
-        }
         flag = sel ? 1u : 0u;
         total = c_case;
       }
@@ -242,66 +199,11 @@ __global__ void __launch_bounds__(256) run_scatter_kernel(RunParams P) {
   if (!P.flags[i]) return;
   const uint64_t g = P.keys[i];
   const uint64_t mer = g & ((P.k == 32) ? ~0ull : ((1ull << (2 * P.k)) - 1ull));
-  const uint32_t dst = P.pos[i] + (P.out_base_dev ? *P.out_base_dev : 0u);
+  const uint32_t dst = P.pos[i];
   P.out_mers[dst] = mer;
   P.out_counts[dst] = P.run_count[i];
-  if (P.out_seg) P.out_seg[dst] = (uint32_t)(g >> (2 * P.k));
   if (P.seg_counts) atomicAdd(&P.seg_counts[(uint32_t)(g >> (2 * P.k))], 1u);
 }
-
-// ---- probe mode: candidate hash table + survivor compaction -------------------------------------------------
-// insert every selected run head [region | mer] -> its compacted index
-// The candidate table is allocated for the worst case (every soft-clip window a candidate) but only its first
-// mask + 1 slots are used: mask is chosen on the device from the actual candidate count (load <= 0.5), so the table
-// stays L2 resident and the host never has to learn the count.
-__global__ void cand_table_size_kernel(const uint32_t* __restrict__ n_cand, uint64_t cap_bound, uint64_t* __restrict__ mask) {
-  uint64_t cap = 1024;
-  while (cap < 2ull * (uint64_t)*n_cand && cap < cap_bound) cap <<= 1;
-  *mask = cap - 1;
-}
-__global__ void __launch_bounds__(256) cand_table_clear_kernel(uint64_t* __restrict__ tkeys, const uint64_t* __restrict__ mask) {
-  const uint64_t n = *mask + 1;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) tkeys[i] = KEY_INVALID;
-}
-
-__global__ void __launch_bounds__(256) cand_insert_kernel(RunParams P, uint64_t* __restrict__ tkeys,
-                                                          uint32_t* __restrict__ tidx, const uint64_t* __restrict__ mask_dev) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n) return;
-  if (!P.flags[i]) return;
-  const uint64_t mask = *mask_dev;
-  const uint64_t key = P.keys[i];
-  uint64_t slot = cand_hash(key) & mask;
-  for (;;) {
-    const unsigned long long prev = atomicCAS((unsigned long long*)&tkeys[slot], (unsigned long long)KEY_INVALID,
-                                              (unsigned long long)key);
-    if (prev == (unsigned long long)KEY_INVALID) { tidx[slot] = P.pos[i]; return; }
-    slot = (slot + 1) & mask;
-  }
-}
-
-// n_bound elements are written (the scan that follows covers all of them); candidates are [0, *n_cand)
-__global__ void __launch_bounds__(256) survivor_flag_kernel(const uint8_t* __restrict__ dead, const uint32_t* __restrict__ n_cand,
-                                                            int64_t n_bound, uint32_t* __restrict__ flags) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_bound) flags[i] = (i < (int64_t)*n_cand && !dead[i]) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(256) survivor_scatter_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos,
-                                                               int64_t n, const uint64_t* __restrict__ in_mers,
-                                                               const uint32_t* __restrict__ in_counts,
-                                                               const uint32_t* __restrict__ in_seg,
-                                                               uint64_t* __restrict__ out_mers, uint32_t* __restrict__ out_counts,
-                                                               uint32_t* __restrict__ seg_counts,
-                                                               const uint32_t* __restrict__ out_base_dev) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flags[i]) return;
-  const uint32_t dst = pos[i] + (out_base_dev ? *out_base_dev : 0u);
-  out_mers[dst] = in_mers[i];
-  out_counts[dst] = in_counts[i];
-  atomicAdd(&seg_counts[in_seg[i]], 1u);
-}
-
 
 __global__ void set_u32_kernel(uint32_t* __restrict__ dst, uint32_t v) { *dst = v; }
 __global__ void add_u32_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ acc) { *acc += *a; }

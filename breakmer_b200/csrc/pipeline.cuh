@@ -23,6 +23,8 @@ struct RecordSet {          // one of: reads, soft clips, normal reads (device c
   int64_t kn_rec = 0;
   // host copies of the region boundaries (bases, compacted records): the k-mer stage may run in region chunks
   std::vector<int64_t> reg_base, reg_krec;
+  const int64_t* d_reg_base = nullptr;   // device copies (region_kmers.cuh)
+  const int64_t* d_reg_krec = nullptr;
   int64_t max_reg_bases = 0;          // largest region (bases)
 };
 
@@ -43,6 +45,12 @@ struct Pipeline {
   // upper bounds known from the input offsets (they size arrays and sort keys; results never depend on them)
   int64_t max_reg_records = 0;            // most read records in one region  >= its unique reads
   int64_t max_reg_mers = 0;               // most soft-clip bases (or given mers) in one region >= its sample-only mers
+  // hash-table placement of the k-mer stage (region_kmers.cuh): per region table slots, and the offset of its slice of
+  // the global table when it does not fit shared memory
+  const uint32_t* d_tab_cap = nullptr;
+  const int64_t* d_gtab_off = nullptr;
+  int rk_smem_cap = 1024;
+  int64_t rk_gtab_slots = 0;
   // regions left out of the device pass because a read exceeds the DP's length limit (their status is
   // BK_ERR_CAPACITY, every other region of the batch is processed): reads of those regions are not uploaded
   std::vector<uint8_t> region_skipped;    // empty = none

@@ -65,6 +65,8 @@ void upload_record_set(bk_handle_t h, Arena<false>& A, const char* bases, const 
   rs.kn_rec = (int64_t)koff.size() - 1;
   rs.koff = to_device(h, A, koff.data(), koff.size());
   rs.kseg = to_device(h, A, kseg.data(), kseg.size());
+  rs.d_reg_base = to_device(h, A, rs.reg_base.data(), rs.reg_base.size());
+  rs.d_reg_krec = to_device(h, A, rs.reg_krec.data(), rs.reg_krec.size());
   h2d += n_bases + (n_rec + 1) * 8;
 }
 
@@ -152,6 +154,21 @@ void pipeline_upload_into(bk_handle_t h, Arena<false>& A, const bk_batch_input* 
     upload_record_set(h, A, in->sc_bases, in->sc_off, in->sc_reg_off, R, p.sc, p.h2d_bytes, "soft-clip");
     upload_record_set(h, A, in->normal_bases, in->normal_off, in->normal_reg_off, R, p.normal, p.h2d_bytes, "normal");
     p.max_reg_mers = p.sc.max_reg_bases;        // every sample-only mer of a region is a soft-clip window of it
+    // k-mer stage tables: a power of two of slots > the region's soft-clip windows (its distinct k-mers can never fill
+    // it), in shared memory when that is at most RK_SMEM_CAP_MAX slots, else a slice of the global table
+    std::vector<uint32_t> cap(R ? R : 1, 1024);
+    std::vector<int64_t> goff(R ? R : 1, -1);
+    for (int r = 0; r < R; ++r) {
+      const int64_t n_sc = p.sc.reg_base.empty() ? 0 : p.sc.reg_base[r + 1] - p.sc.reg_base[r];
+      uint64_t c = 1024;
+      while (c <= (uint64_t)n_sc) c <<= 1;
+      if (c > (uint64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: a region has more than 2^31 soft-clip bases");
+      cap[r] = (uint32_t)c;
+      if (c <= (uint64_t)RK_SMEM_CAP_MAX) p.rk_smem_cap = std::max<int>(p.rk_smem_cap, (int)c);
+      else { goff[r] = p.rk_gtab_slots; p.rk_gtab_slots += (int64_t)c; }
+    }
+    p.d_tab_cap = to_device(h, A, cap.data(), cap.size());
+    p.d_gtab_off = to_device(h, A, goff.data(), goff.size());
   }
 }
 
@@ -180,7 +197,7 @@ inline unsigned nblk(int64_t n, int per) { return (unsigned)((n + per - 1) / per
 
 // k-mer windows of the records of regions [r0, r1) of one input set
 void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag, bool rc, uint64_t* keys, uint32_t* vals,
-              int64_t base, int64_t base_rc, const ProbeTable* probe = nullptr) {
+              int64_t base, int64_t base_rc) {
   if (rs.reg_base.empty()) return;
   const int64_t b0 = rs.reg_base[r0], b1 = rs.reg_base[r1];
   if (b1 == b0) return;
@@ -189,7 +206,6 @@ void emit_set(bk_handle_t h, const RecordSet& rs, int r0, int r1, int k, int tag
   E.bases = rs.bases + b0; E.n_bases = b1 - b0; E.rec_off = rs.koff + kr0; E.n_rec = kr1 - kr0; E.rec_seg = rs.kseg + kr0;
   E.rec_mult = nullptr; E.k = k; E.tag = tag; E.emit_rc = rc ? 1 : 0; E.off_shift = b0; E.seg_shift = r0;
   E.keys = keys; E.vals = vals; E.out_base = base; E.out_base_rc = base_rc;
-  if (probe) { E.probe_keys = probe->keys; E.probe_idx = probe->idx; E.probe_mask_dev = probe->mask_dev; E.dead = probe->dead; }
   TimedLaunch t(h->timers, h->st, KF_EMIT);
   kmer_emit_kernel<<<nblk(E.n_bases, EMIT_TILE), EMIT_THREADS, 0, h->st>>>(E);
 }
@@ -367,46 +383,48 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
   } else {
     const int64_t n_keys = 2 * p.ref.n_bases + p.reads.n_bases + p.sc.n_bases + p.normal.n_bases;
     B.n_keys = n_keys;
-    // The sort key is [0 | region | mer]: 2k + region bits + 1 <= 64.  Large k leaves few region bits, so the stage runs
-    // over chunks of regions (one chunk for the usual k); selected mers come out in (region, mer) order either way.
-    const int max_seg_bits = 63 - 2 * k;
-    const int chunk = (int)std::min<int64_t>(R > 0 ? R : 1, int64_t(1) << std::min(max_seg_bits, 16));
     uint64_t* all_m = h->dev.get<uint64_t>(SB ? SB : 1);
     uint32_t* all_c = h->dev.get<uint32_t>(SB ? SB : 1);
-    uint32_t* seg_counts_all = dev_zero<uint32_t>(h, (size_t)R + 1);
-    auto span = [&](const RecordSet& rs, int r0, int r1) { return rs.reg_base.empty() ? int64_t(0) : rs.reg_base[r1] - rs.reg_base[r0]; };
-    for (int r0 = 0; r0 < R; r0 += chunk) {
-      const int r1 = std::min(R, r0 + chunk);
-      const int64_t nr = span(p.ref, r0, r1), nd = span(p.reads, r0, r1), ns = span(p.sc, r0, r1), nn = span(p.normal, r0, r1);
-      // Only the sample's windows are sorted.  The reference (forward + reverse FASTA, Q2) and normal (K4) windows are
-      // streamed past the candidates (case & case_sc) afterwards: a hit removes the candidate.
-      const bool probe_ref = nr > 0 && !p.use_ref_cache, probe_normal = nn > 0;
-      const int64_t nk = nd + ns;
-      if (2 * nr + nk + nn >= (int64_t(1) << 31)) fail(BK_ERR_CAPACITY, "batch: more than 2^31 k-mer windows in one chunk; use fewer regions per call");
-      B.n_sorted += nk;
-      uint64_t* keys = h->dev.get<uint64_t>(nk);
-      uint32_t* vals = h->dev.get<uint32_t>(nk);
-      emit_set(h, p.reads, r0, r1, k, TAG_CASE, false, keys, vals, 0, 0);         // every record, duplicates included (Q3)
-      emit_set(h, p.sc, r0, r1, k, TAG_SC, false, keys, vals, nd, 0);
-      std::function<void(const ProbeTable&)> probe;
-      if (probe_ref || probe_normal)
-        probe = [&, r0, r1](const ProbeTable& T) {
-          if (probe_ref) emit_set(h, p.ref, r0, r1, k, TAG_REF, true, nullptr, nullptr, 0, 0, &T);
-          if (probe_normal) emit_set(h, p.normal, r0, r1, k, TAG_NORMAL, false, nullptr, nullptr, 0, 0, &T);
-        };
-      // this chunk's k-mers go behind those of the earlier chunks: d_S is the running total
-      SelectOut so = sort_and_select(h, keys, vals, nk, k, bits_for((uint64_t)(r1 - r0)), SELECT_SAMPLE_ONLY, r1 - r0, std::min(nd, ns),
-                                     p.use_ref_cache, r0, probe, all_m, all_c, d_S);
-      BK_CUDA(cudaMemcpyAsync(seg_counts_all + r0, so.seg_counts, (size_t)(r1 - r0) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-      add_u32_kernel<<<1, 1, 0, st>>>(so.d_n, d_S);
+    uint32_t* seg_counts = dev_zero<uint32_t>(h, (size_t)R + 1);
+    if (R > 0 && SB > 0) {
+      // one CTA per region: shared-memory hash table of its soft-clip k-mers, reads counted into it, reference and
+      // normal windows streamed past it (region_kmers.cuh)
+      RegionKmerParams K{};
+      K.n_regions = R; K.k = k;
+      auto view = [](const RecordSet& rs) { return RkSet{rs.n_bases > 0 ? rs.bases : nullptr, rs.koff, rs.d_reg_base, rs.d_reg_krec}; };
+      K.sc = view(p.sc); K.reads = view(p.reads); K.normal = view(p.normal);
+      if (p.use_ref_cache) { K.ref_mers = h->ref_cache_mers; K.ref_koff = h->ref_cache_koff; }
+      else K.ref = view(p.ref);
+      K.smem_cap = p.rk_smem_cap; K.tab_cap = p.d_tab_cap; K.gtab_off = p.d_gtab_off;
+      K.gkeys = h->dev.get<uint64_t>(p.rk_gtab_slots ? p.rk_gtab_slots : 1);
+      K.gcnt = h->dev.get<uint32_t>(p.rk_gtab_slots ? p.rk_gtab_slots : 1);
+      K.st_mer = h->dev.get<uint64_t>(p.sc.n_bases); K.st_cnt = h->dev.get<uint32_t>(p.sc.n_bases);
+      K.seg_counts = seg_counts;
+      const size_t smem = (size_t)K.smem_cap * 12 + RK_TILE + 64;
+      BK_CUDA(cudaFuncSetAttribute(region_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int per_sm = std::max<int>(1, (int)((220 * 1024) / (smem + 1024)));
+      const int grid_k = (int)std::min<int64_t>(R, (int64_t)h->sm_count * std::min(per_sm, 4) * 2);
+      {
+        TimedLaunch t(h->timers, st, KF_REGION_KMERS);
+        region_kmer_kernel<<<grid_k, RK_THREADS, smem, st>>>(K);
+      }
+      uint32_t* seg_excl = h->dev.get<uint32_t>(R + 1);
+      uint32_t* stmp = h->dev.get<uint32_t>(scan_tmp_elems(R));
+      {
+        TimedLaunch t(h->timers, st, KF_SCAN, 4);
+        exclusive_scan_u32(seg_counts, seg_excl, R, stmp, d_S, st);
+        widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_S, R, so_off);
+      }
+      {
+        TimedLaunch t(h->timers, st, KF_REGION_KMERS);
+        region_compact_kernel<<<(unsigned)std::min<int64_t>(R, (int64_t)h->sm_count * 16), 256, 0, st>>>(K.st_mer, K.st_cnt, p.sc.d_reg_base, so_off, R,
+                                                                                                       all_m, all_c);
+      }
+      BK_CUDA(cudaGetLastError());
+    } else {
+      BK_CUDA(cudaMemsetAsync(so_off, 0, (R + 1) * sizeof(int64_t), st));
     }
     so_mer = all_m; so_cnt = all_c;
-    uint32_t* seg_excl = h->dev.get<uint32_t>(R + 1);
-    uint32_t* d_tot = h->dev.get<uint32_t>(1);
-    uint32_t* stmp = h->dev.get<uint32_t>(scan_tmp_elems(R));
-    TimedLaunch t(h->timers, st, KF_SCAN, 4);
-    exclusive_scan_u32(seg_counts_all, seg_excl, R, stmp, d_tot, st);
-    widen_scan_kernel<<<nblk(R + 1, 256), 256, 0, st>>>(seg_excl, d_tot, R, so_off);
   }
 
   // ---- 3. inverted index ------------------------------------------------------------------------------
