@@ -62,7 +62,8 @@ struct SpecShared {               // command + results of one speculation round 
 };
 
 // optional phase timing (-DBK_PHASE_PROF, experiments only): cycles per phase, summed over regions
-enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_PREDICT, PH_TOTAL, PH_MAXREGION, PH_COUNT_ };
+enum { PH_NW = 0, PH_FIND, PH_KMERS, PH_FINALIZE, PH_EMIT, PH_PREDICT, PH_TOTAL, PH_MAXREGION,
+       PH_APPLY, PH_REFRESH, PH_SEED, PH_VALID, PH_DP, PH_STAGE, PH_INIT, PH_BIND, PH_COUNT_ };
 #if defined(BK_PHASE_PROF) && !defined(BK_SIM)
 #define BK_PH_BEGIN long long _ph_t0 = clock64();
 #define BK_PH_END(c, ph) (c).ph_cycles[ph] += clock64() - _ph_t0;
@@ -428,6 +429,7 @@ BK_DEV int find_in_slice(const uint8_t* seq, int a, int b, int k, uint64_t code)
 
 // ---- contig.__init__ (:417-426) ---------------------------------------------------------
 BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
+  BK_PH_BEGIN
   c.serial += 1;
   if (c.serial >= (1u << 20)) { c.status = ST_CAPACITY; return; }   // tag width of m_first
   const int lr = stage_read(c, u);
@@ -447,6 +449,7 @@ BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
   c.n_alt = 0; c.n_del = 0;
   if (lane() == 0) { c.checked[seed_s] = c.serial; c.r_buf[u] = c.serial; }    // checked_kmers=[seed] (Q24), buffer={read}
   syncwarp();
+  BK_PH_END(c, PH_INIT)
 }
 
 // ---- contig.check_align (:449-504) and the two overlap cases (:506-546) ------------------
@@ -599,9 +602,13 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
 #ifdef BK_SIM
   for (int w = 0; w < cnt; ++w) spec_stage(*c.P, sp, c.s_reads, w);
 #else
-  if (multi) __syncthreads();
-  spec_stage(*c.P, sp, c.s_reads, 0);
-  if (multi) __syncthreads();
+  {
+    BK_PH_BEGIN
+    if (multi) __syncthreads();
+    spec_stage(*c.P, sp, c.s_reads, 0);
+    if (multi) __syncthreads();
+    BK_PH_END(c, PH_STAGE)
+  }
 #endif
   // 2. warp 0 predicts the contig each later slot will see
   if (lane() == 0) { atomic_add(&c.P->stats[4], 1ull); atomic_add(&c.P->stats[5], (unsigned long long)cnt); }
@@ -629,16 +636,27 @@ BK_DEV void nw_round(RegionCtx& c, int pos, int cnt) {
 #ifdef BK_SIM
   for (int w = 0; w < cnt; ++w) spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, w, nullptr, nullptr, nullptr);
 #else
-  if (multi) __syncthreads();
-  spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol, c.tab);
-  if (multi) __syncthreads();
+  {
+    BK_PH_BEGIN
+    if (multi) __syncthreads();
+    spec_dp(sp, c.s_reads, c.P->read_cap, c.s_contig, c.s_pred, 0, c.edge_all, c.lastcol, c.tab);
+    if (multi) __syncthreads();
+    BK_PH_END(c, PH_DP)
+  }
 #endif
   c.rnd_base = pos; c.rnd_cnt = cnt;
   BK_PH_END(c, PH_NW)
 }
 
 // ---- contig.check_align (:449-504), decision part: v1/v2 come from the round -------------------------------
+BK_DEV bool apply_align_impl(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2);
 BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2) {
+  BK_PH_BEGIN
+  const bool r = apply_align_impl(c, u, seed_s, grow, rd, lr, v1, v2);
+  BK_PH_END(c, PH_APPLY)
+  return r;
+}
+BK_DEV bool apply_align_impl(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2) {
   const int lc = c.clen;
   c.n_align += 1ull;
   c.n_cells += (unsigned long long)lc * (unsigned long long)lr;
@@ -697,7 +715,11 @@ BK_DEV bool round_slot_valid(const RegionCtx& c, int w) {
 
 BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
   bool have = pos < c.rnd_base + c.rnd_cnt;
-  if (have) have = round_slot_valid(c, pos - c.rnd_base);
+  if (have) {
+    BK_PH_BEGIN
+    have = round_slot_valid(c, pos - c.rnd_base);
+    BK_PH_END(c, PH_VALID)
+  }
   if (!have) {
     int cnt = c.st_n - pos;
     if (cnt > c.spec_w) cnt = c.spec_w;
@@ -991,6 +1013,7 @@ BK_DEV void grow(RegionCtx& c) {
   int32_t* Ns = c.NK; int32_t* Nend = c.NK + ASM_KCAP; int32_t* Nm = c.NK + 2 * ASM_KCAP; int32_t* Nb = c.NK + 3 * ASM_KCAP;
   while (c.status == ST_OK) {
     // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
+    BK_PH_BEGIN
     int nn = 0;
     for (int t = 0; t < c.nK; t += WARP) {
       const int e = t + lane();
@@ -1003,6 +1026,7 @@ BK_DEV void grow(RegionCtx& c) {
     }
     c.nNK = nn;
     syncwarp();
+    BK_PH_END(c, PH_REFRESH)
     if (nn == 0) break;
     // The read stream of this snapshot: get_mer_reads (:604-614) for every tuple, in
     // order.  It does not depend on how the alignments turn out (see find_reads).
@@ -1096,7 +1120,12 @@ BK_DEV void assemble_region(RegionCtx& c) {
   c.q_head = 0; c.q_tail = 0; c.n_alt = 0; c.n_del = 0;
   if (c.S == 0) return;                                              // :33-34
   while (c.status == ST_OK) {
-    const int seed = next_seed(c);                                   // has_mers (:318-322): max count must be > 1
+    int seed;
+    {
+      BK_PH_BEGIN
+      seed = next_seed(c);                                           // has_mers (:318-322): max count must be > 1
+      BK_PH_END(c, PH_SEED)
+    }
     if (seed < 0) break;
     if (lane() == 0) atomic_add(&P.stats[3], 1ull);
     const bool queued = setup_contigs(c, seed);
@@ -1116,9 +1145,13 @@ BK_DEV void assemble_region(RegionCtx& c) {
       finish_contig(c, P.rc_thresh, read_len);
     }
     // buff.remove_kmers (:358-360); remove_reads is a no-op (Q10)
-    for (int s = lane(); s < c.S; s += WARP)
-      if (c.mused[s]) { c.alive[s] = 0; c.mused[s] = 0; }
-    syncwarp();
+    {
+      BK_PH_BEGIN
+      for (int s = lane(); s < c.S; s += WARP)
+        if (c.mused[s]) { c.alive[s] = 0; c.mused[s] = 0; }
+      syncwarp();
+      BK_PH_END(c, PH_SEED)
+    }
   }
 }
 
@@ -1183,7 +1216,9 @@ __global__ void __launch_bounds__(32 * W, (CTAS > 0 ? CTAS : (W >= 8 ? 1 : (W ==
   int32_t* s_hash = reinterpret_cast<int32_t*>(s_pred + (size_t)(W - 1) * ASM_CAP);
   SpecShared& sp = *reinterpret_cast<SpecShared*>(s_hash + MER_HASH_SIZE);
   const int64_t slot = blockIdx.x;
-  const int warp = threadIdx.x >> 5;
+  // Roles rotate with the CTA index: the controller (role 0: state machine + stream slot 0) is hardware warp
+  // blockIdx % W, so the controllers of the CTAs resident on an SM do not all sit on the same sub-partition.
+  const int warp = ((int)(threadIdx.x >> 5) + W - (int)(blockIdx.x % W)) % W;
   if (W > 1 && warp > 0) {
     int2* edge = P.w_edge ? P.w_edge + (slot * W + warp) * 2 * ASM_CAP : nullptr;
     uint2* lastcol = P.w_lastcol + (size_t)(slot * W + warp) * ASM_LASTCOL;
@@ -1206,10 +1241,13 @@ __global__ void __launch_bounds__(32 * W, (CTAS > 0 ? CTAS : (W >= 8 ? 1 : (W ==
     w = shfl(w, 0);
     if (w >= P.n_regions) break;
     const int region = P.work_order[w];
+#if defined(BK_PHASE_PROF)
+    const long long t_reg0 = clock64();
+#endif
     bind_region(c, P, region, slot, s_reads, s_contig, s_pred, s_hash, &sp, W);
 #if defined(BK_PHASE_PROF)
     for (int i = 0; i < PH_COUNT_; ++i) c.ph_cycles[i] = 0;
-    const long long t_reg0 = clock64();
+    c.ph_cycles[PH_BIND] = clock64() - t_reg0;
     unsigned long long gt0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt0));
 #endif
@@ -1218,6 +1256,7 @@ __global__ void __launch_bounds__(32 * W, (CTAS > 0 ? CTAS : (W >= 8 ? 1 : (W ==
     c.ph_cycles[PH_TOTAL] = clock64() - t_reg0;
     if (lane() == 0) {
       for (int i = 0; i < PH_MAXREGION; ++i) atomicAdd(&P.stats[8 + i], (unsigned long long)c.ph_cycles[i]);
+      for (int i = PH_MAXREGION + 1; i < PH_COUNT_; ++i) atomicAdd(&P.stats[8 + i], (unsigned long long)c.ph_cycles[i]);
       atomicMax(&P.stats[8 + PH_MAXREGION], (unsigned long long)c.ph_cycles[PH_TOTAL]);
       if (P.prof_regions) {
         for (int i = 0; i < 8; ++i) P.prof_regions[(size_t)region * 12 + i] = (unsigned long long)c.ph_cycles[i];

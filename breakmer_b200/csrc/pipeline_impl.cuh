@@ -290,7 +290,7 @@ void launch_assembly(bk_handle_t h, PendingBatch& B) {
   }
   BK_CUDA(cudaGetLastError());
   B.h_cursor = to_host(h, A.out_cursor, 5);
-  B.h_stats = to_host(h, A.stats, 16);
+  B.h_stats = to_host(h, A.stats, 32);
   B.h_status = to_host(h, A.region_status, (size_t)(R ? R : 1));
   B.h_cells = to_host(h, A.region_cells, (size_t)(R ? R : 1));
 }
@@ -519,7 +519,7 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
   auto zalloc = [&](size_t bytes) { bytes = (bytes + 255) & ~size_t(255); size_t o = zero_bytes; zero_bytes += bytes; return o; };
   const size_t o_mused = zalloc(SB), o_checked = zalloc(SB * 4), o_taken = zalloc(SB * 4), o_first = zalloc(SB * 4);
   const size_t o_rused = zalloc(NUB), o_rdel = zalloc(NUB), o_rq = zalloc(NUB), o_rbuf = zalloc(NUB * 4), o_rin = zalloc(NUB * 4);
-  const size_t o_work = zalloc(sizeof(int)), o_cursor = zalloc(5 * sizeof(unsigned long long)), o_stats = zalloc(16 * sizeof(unsigned long long));
+  const size_t o_work = zalloc(sizeof(int)), o_cursor = zalloc(5 * sizeof(unsigned long long)), o_stats = zalloc(32 * sizeof(unsigned long long));
   uint8_t* zero_lo = h->dev.get<uint8_t>(zero_bytes);
   B.zero_lo = zero_lo; B.zero_bytes = zero_bytes;
   A.m_used = zero_lo + o_mused; A.m_checked = (uint32_t*)(zero_lo + o_checked); A.m_taken = (uint32_t*)(zero_lo + o_taken); A.m_first = (uint32_t*)(zero_lo + o_first);
@@ -664,8 +664,9 @@ void phase_print(bk_handle_t h, const PendingBatch& B) {
   const int R = A.n_regions;
   const unsigned long long* h_stats = B.h_stats;
   const int64_t* h_u_off = B.h_u_off; const int64_t* h_so_off = B.h_so_off;
-  static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "predict", "total", "max_region"};
-  for (int i = 0; i < 8; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
+  static const char* nm[] = {"nw", "find_reads", "kmers", "finalize", "emit", "predict", "total", "max_region",
+                             "apply", "refresh", "seed", "valid", "dp", "stage", "init", "bind"};
+  for (int i = 0; i < 16; ++i) fprintf(stderr, "phase %-10s %12llu cycles\n", nm[i], h_stats[8 + i]);
   fprintf(stderr, "find_reads calls %llu seeds %llu check_align %llu rounds %llu slots %llu\n", h_stats[2], h_stats[3], h_stats[0],
           h_stats[4], h_stats[5]);
   if (!A.prof_regions) return;
