@@ -122,7 +122,7 @@ class BatchOutput:
         self._kmer_str = None
         self.n_regions = R
         self.n_contigs = C
-        self.read_ids = packed.read_ids
+        self._packed = packed                 # read ids are decoded only if somebody asks (contig_records)
         self.so_off = _arr(res.so_off, R + 1, np.int64)
         S = int(self.so_off[-1]) if R >= 0 and len(self.so_off) else 0
         self.so_mers = _arr(res.so_mers, S, np.uint64)
@@ -156,6 +156,10 @@ class BatchOutput:
         self.n_dp_cells = int(res.n_dp_cells)
         self.n_kmer_occurrences = int(res.n_kmer_occurrences)
         self.gpu_ms = float(res.gpu_ms)
+
+    @property
+    def read_ids(self):
+        return self._packed.read_ids
 
     def sample_only(self, r):
         a, b = int(self.so_off[r]), int(self.so_off[r + 1])

@@ -254,9 +254,14 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
       h->dev.reset();
       h->pin.reset();
     }
+    if (n_seq > 0 && seq_off) {                        // the whole table is uploaded: all of it must be a valid offset table
+      if (seq_off[0] != 0) fail(BK_ERR_ARG, "bk_nw_batch: seq_off must start at 0");
+      for (int64_t q = 0; q < n_seq; ++q)
+        if (seq_off[q + 1] < seq_off[q]) fail(BK_ERR_ARG, "bk_nw_batch: seq_off not monotone at %lld", (long long)q);
+    }
     int max_m = 0;
     std::vector<int64_t> ptr_off;
-    int64_t ptr_total = 0, aln_total = 0;
+    int64_t ptr_total = 0, aln_total = 0, aln_end_prev = 0;
     if (want_aln) ptr_off.resize(n_pairs);
     for (int64_t p = 0; p < n_pairs; ++p) {
       const int a = pair_a[p], b = pair_b[p];
@@ -267,6 +272,10 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
         fail(BK_ERR_CAPACITY, "nw: sequence longer than %d bases in pair %lld", NW_MAX_LEN, (long long)p);
       max_m = std::max<int>(max_m, (int)m);
       if (want_aln) {
+        // the two strings of pair p occupy [aln_off[p], aln_off[p] + m + n): non-negative, and not overlapping the next pair's
+        if (aln_off[p] < 0 || (p > 0 && aln_off[p] < aln_end_prev))
+          fail(BK_ERR_ARG, "bk_nw_batch: aln_off[%lld] is negative or overlaps the previous pair's strings", (long long)p);
+        aln_end_prev = aln_off[p] + m + n;
         ptr_off[p] = ptr_total;
         ptr_total += (m + 1) * (n + 1);
         aln_total = std::max<int64_t>(aln_total, aln_off[p] + m + n);

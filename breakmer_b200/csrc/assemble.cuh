@@ -99,6 +99,8 @@ struct AsmParams {
   const int32_t* rk_pos;           // first position of that mer in the read
   // mutable per-mer / per-read state (zero-initialised except m_alive)
   uint8_t* m_alive;                // akmers.mers membership (set by bind_region: homopolymers start dead, Q5)
+  uint64_t* seed_a;                // two buffers of [count : 32 | local index : 32] per mer: the region's seed order is
+  uint64_t* seed_b;                // sorted into one of them by bind_region (Q7)
   uint8_t* m_used;                 // buffer.used_mers
   uint32_t* m_checked;             // contig serial in whose checked_kmers the mer is
   uint32_t* m_taken;               // finalize serial (check_alt_reads' mer_set)
@@ -113,6 +115,8 @@ struct AsmParams {
   int32_t* l_alt;                  // read_batch.alt / .delete, find_reads results (size U each)
   int32_t* l_del;
   int32_t* hit_u; int32_t* hit_pos; int32_t* hit2_u; int32_t* hit2_pos;
+  uint64_t* sort_a; uint64_t* sort_b;  // size U each: sort buffers of find_reads
+  int32_t* l_mused;                    // size S: list form of buffer.used_mers
   // per-warp scratch, slot = global warp index
   uint8_t* w_cseq;                 // ASM_BUF bytes
   int32_t* w_cnt;                  // 4 * ASM_BUF ints: io[2], ot[2]
@@ -159,6 +163,48 @@ BK_DEV int warp_max_i(int v) {
   return v;
 }
 
+// Sort n UNIQUE 64-bit keys (all > 0) in descending order with one warp; a and b are two buffers of n keys, the input
+// is in a, the result is in the buffer returned.  Chunks of a warp are sorted in registers (bitonic over the lanes),
+// then merged pass by pass: every element finds its place in the merged run by a binary search in the neighbouring
+// run.  O(n log^2 n / 32) steps.
+BK_DEV uint64_t* warp_sort_desc(uint64_t* a, uint64_t* b, int n) {
+#ifndef BK_SIM
+  for (int base = 0; base < n; base += WARP) {
+    const int i = base + lane();
+    unsigned long long v = i < n ? (unsigned long long)a[i] : 0ull;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool desc = (lane() & k) == 0, lower = (lane() & j) == 0;
+        v = (lower == desc) ? (v > o ? v : o) : (v < o ? v : o);
+      }
+    if (i < n) a[i] = v;
+  }
+#endif
+  syncwarp();
+  uint64_t* src = a; uint64_t* dst = b;
+  for (int L = WARP; L < n; L <<= 1) {
+    for (int i = lane(); i < n; i += WARP) {
+      const int a0 = (i / (2 * L)) * 2 * L;
+      const int a1 = (a0 + L) < n ? (a0 + L) : n, b1 = (a0 + 2 * L) < n ? (a0 + 2 * L) : n;
+      const uint64_t key = src[i];
+      const bool left = i < a1;
+      int lo = left ? a1 : a0, hi = left ? b1 : a1;      // the other run (descending): count its elements > key
+      const int o0 = lo;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (src[mid] > key) lo = mid + 1; else hi = mid;
+      }
+      dst[a0 + (left ? i - a0 : i - a1) + (lo - o0)] = key;
+    }
+    syncwarp();
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
 // 2-bit code of the k-mer starting at seq[x]; false if it holds a non-ACGT byte
 BK_DEV bool window_code(const uint8_t* seq, int x, int k, uint64_t& code) {
   uint64_t c = 0;
@@ -178,6 +224,7 @@ struct RegionCtx {
   // mers
   int S; int64_t gm0;
   const uint64_t* mer; const uint32_t* cnt;
+  const uint64_t* seed_keys; int seed_cursor;   // mers by (count, mer) descending; first position not yet consumed
   uint8_t* alive; uint8_t* mused; uint32_t* checked; uint32_t* taken; uint32_t* first;
   int32_t* s_hash; bool hash_on;   // shared-memory hash of the region's mer table (find_mer)
   // reads
@@ -187,6 +234,8 @@ struct RegionCtx {
   int32_t* q_read; int32_t* q_seed; int q_head, q_tail;
   int32_t* l_alt; int32_t* l_del; int n_alt, n_del;
   int32_t* hit_u; int32_t* hit_pos; int32_t* hit2_u; int32_t* hit2_pos;
+  uint64_t* sort_a; uint64_t* sort_b;   // find_reads: sort buffers for long posting lists (U keys each)
+  int32_t* l_mused; int n_mused;        // mers in buffer.used_mers since the last remove_kmers
   // read stream of the current snapshot (st_u aliases hit_u) and speculation state
   int st_n;
   int rnd_base, rnd_cnt;          // stream range the last round covers
@@ -847,6 +896,8 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
       if (filter_buffer) c.r_buf[u] = c.serial;
     }
   } else {
+    // long posting list (deep coverage): compact the kept reads, then sort [key | index] with the warp merge sort.
+    // Ascending (key, list order) == descending of the complemented pair; ties keep read order (Q9).
     for (int t = 0; t < n0; t += WARP) {
       const int i = t + lane();
       bool keep = false;
@@ -858,27 +909,21 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
       const unsigned mk = ballot(keep);
       if (keep) {
         const int dst = n + popc(mk & lt);
+        const unsigned key = (unsigned)(((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - c.u_len[u]));
         c.hit2_u[dst] = u;
-        c.hit2_pos[dst] = ((rev ? (ASM_CAP - 1 - pos) : pos) << 12) | (ASM_CAP - 1 - c.u_len[u]);
+        c.sort_a[dst] = ((unsigned long long)(0xFFFFFFu - key) << 32) | (unsigned)(0x7FFFFFFF - dst);
         if (filter_buffer) c.r_buf[u] = c.serial;
       }
       n += popc(mk);
     }
     syncwarp();
-    // stable rank sort (lists are short: at most the reads that contain one k-mer)
-    for (int t = 0; t < n; t += WARP) {
-      const int i = t + lane();
-      if (i < n) {
-        const int key = c.hit2_pos[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-          const int kj = c.hit2_pos[j];
-          rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
-        }
-        c.hit_u[at + rank] = c.hit2_u[i];
-        const int hi = key >> 12;
-        c.hit_pos[at + rank] = rev ? (ASM_CAP - 1 - hi) : hi;
-      }
+    const uint64_t* sorted = warp_sort_desc(c.sort_a, c.sort_b, n);
+    for (int r = lane(); r < n; r += WARP) {
+      const uint64_t kk = sorted[r];
+      const int i = 0x7FFFFFFF - (int)(kk & 0xFFFFFFFFu);
+      const int hi = (int)((0xFFFFFFu - (unsigned)(kk >> 32)) >> 12);
+      c.hit_u[at + r] = c.hit2_u[i];
+      c.hit_pos[at + r] = rev ? (ASM_CAP - 1 - hi) : hi;
     }
   }
   syncwarp();
@@ -887,11 +932,22 @@ BK_DEV int find_reads(RegionCtx& c, int s, bool filter_buffer, bool rev, int at)
   return n;
 }
 
+// buffer.add_used_mer (:334-335): used_mers is a dict; the mers added since the last remove_kmers are also kept in a
+// list so that remove_kmers (:358-360) touches those instead of sweeping the whole table once per seed
+BK_DEV void add_used_mer(RegionCtx& c, int s) {
+  if (!c.mused[s]) {                                                 // (warp-uniform: every lane reads the same byte)
+    syncwarp();
+    if (lane() == 0) { c.mused[s] = 1; c.l_mused[c.n_mused] = s; }
+    c.n_mused += 1;
+  }
+  syncwarp();
+}
+
 // ---- setup_contigs (:11-26, Q20) ---------------------------------------------------------------------
 // returns true if the new contig was queued (it is then the FIFO head and is grown next)
 BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
   const int n = find_reads(c, seed_s, false, false, 0);
-  if (lane() == 0) c.mused[seed_s] = 1;                              // buff.add_used_mer
+  add_used_mer(c, seed_s);                                           // buff.add_used_mer
   syncwarp();
   if (n == 0) return false;
   c.st_n = n;
@@ -1054,7 +1110,7 @@ BK_DEV void grow(RegionCtx& c) {
       c.cur_e = e;
       const int s = Ns[e];
       const int end = Nend[e];
-      if (lane() == 0) c.mused[s] = 1;                                 // buff.add_used_mer (:632)
+      add_used_mer(c, s);                                              // buff.add_used_mer (:632)
       syncwarp();
       for (; pos < end && c.status == ST_OK; ++pos) {
         const int u = c.hit_u[pos];
@@ -1089,27 +1145,25 @@ BK_DEV void finish_contig(RegionCtx& c, int rc_thresh, int read_len) {
 }
 
 // ---- akmers.has_mers + mers.items()[0] (:43-45, :318-322; seed order Q7) ----------------------------------------
-// The reference keeps the mers in an OrderedDict sorted by (count, mer) descending and takes the first remaining one.
-// That is the live mer with the largest (count, local index) -- mers ascend with the index -- found here by a warp
-// arg-max over the region's table (S / 32 steps per seed, a few dozen seeds per region) instead of a global sort.
-// Returns -1 when no live mer with count > 1 is left.
-BK_DEV int next_seed(const RegionCtx& c) {
-  unsigned best_c = 0;
-  int best_s = -1;
-  for (int s = lane(); s < c.S; s += WARP) {
-    if (!c.alive[s]) continue;
-    const unsigned v = c.cnt[s];
-    if (best_s < 0 || v >= best_c) { best_c = v; best_s = s; }       // s ascends within a lane: >= keeps the larger index
+// The reference keeps the mers in an OrderedDict sorted by (count, mer) descending and takes the first remaining one:
+// the first live entry of the region's seed order.  Mers only ever leave akmers, so a cursor over the order suffices;
+// 32 entries are tested per step.  Returns -1 when no live mer with count > 1 is left.
+BK_DEV int next_seed(RegionCtx& c) {
+  while (c.seed_cursor < c.S) {
+    const int i = c.seed_cursor + lane();
+    bool live = false;
+    uint64_t key = 0;
+    if (i < c.S) { key = c.seed_keys[i]; live = c.alive[(int)(key & 0xffffffffu)] != 0; }
+    const unsigned mk = ballot(live);
+    if (mk) {
+      const int first = ffs(mk) - 1;
+      c.seed_cursor += first;
+      const uint64_t k0 = shfl(key, first);
+      return (unsigned)(k0 >> 32) > 1u ? (int)(k0 & 0xffffffffu) : -1;
+    }
+    c.seed_cursor += WARP;
   }
-#ifndef BK_SIM
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-    const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
-    if (os >= 0 && (best_s < 0 || oc > best_c || (oc == best_c && os > best_s))) { best_c = oc; best_s = os; }
-  }
-#endif
-  return (best_s >= 0 && best_c > 1u) ? best_s : -1;
+  return -1;
 }
 
 // ---- init_assembly (:30-63) for one region ------------------------------------------------------------------
@@ -1147,12 +1201,25 @@ BK_DEV void assemble_region(RegionCtx& c) {
     // buff.remove_kmers (:358-360); remove_reads is a no-op (Q10)
     {
       BK_PH_BEGIN
-      for (int s = lane(); s < c.S; s += WARP)
-        if (c.mused[s]) { c.alive[s] = 0; c.mused[s] = 0; }
+      for (int i = lane(); i < c.n_mused; i += WARP) {                // the mers add_used_mer recorded since the last sweep
+        const int s = c.l_mused[i];
+        c.alive[s] = 0; c.mused[s] = 0;
+      }
+      c.n_mused = 0;
       syncwarp();
       BK_PH_END(c, PH_SEED)
     }
   }
+}
+
+// ---- kmers.get_all_kmer_values (:280-285, Q7): the region's mers by (count, mer) descending -----------------------
+// Keys [count | local index] are unique, mers ascend with the index: one warp_sort_desc per region instead of a scan
+// per seed.
+BK_DEV void build_seed_order(RegionCtx& c, uint64_t* a, uint64_t* b) {
+  for (int i = lane(); i < c.S; i += WARP) a[i] = ((unsigned long long)c.cnt[i] << 32) | (unsigned)i;
+  syncwarp();
+  c.seed_keys = warp_sort_desc(a, b, c.S);
+  c.seed_cursor = 0;
 }
 
 BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t slot, uint8_t* s_reads, uint8_t* s_contig,
@@ -1171,6 +1238,8 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
   c.q_read = P.q_read + c.gu0; c.q_seed = P.q_seed + c.gu0;
   c.l_alt = P.l_alt + c.gu0; c.l_del = P.l_del + c.gu0;
   c.hit_u = P.hit_u + c.gu0; c.hit_pos = P.hit_pos + c.gu0; c.hit2_u = P.hit2_u + c.gu0; c.hit2_pos = P.hit2_pos + c.gu0;
+  c.sort_a = P.sort_a + c.gu0; c.sort_b = P.sort_b + c.gu0;
+  c.l_mused = P.l_mused + c.gm0; c.n_mused = 0;
   c.cseq = P.w_cseq + slot * ASM_BUF;
   c.cnt_buf = P.w_cnt + slot * 4 * ASM_BUF;
   c.K = P.w_K + slot * 4 * ASM_KCAP;
@@ -1191,6 +1260,7 @@ BK_DEV void bind_region(RegionCtx& c, const AsmParams& P, int region, int64_t sl
     c.alive[s] = homo ? 0 : 1;
   }
   syncwarp();
+  build_seed_order(c, P.seed_a + c.gm0, P.seed_b + c.gm0);
   build_mer_hash(c);
 }
 

@@ -28,6 +28,8 @@
 
 #include <atomic>
 #include <string>
+#include <exception>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -211,9 +213,22 @@ struct Ingest {
     std::atomic<int> next{0};
     std::vector<std::thread> th;
     th.reserve(nt);
+    // an exception inside a worker (bad_alloc from a growing string, fail()) must not escape its thread -- that would
+    // terminate the host process: the first one is kept and rethrown on the calling thread after the join
+    std::exception_ptr first;
+    std::mutex first_mu;
     for (int t = 0; t < nt; ++t)
-      th.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n;) f(i); });
+      th.emplace_back([&] {
+        try {
+          for (int i; (i = next.fetch_add(1)) < n;) f(i);
+        } catch (...) {
+          std::lock_guard<std::mutex> lk(first_mu);
+          if (!first) first = std::current_exception();
+          next.store(n);                       // stop handing out work
+        }
+      });
     for (auto& x : th) x.join();
+    if (first) std::rethrow_exception(first);
   }
 };
 
@@ -230,8 +245,10 @@ inline bool read_whole_file(const char* path, std::string& out) {
   if (fd < 0) return false;
   out.clear();
   struct stat st;
+  memset(&st, 0, sizeof st);
   size_t have = 0;
-  if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) out.resize((size_t)st.st_size);
+  const bool is_reg = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+  if (is_reg && st.st_size > 0) out.resize((size_t)st.st_size);
   else out.resize(1 << 16);
   bool ok = true;
   for (;;) {
@@ -240,7 +257,7 @@ inline bool read_whole_file(const char* path, std::string& out) {
     if (got < 0) { if (errno == EINTR) continue; ok = false; break; }
     if (got == 0) break;
     have += (size_t)got;
-    if (S_ISREG(st.st_mode) && have == (size_t)st.st_size) break;                        // the common case: one read
+    if (is_reg && have == (size_t)st.st_size) break;                        // the common case: one read
   }
   close(fd);
   out.resize(have);

@@ -514,6 +514,9 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
   A.region_ncontigs = h->dev.get<int32_t>(R ? R : 1);
   A.region_cells = h->dev.get<unsigned long long>(R ? R : 1);
   A.m_alive = h->dev.get<uint8_t>(SB ? SB : 1);            // set by the kernel (bind_region)
+  A.seed_a = h->dev.get<uint64_t>(SB ? SB : 1);            // seed order of each region, sorted by the kernel (bind_region)
+  A.seed_b = h->dev.get<uint64_t>(SB ? SB : 1);
+  A.l_mused = h->dev.get<int32_t>(SB ? SB : 1);
   // everything else starts zeroed (per attempt)
   size_t zero_bytes = 0;
   auto zalloc = [&](size_t bytes) { bytes = (bytes + 255) & ~size_t(255); size_t o = zero_bytes; zero_bytes += bytes; return o; };
@@ -532,6 +535,7 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
   A.l_alt = h->dev.get<int32_t>(NUB ? NUB : 1); A.l_del = h->dev.get<int32_t>(NUB ? NUB : 1);
   A.hit_u = h->dev.get<int32_t>(NUB ? NUB : 1); A.hit_pos = h->dev.get<int32_t>(NUB ? NUB : 1);
   A.hit2_u = h->dev.get<int32_t>(NUB ? NUB : 1); A.hit2_pos = h->dev.get<int32_t>(NUB ? NUB : 1);
+  A.sort_a = h->dev.get<uint64_t>(NUB ? NUB : 1); A.sort_b = h->dev.get<uint64_t>(NUB ? NUB : 1);
   A.prof_regions = getenv("BK_PHASE_PRINT") ? dev_zero<unsigned long long>(h, (size_t)R * 12 + 12) : nullptr;
   B.cap_seq = (unsigned long long)std::max<int64_t>(1 << 20, 8 * p.total_read_bytes);
   B.so_mer = so_mer; B.so_cnt = so_cnt; B.so_off = so_off; B.u_off = u_off; B.u_rec = u_rec; B.u_mult = u_mult;

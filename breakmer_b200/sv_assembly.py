@@ -133,6 +133,67 @@ class contig:
         return self.aseq.counts
 
 
+def _filled(name):
+    def method(self, *a, **kw):
+        self._fill()
+        return getattr(list, name)(self, *a, **kw)
+    method.__name__ = name
+    return method
+
+
+class contig_list(list):
+    """kmers['clusters'] of one target: a list of `contig` objects that are created when the list is first looked at
+    (len() and truth value come straight from the result tables).  A panel batch returns thousands of contigs; building
+    every Python object eagerly costs more than the device pass."""
+
+    def __init__(self, out, c0, c1, objs, kmer_len):
+        list.__init__(self)
+        self._pending = (out, int(c0), int(c1), objs, kmer_len)
+
+    def _fill(self):
+        if self._pending is not None:
+            out, c0, c1, objs, k = self._pending
+            self._pending = None
+            list.extend(self, [contig(out, c, objs, k) for c in range(c0, c1)])
+
+    def __len__(self):
+        if self._pending is not None:
+            return self._pending[2] - self._pending[1]
+        return list.__len__(self)
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(self),))
+
+    __iter__ = _filled("__iter__")
+    __getitem__ = _filled("__getitem__")
+    __setitem__ = _filled("__setitem__")
+    __delitem__ = _filled("__delitem__")
+    __contains__ = _filled("__contains__")
+    __reversed__ = _filled("__reversed__")
+    __eq__ = _filled("__eq__")
+    __ne__ = _filled("__ne__")
+    __add__ = _filled("__add__")
+    __iadd__ = _filled("__iadd__")
+    __mul__ = _filled("__mul__")
+    __repr__ = _filled("__repr__")
+    __hash__ = None
+    append = _filled("append")
+    extend = _filled("extend")
+    insert = _filled("insert")
+    pop = _filled("pop")
+    remove = _filled("remove")
+    index = _filled("index")
+    count = _filled("count")
+    sort = _filled("sort")
+    reverse = _filled("reverse")
+    copy = _filled("copy")
+    clear = _filled("clear")
+
+
 class _AssemblyInput:
     """Region-like view of one init_assembly call for batch.PackedBatch."""
 

@@ -38,7 +38,7 @@ library's host threads (bk_write_contigs).
 import os
 
 from . import batch, get_handle, utils
-from .sv_assembly import contig
+from .sv_assembly import contig, contig_list
 
 
 class _TargetInput:
@@ -117,39 +117,41 @@ class CapacityError(RuntimeError):
 
 def _apply_chunk(targets, pk, res, inputs_k, objs, ingest, write_contigs, failed):
     """Results of one device call -> the state target.compare_kmers leaves behind, for the targets of that call."""
-    status = [int(res.region_status[i]) for i in range(len(targets))]
-    ok = [st == 0 for st in status]
+    import numpy as np
+    n = len(targets)
+    status = np.ctypeslib.as_array(res.region_status, shape=(max(n, 1),))[:n].tolist()
+    join = os.path.join
+    sk_paths = [join(t.paths['kmers'], t.name) + "_sample_kmers.out" for t in targets]
     if ingest == "native":
         ing = _get_ingest()
+        all_ok = not any(status)
         if write_contigs:
             # contig.setup's files for every contig of every completed target in one pass (sv_processor.py:749-782,
             # bk_write_contigs); the reference-side contig.__init__ then skips its own setup() call (INTEGRATION.md)
-            ing.write_contigs(res, pk, [t.paths['contigs'] if g else None for t, g in zip(targets, ok)],
-                              [os.path.join(t.paths['kmers'], t.name + "_sample_kmers_merged.out") if g else None
-                               for t, g in zip(targets, ok)])
+            ing.write_contigs(res, pk, [t.paths['contigs'] if st == 0 else None for t, st in zip(targets, status)],
+                              [p[:-4] + "_merged.out" if st == 0 else None for p, st in zip(sk_paths, status)])
         # the "<mer>\t<count>" files of the completed targets in one multi-threaded sweep (bk_write_sample_kmers)
-        ing.write_sample_kmers(res, pk.k, [os.path.join(t.paths['kmers'], t.name + "_sample_kmers.out") if g else None
-                                           for t, g in zip(targets, ok)])
+        ing.write_sample_kmers(res, pk.k, sk_paths if all_ok else [p if st == 0 else None for p, st in zip(sk_paths, status)])
     out = batch.BatchOutput(res, pk)
     ctg_reg_off = out.ctg_reg_off.tolist()
     so_off = out.so_off.tolist()
     for i, trgt in enumerate(targets):
-        if not ok[i]:
+        if status[i] != 0:
             failed.append(trgt.name)
             continue
-        trgt.files['sample_kmers'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers.out")
+        files = trgt.files
+        files['sample_kmers'] = sk_paths[i]
         if ingest != "native":
-            with open(trgt.files['sample_kmers'], 'w') as f:
+            with open(sk_paths[i], 'w') as f:
                 for mer, cnt in out.sample_only(i).items():
                     f.write("\t".join([mer, str(cnt)]) + "\n")
         kmers = trgt.kmers
         kmers['ref'] = {}; kmers['case'] = {}; kmers['case_sc'] = {}
         logger = getattr(trgt, "logger", None)
         if logger is not None and logger.isEnabledFor(20):
-            logger.info('Writing %d sample-only kmers to file %s' % (so_off[i + 1] - so_off[i], trgt.files['sample_kmers']))
-        trgt.files['kmer_clusters'] = os.path.join(trgt.paths['kmers'], trgt.name + "_sample_kmers_merged.out")
-        k = inputs_k[i]
-        kmers['clusters'] = [contig(out, c, objs, k) for c in range(ctg_reg_off[i], ctg_reg_off[i + 1])]
+            logger.info('Writing %d sample-only kmers to file %s' % (so_off[i + 1] - so_off[i], sk_paths[i]))
+        files['kmer_clusters'] = sk_paths[i][:-4] + "_merged.out"
+        kmers['clusters'] = contig_list(out, ctg_reg_off[i], ctg_reg_off[i + 1], objs, inputs_k[i])
         trgt.cleaned_read_recs = None
         kmers['case_only'] = {}
 
@@ -160,15 +162,15 @@ def _pack_targets(targets, ingest, slot=0):
     if ingest == "native":
         get = lambda t, key: (t.files.get(key) if hasattr(t.files, "get") else None)   # noqa: E731
         k = int(targets[0].params.get_kmer_size())
-        if any(int(t.params.get_kmer_size()) != k for t in targets):
+        params = {id(t.params): t.params for t in targets}                  # (targets of a run share one params object)
+        if any(int(p.get_kmer_size()) != k for p in params.values()):
             raise ValueError("one k per batch")
         nfq = [get(t, 'normal_fq') for t in targets]
         pk = _get_ingest(slot).files([t.files['target_ref_fn'][0] for t in targets], [t.files['cleaned_fq'] for t in targets],
                                  [t.files['sv_sc_unmapped_fa'] for t in targets], normal=nfq if any(nfq) else None,
                                  k=k, rc_thresh=int(targets[0].params.get_sr_thresh('min')),
                                  names=[t.name for t in targets])
-        for i, t in enumerate(targets):             # target.read_len is what get_fastq_reads returned (utils.py:236,246)
-            pk.read_len[i] = int(t.read_len)
+        pk.read_len[:len(targets)] = [t.read_len for t in targets]   # what get_fastq_reads returned (utils.py:236,246)
         return pk, [k] * len(targets), _LazyReads(pk)
     if ingest == "python":
         inputs = [_TargetInput(t) for t in targets]
@@ -178,10 +180,14 @@ def _pack_targets(targets, ingest, slot=0):
     raise ValueError("ingest must be 'python' or 'native'")
 
 
-def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False, devices=None, max_targets=2048):
-    """target.compare_kmers() for many targets: one device pass (or, with `devices=[0, 1, ...]`, the targets sharded by
-    region over several GPUs of the box: breakmer_b200.shard, one host thread per device, chunks of at most max_targets
-    handed out largest-first, no collective; results are applied to the targets in name order).
+def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False, devices=None, max_targets=160, inflight=3):
+    """target.compare_kmers() for many targets (the region loop of sv_processor.py:185-201 as one call).
+
+    The targets are cut into chunks of at most max_targets, most expensive first (static cost, breakmer_b200.shard), and
+    the chunks are pipelined: `inflight` of them are kept on the device at once (bk_batch_submit / bk_batch_wait) so the
+    serial tail of one chunk's assembly overlaps the bulk of the next.  With `devices=[0, 1, ...]` the chunks are handed
+    out dynamically to one host thread per GPU (region sharding, no collective); results are applied to the target objects
+    as chunks complete.
 
     Targets that exceed a device limit do not disturb the others: everything else completes, then CapacityError lists
     them (their state is untouched)."""
@@ -192,23 +198,33 @@ def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False,
     if ingest not in ("python", "native"):
         raise ValueError("ingest must be 'python' or 'native'")
     failed = []
-    if devices is None or len(devices) <= 1:
-        dev = device if not devices else devices[0]
-        for a in range(0, len(targets), max_targets):
-            chunk = targets[a:a + max_targets]
-            pk, ks, objs = _pack_targets(chunk, ingest)
-            res = batch.run(get_handle(dev), pk, decode=False)
-            _apply_chunk(chunk, pk, res, ks, objs, ingest, write_contigs, failed)
+    devices = list(devices) if devices else [device]
+    if len(targets) <= max_targets and len(devices) == 1:
+        pk, ks, objs = _pack_targets(targets, ingest)
+        res = batch.run(get_handle(devices[0]), pk, decode=False)
+        _apply_chunk(targets, pk, res, ks, objs, ingest, write_contigs, failed)
     else:
-        _sharded(targets, list(devices), ingest, write_contigs, max_targets, failed)
+        _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed)
     if failed:
         raise CapacityError(sorted(failed))
 
 
-def _sharded(targets, devices, ingest, write_contigs, max_targets, failed):
-    """Region-sharded multi-GPU pass: sv_processor.py:185-201 over `devices` (see shard.run_sharded)."""
+_pipes = {}
+
+
+def _get_pipe(dev, inflight):
+    """The calling thread's DevicePipeline (its handles keep their arenas from call to call)."""
     import threading
     from . import shard
+    key = (threading.get_ident(), dev, inflight)
+    if key not in _pipes:
+        _pipes[key] = shard.DevicePipeline(dev, inflight=inflight)
+    return _pipes[key]
+
+
+def _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed):
+    """Chunked, pipelined (and with several devices region-sharded) pass: sv_processor.py:185-201 over `devices`."""
+    import threading
     costs = [_target_cost(t) for t in targets]
     order = sorted(range(len(targets)), key=lambda i: (-costs[i], i))
     n_chunks = max(len(devices), (len(targets) + max_targets - 1) // max_targets)
@@ -228,11 +244,12 @@ def _sharded(targets, devices, ingest, write_contigs, max_targets, failed):
             cursor[0] += 1
             return c
 
-    def worker(dev):
-        pipe = None
+    def worker(dev, own_pipe):
+        from . import shard
         n_sub = 0
+        pipe = None
         try:
-            pipe = shard.DevicePipeline(dev, inflight=2)
+            pipe = shard.DevicePipeline(dev, inflight=inflight) if own_pipe else _get_pipe(dev, inflight)
 
             def drain_one():
                 res, pk, tag = pipe.pop(decode=False)
@@ -249,39 +266,40 @@ def _sharded(targets, devices, ingest, write_contigs, max_targets, failed):
                 chunk = [targets[i] for i in idx]
                 if pipe.full():
                     drain_one()
-                # (a native ingest buffer is reused call to call: two of them alternate under the two batches in flight)
-                pk, ks, objs = _pack_targets(chunk, ingest, slot=n_sub % 2)
+                # (a native ingest buffer is reused call to call: `inflight` of them rotate under the batches in flight)
+                pk, ks, objs = _pack_targets(chunk, ingest, slot=n_sub % inflight)
                 n_sub += 1
                 pipe.submit(pk, (chunk, ks, objs))
             while pipe.pending():
                 drain_one()
         except Exception as e:                           # noqa: BLE001 -- re-raised on the calling thread
             errors.append(e)
+            if pipe is not None and not own_pipe:        # a cached pipeline with batches in flight is not reusable
+                _pipes.pop((threading.get_ident(), dev, inflight), None)
+                pipe.close()
         finally:
-            if pipe is not None:
+            if pipe is not None and own_pipe:
                 pipe.close()
 
-    threads = [threading.Thread(target=worker, args=(d,)) for d in devices]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    if len(devices) == 1:
+        worker(devices[0], False)                        # one device: the calling thread drives it (handles are kept)
+    else:
+        threads = [threading.Thread(target=worker, args=(d, True)) for d in devices]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     if errors:
         raise errors[0]
 
 
 def _target_cost(trgt):
-    """Static cost of a target before the device pass (shard.region_cost on what the target object knows)."""
+    """Static cost of a target before the device pass: shard.region_cost's read terms on the number of distinct read
+    sequences the target object already holds (O(1); the byte term needs file sizes and is left out)."""
     from . import shard
     recs = getattr(trgt, "cleaned_read_recs", None)
-    n = sum(len(g) for g in recs.values()) if recs else 0
-    nbytes = 0
-    for key in ('cleaned_fq', 'sv_sc_unmapped_fa'):
-        try:
-            nbytes += os.path.getsize(trgt.files[key])
-        except (OSError, KeyError, TypeError):
-            pass
-    return shard.COST_CELLS_PER_READ2 * n * n + shard.COST_CELLS_PER_READ * n + shard.COST_CELLS_PER_BYTE * nbytes + 1.0
+    n = len(recs) if recs else 0
+    return shard.COST_CELLS_PER_READ2 * n * n + shard.COST_CELLS_PER_READ * n + 1.0
 
 
 def compare_kmers(target, device=0, ingest="python"):

@@ -39,6 +39,10 @@ extern "C" int sim_assemble_region(
   P.so_off = so_off; P.so_mer = mers; P.so_cnt = counts;
   // seed order and the homopolymer filter are evaluated inside the assembler (next_seed, bind_region)
   std::vector<uint8_t> alive(n_mers + 1), mused(n_mers + 1, 0);
+  std::vector<uint64_t> seed_a(n_mers + 1), seed_b(n_mers + 1);
+  P.seed_a = seed_a.data(); P.seed_b = seed_b.data();
+  std::vector<int32_t> l_mused(n_mers + 1);
+  P.l_mused = l_mused.data();
   // posting lists (kernel: index)
   std::vector<std::vector<std::pair<int, int>>> post(n_mers);
   for (int u = 0; u < n_reads; ++u) {
@@ -86,6 +90,8 @@ extern "C" int sim_assemble_region(
   P.r_buf = r_buf.data(); P.r_inreads = r_inreads.data();
   P.q_read = q_read.data(); P.q_seed = q_seed.data(); P.l_alt = l_alt.data(); P.l_del = l_del.data();
   P.hit_u = hit_u.data(); P.hit_pos = hit_pos.data(); P.hit2_u = hit2_u.data(); P.hit2_pos = hit2_pos.data();
+  std::vector<uint64_t> sort_a(U), sort_b(U);
+  P.sort_a = sort_a.data(); P.sort_b = sort_b.data();
   std::vector<uint8_t> w_cseq(ASM_BUF);
   std::vector<int32_t> w_cnt(4 * ASM_BUF), w_K(4 * ASM_KCAP), w_NK(4 * ASM_KCAP), w_diff(ASM_CAP + 1);
   std::vector<uint64_t> w_wcode(ASM_CAP);
