@@ -167,7 +167,12 @@ BK_DEV int warp_max_i(int v) {
 // is in a, the result is in the buffer returned.  Chunks of a warp are sorted in registers (bitonic over the lanes),
 // then merged pass by pass: every element finds its place in the merged run by a binary search in the neighbouring
 // run.  O(n log^2 n / 32) steps.
-BK_DEV uint64_t* warp_sort_desc(uint64_t* a, uint64_t* b, int n) {
+#ifdef BK_SIM
+inline
+#else
+static __device__ __noinline__                           // (rarely executed, several call sites: keep one copy out of line)
+#endif
+uint64_t* warp_sort_desc(uint64_t* a, uint64_t* b, int n) {
 #ifndef BK_SIM
   for (int base = 0; base < n; base += WARP) {
     const int i = base + lane();
@@ -460,7 +465,12 @@ BK_DEV void set_superseq(RegionCtx& c, int u, const uint8_t* rd, int lr, int sta
 }
 
 // first occurrence of mer `code` in seq[a, b) (str.find on the slice); -1 if none
-BK_DEV int find_in_slice(const uint8_t* seq, int a, int b, int k, uint64_t code) {
+#ifdef BK_SIM
+inline
+#else
+static __device__ __noinline__                           // (rare paths, five call sites)
+#endif
+int find_in_slice(const uint8_t* seq, int a, int b, int k, uint64_t code) {
   const int nwin = b - a - k + 1;
   int best = 0x7fffffff;
   for (int t = 0; t < nwin; t += WARP) {
@@ -558,8 +568,13 @@ BK_DEV void spec_stage(const AsmParams& P, SpecShared* sp, uint8_t* s_reads, int
   if (lane() == 0) sp->lr[w] = lr;
   syncwarp();
 }
-BK_DEV void spec_dp(SpecShared* sp, const uint8_t* s_reads, int read_cap, const uint8_t* s_contig, const uint8_t* s_pred, int w,
-                    int2* edge, uint2* lastcol, uint8_t* tab) {
+#if defined(BK_SIM)
+inline
+#else
+static __device__ __noinline__                           // one copy of the sweeps: the controller and the aligner warps share it
+#endif
+void spec_dp(SpecShared* sp, const uint8_t* s_reads, int read_cap, const uint8_t* s_contig, const uint8_t* s_pred, int w,
+             int2* edge, uint2* lastcol, uint8_t* tab) {
   const uint8_t* rd = s_reads + (size_t)w * read_cap;
   const int lr = sp->lr[w];
   const int b = sp->abuf[w];

@@ -516,6 +516,7 @@ __device__ __forceinline__ void nw_trace_walk(const uint8_t* __restrict__ cs, co
 //   - for the other direction only if the first one fails the identity test (:461-464) or the scores tie.
 // The direction that is not read is typically the one in which the read overhangs the contig: a low-scoring path of
 // dozens of single gap steps, i.e. dozens of dependent table look-ups.  Its origin is left at the end cell.
+#define BK_TAB_ST(p, v) __stcg((p), (v))
 #ifdef BK_NW_PROF
 __device__ long long bk_nw_prof[8];
 #define BK_NW_T(i) if (lane() == 0) bk_nw_prof[i] = clock64();
@@ -540,8 +541,8 @@ __device__ __forceinline__ void nw_dual_trace(const uint8_t* __restrict__ cs, in
   }
   int diag = 2 * (jfirst - 1);
   int last0 = 0, last1 = col[C - 1];
-  const bool own = L == (m - 1) / C;
-  int rc0_next = rs[0], rc1_next = rs[1];
+  const bool own = L == (m - 1) / C;             // (the slot of column m in that lane is OWN_C, resolved at compile time:
+  int rc0_next = rs[0], rc1_next = rs[1];        //  selecting it at run time costs 7 % of the sweep)
   BK_NW_T(0)
   // ---- pass 1: scores ----
   for (int t = 0; t < steps; ++t) {
@@ -577,12 +578,12 @@ __device__ __forceinline__ void nw_dual_trace(const uint8_t* __restrict__ cs, in
       }
       diag = h1;
       last0 = r0[C - 1]; last1 = col[C - 1];
-      if (own) lastcol[q] = make_uint2((unsigned)r0[OWN_C], (unsigned)col[OWN_C]);
-      // low bytes of the 2 x C cells of this step -> table[(t, L)]
+      if (own) BK_TAB_ST(lastcol + q, make_uint2((unsigned)r0[OWN_C], (unsigned)col[OWN_C]));
+      // low bytes of the 2 x C cells of this step -> table[(t, L)]  (st.global.cg: the table is read back once, from L2)
       if (C == 4) {
         const unsigned w0 = __byte_perm(__byte_perm(r0[0], r0[1], 0x0040), __byte_perm(r0[2], r0[3], 0x0040), 0x5410);
         const unsigned w1 = __byte_perm(__byte_perm(col[0], col[1], 0x0040), __byte_perm(col[2], col[3], 0x0040), 0x5410);
-        reinterpret_cast<uint2*>(tab)[t * 32 + L] = make_uint2(w0, w1);
+        BK_TAB_ST(reinterpret_cast<uint2*>(tab) + (t * 32 + L), make_uint2(w0, w1));
       } else {
         unsigned w[4];
 #pragma unroll
@@ -590,7 +591,7 @@ __device__ __forceinline__ void nw_dual_trace(const uint8_t* __restrict__ cs, in
           w[g] = __byte_perm(__byte_perm(r0[4 * g], r0[4 * g + 1], 0x0040), __byte_perm(r0[4 * g + 2], r0[4 * g + 3], 0x0040), 0x5410);
           w[2 + g] = __byte_perm(__byte_perm(col[4 * g], col[4 * g + 1], 0x0040), __byte_perm(col[4 * g + 2], col[4 * g + 3], 0x0040), 0x5410);
         }
-        reinterpret_cast<uint4*>(tab)[t * 32 + L] = make_uint4(w[0], w[1], w[2], w[3]);
+        BK_TAB_ST(reinterpret_cast<uint4*>(tab) + (t * 32 + L), make_uint4(w[0], w[1], w[2], w[3]));
       }
     }
   }
@@ -683,12 +684,7 @@ __device__ __forceinline__ void nw_dual_dispatch(const uint8_t* __restrict__ cs,
       }
       return;
     }
-    switch ((m - 1) & 3) {
-      case 0: nw_dual_warp_fast<4, 0>(cs, m, rs, n, e0, e1, lastcol, out); break;
-      case 1: nw_dual_warp_fast<4, 1>(cs, m, rs, n, e0, e1, lastcol, out); break;
-      case 2: nw_dual_warp_fast<4, 2>(cs, m, rs, n, e0, e1, lastcol, out); break;
-      default: nw_dual_warp_fast<4, 3>(cs, m, rs, n, e0, e1, lastcol, out); break;
-    }
+    nw_dual_warp_fast<4>(cs, m, rs, n, e0, e1, lastcol, out);      // (rare now: contigs beyond the score table's reach)
   } else {
     nw_dual_warp_fast<8>(cs, m, rs, n, e0, e1, lastcol, out);
   }
