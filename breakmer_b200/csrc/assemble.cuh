@@ -264,6 +264,7 @@ struct RegionCtx {
   uint64_t* wcode; int32_t* diff; int2* edge;
   uint32_t serial, fin_serial;
   bool ct_setup, ct_finalized;
+  bool setup_queued;              // setup_contigs: the new contig went into buffer.contigs
   int ct_init_read;
   int status;
   int n_out;
@@ -511,49 +512,7 @@ BK_DEV void contig_init(RegionCtx& c, int seed_s, int u) {
   BK_PH_END(c, PH_INIT)
 }
 
-// ---- contig.check_align (:449-504) and the two overlap cases (:506-546) ------------------
-BK_DEV void contig_overlap_read(RegionCtx& c, const NwOut& v1, int u, const uint8_t* rd, int lr, bool grow) {
-  const int lc = c.clen;
-  if (v1.j0 == 0) {                                                 // :508 (prej == len always, Q15)
-    set_superseq(c, u, rd, lr, v1.i0, v1.prei);
-    if (grow) set_kmers(c);
-    return;
-  }
-  const int plen = lr - v1.prei;                                    // post_seq = read[aln[4]:]
-  if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
-  for (int x = lane(); x < plen; x += WARP) {
-    const uint8_t ch = rd[v1.prei + x];
-    c.cseq[c.c0 + lc + x] = ch; c.s_contig[lc + x] = ch;
-  }
-  c.clen = lc + plen;
-  if (plen > 0) c.seq_ver += 1;
-  syncwarp();
-  const int n = (int)c.u_mult[u];
-  const bool io = c.u_io[u] != 0;
-  set_counts(c, v1.j0, lc, n, io);                                  // add_postseq :243-250
-  extend_counts(c, plen, n, io, true);
-  if (grow) append_kmers(c, c.s_contig, lc - (c.k - 1), (c.k - 1) + plen, ORDER_FOR);   // :521,525-527
-}
-
-BK_DEV void read_overlap_contig(RegionCtx& c, const NwOut& v2, int u, const uint8_t* rd, int lr, bool grow) {
-  const int n = (int)c.u_mult[u];
-  const bool io = c.u_io[u] != 0;
-  if (v2.j0 == 0) {                                                 // :531
-    set_counts(c, v2.i0, v2.prei, n, io);
-    return;
-  }
-  const int plen = v2.j0;                                           // pre_seq = read[0:aln[3]]
-  const int lc = c.clen;
-  if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return; }
-  for (int x = lane(); x < plen; x += WARP) c.cseq[c.c0 - plen + x] = rd[x];
-  c.c0 -= plen; c.clen = lc + plen;
-  c.seq_ver += 1;
-  sync_contig_to_smem(c);
-  set_counts(c, v2.i0, v2.prei, n, io);                             // add_preseq :255-262 (old coordinates)
-  extend_counts(c, plen, n, io, false);
-  const int head = (c.k - 1) < lc ? (c.k - 1) : lc;
-  if (grow) append_kmers(c, c.s_contig, 0, plen + head, ORDER_REV);  // :539,543-545
-}
+// (contig.check_align and its two overlap cases, :449-546, are apply_align below: decision first, then ONE site per action)
 
 // ---- the two olc.nw calls of check_align (:451-452), one warp per read ------------------------------
 // Executed by every warp of the CTA (warp w takes stream slot w of the round).
@@ -720,6 +679,9 @@ BK_DEV bool apply_align(RegionCtx& c, int u, int seed_s, bool grow, const uint8_
   BK_PH_END(c, PH_APPLY)
   return r;
 }
+// contig.check_align (:449-504) with contig_overlap_read (:506-528) and read_overlap_contig (:530-546).  The decision
+// tree is evaluated first and yields one action; every action's body exists once (instruction footprint).
+enum { ACT_SUPERSEQ = 1, ACT_COUNTS, ACT_APPEND, ACT_PREPEND };
 BK_DEV bool apply_align_impl(RegionCtx& c, int u, int seed_s, bool grow, const uint8_t* rd, int lr, const NwOut& v1, const NwOut& v2) {
   const int lc = c.clen;
   c.n_align += 1ull;
@@ -731,35 +693,75 @@ BK_DEV bool apply_align_impl(RegionCtx& c, int u, int seed_s, bool grow, const u
   const bool bad2 = (4 * s2 < mn) || (200 * s2 < 179 * (v2.prej - v2.j0));
   if (bad1 && bad2) return false;
   if (s1 == s2 && v1.j0 == 0 && v1.i0 == 0 && lc == lr) return true;            // :466 (Q16)
+  // contig_overlap_read(v1): the read replaces the contig if the alignment starts at the contig's first base (:508; prej ==
+  // len always, Q15), else its overhang is appended.  read_overlap_contig(v2): counts only if the alignment starts at the
+  // read's first base (:531), else the read's head is prepended.
+  const int act_cr = v1.j0 == 0 ? ACT_SUPERSEQ : ACT_APPEND;
+  const int act_rc = v2.j0 == 0 ? ACT_COUNTS : ACT_PREPEND;
+  int act;
+  if (s1 == s2) {
+    if (lc < lr || v1.j0 == 0) act = ACT_SUPERSEQ;                   // :471
+    else if (lr < lc || v2.j0 == 0) act = ACT_COUNTS;                // :480
+    else {
+      // :485-496 -- alignment strings minus '-' are the aligned spans themselves
+      const uint64_t code = c.mer[seed_s];
+      const int i11 = find_in_slice(c.s_contig, v1.j0, lc, c.k, code);
+      const int i12 = find_in_slice(rd, v1.i0, v1.prei, c.k, code);
+      const int i21 = find_in_slice(rd, v2.j0, lr, c.k, code);
+      const int i22 = find_in_slice(c.s_contig, v2.i0, v2.prei, c.k, code);
+      const int d1 = i11 > i12 ? i11 - i12 : i12 - i11;
+      const int d2 = i21 > i22 ? i21 - i22 : i22 - i21;
+      act = 0;
+      if (i11 > -1 && i12 > -1) {
+        if ((i21 == -1 && i22 == -1) || d2 > d1) act = act_cr;
+      } else if (i21 > -1 && i22 > -1) {
+        if ((i11 == -1 && i12 == -1) || d2 < d1) act = act_rc;
+      }
+      if (act == 0) return false;
+    }
+  } else {
+    act = s1 > s2 ? act_cr : act_rc;
+  }
   const int n = (int)c.u_mult[u];
   const bool io = c.u_io[u] != 0;
-  if (s1 == s2) {
-    if (lc < lr || v1.j0 == 0) {                                     // :471
-      set_superseq(c, u, rd, lr, v1.i0, v1.prei);
-      if (grow) set_kmers(c);
-      return true;
+  // k-mers to add to the contig's list afterwards (grow only): window range and order
+  int k_base = 0, k_len = 0, k_order = ORDER_MID;
+  bool k_reset = false;
+  if (act == ACT_SUPERSEQ) {
+    set_superseq(c, u, rd, lr, v1.i0, v1.prei);
+    k_reset = true; k_len = c.clen;                                  // set_kmers (:548-550)
+  } else if (act == ACT_COUNTS) {
+    set_counts(c, v2.i0, v2.prei, n, io);
+    return true;
+  } else if (act == ACT_APPEND) {
+    const int plen = lr - v1.prei;                                    // post_seq = read[aln[4]:]
+    if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return true; }
+    for (int x = lane(); x < plen; x += WARP) {
+      const uint8_t ch = rd[v1.prei + x];
+      c.cseq[c.c0 + lc + x] = ch; c.s_contig[lc + x] = ch;
     }
-    if (lr < lc || v2.j0 == 0) {                                     // :480
-      set_counts(c, v2.i0, v2.prei, n, io);
-      return true;
-    }
-    // :485-496 -- alignment strings minus '-' are the aligned spans themselves
-    const uint64_t code = c.mer[seed_s];
-    const int i11 = find_in_slice(c.s_contig, v1.j0, lc, c.k, code);
-    const int i12 = find_in_slice(rd, v1.i0, v1.prei, c.k, code);
-    const int i21 = find_in_slice(rd, v2.j0, lr, c.k, code);
-    const int i22 = find_in_slice(c.s_contig, v2.i0, v2.prei, c.k, code);
-    const int d1 = i11 > i12 ? i11 - i12 : i12 - i11;
-    const int d2 = i21 > i22 ? i21 - i22 : i22 - i21;
-    if (i11 > -1 && i12 > -1) {
-      if ((i21 == -1 && i22 == -1) || d2 > d1) { contig_overlap_read(c, v1, u, rd, lr, grow); return true; }
-    } else if (i21 > -1 && i22 > -1) {
-      if ((i11 == -1 && i12 == -1) || d2 < d1) { read_overlap_contig(c, v2, u, rd, lr, grow); return true; }
-    }
-    return false;
+    c.clen = lc + plen;
+    if (plen > 0) c.seq_ver += 1;
+    syncwarp();
+    set_counts(c, v1.j0, lc, n, io);                                  // add_postseq :243-250
+    extend_counts(c, plen, n, io, true);
+    k_base = lc - (c.k - 1); k_len = (c.k - 1) + plen; k_order = ORDER_FOR;   // :521,525-527
+  } else {
+    const int plen = v2.j0;                                           // pre_seq = read[0:aln[3]]
+    if (lc + plen > NW_MAX_LEN) { c.status = ST_CAPACITY; return true; }
+    for (int x = lane(); x < plen; x += WARP) c.cseq[c.c0 - plen + x] = rd[x];
+    c.c0 -= plen; c.clen = lc + plen;
+    c.seq_ver += 1;
+    sync_contig_to_smem(c);
+    set_counts(c, v2.i0, v2.prei, n, io);                             // add_preseq :255-262 (old coordinates)
+    extend_counts(c, plen, n, io, false);
+    const int head = (c.k - 1) < lc ? (c.k - 1) : lc;
+    k_base = 0; k_len = plen + head; k_order = ORDER_REV;             // :539,543-545
   }
-  if (s1 > s2) contig_overlap_read(c, v1, u, rd, lr, grow);
-  else read_overlap_contig(c, v2, u, rd, lr, grow);
+  if (grow) {
+    if (k_reset) { c.ct_setup = true; c.nK = 0; }
+    append_kmers(c, c.s_contig, k_base, k_len, k_order);
+  }
   return true;
 }
 
@@ -958,33 +960,6 @@ BK_DEV void add_used_mer(RegionCtx& c, int s) {
   syncwarp();
 }
 
-// ---- setup_contigs (:11-26, Q20) ---------------------------------------------------------------------
-// returns true if the new contig was queued (it is then the FIFO head and is grown next)
-BK_DEV bool setup_contigs(RegionCtx& c, int seed_s) {
-  const int n = find_reads(c, seed_s, false, false, 0);
-  add_used_mer(c, seed_s);                                           // buff.add_used_mer
-  syncwarp();
-  if (n == 0) return false;
-  c.st_n = n;
-  c.round_seed = seed_s;
-  c.seed_anchor = ASM_CAP + c.hit_pos[0];                            // contig_init puts the first read at ASM_CAP
-  c.rnd_base = 0; c.rnd_cnt = 1;                                     // slot 0 is the contig's own read: nothing to align
-  const int u0 = c.hit_u[0];
-  contig_init(c, seed_s, u0);
-  bool queued = false;
-  if (!c.r_used[u0]) {                                               // buff.add_contig(read, ct) (Q20)
-    if (lane() == 0) c.r_used[u0] = 1;
-    queued = true;
-    syncwarp();
-  }
-  for (int h = 1; h < n && c.status == ST_OK; ++h) {
-    if (lane() == 0) c.r_buf[c.hit_u[h]] = c.serial;                 // self.buffer.add(read.id)
-    check_read(c, seed_s, h, false);
-  }
-  if (c.status == ST_OK) finalize(c, true);
-  return queued;
-}
-
 // ---- set_kmer_locs (:434-438, Q25) + emit the accepted contig -------------------------------------------
 BK_DEV void emit_contig(RegionCtx& c) {
   BK_PH_BEGIN
@@ -1076,70 +1051,105 @@ BK_DEV void emit_contig(RegionCtx& c) {
   BK_PH_END(c, PH_EMIT)
 }
 
-// ---- contig.grow (:616-649) ------------------------------------------------------------------------------
-BK_DEV void grow(RegionCtx& c) {
-  if (!c.ct_setup) set_kmers(c);
+// ---- setup_contigs (:11-26, Q20) and contig.grow (:616-649) ------------------------------------------------------------
+// Both walk a read stream with contig.check_read and close every k-mer's reads with contig.finalize; they are one function
+// here so that the (large) check_read / finalize / find_reads code exists once in the kernel -- the controller's
+// instruction footprint is what its speed depends on most.
+//   GROW_SETUP       the stream is the reads of the seed k-mer (slot 0 is the contig's own read); then the contig is
+//                    grown (it was queued: it is the FIFO head)
+//   GROW_SETUP_ONLY  same stream, but the contig was NOT queued (its first read was already used, Q20): check_read and
+//                    finalize still run against it, then it is dropped
+//   GROW_ONLY        a contig popped from the FIFO
+enum { GROW_ONLY = 0, GROW_SETUP = 1, GROW_SETUP_ONLY = 2 };
+BK_DEV void grow(RegionCtx& c, int mode, int seed_s) {
+  bool setup = mode != GROW_ONLY;
+  if (!setup && !c.ct_setup) set_kmers(c);
   const unsigned lt = lane_lt_mask();
   int32_t* Ks = c.K; int32_t* Km = c.K + 2 * ASM_KCAP; int32_t* Kb = c.K + 3 * ASM_KCAP;
   int32_t* Ns = c.NK; int32_t* Nend = c.NK + ASM_KCAP; int32_t* Nm = c.NK + 2 * ASM_KCAP; int32_t* Nb = c.NK + 3 * ASM_KCAP;
   while (c.status == ST_OK) {
-    // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
-    BK_PH_BEGIN
-    int nn = 0;
-    for (int t = 0; t < c.nK; t += WARP) {
-      const int e = t + lane();
-      bool keep = false;
-      int s = 0, meta = 0, xb = 0;
-      if (e < c.nK) { s = Ks[e]; meta = Km[e]; xb = Kb[e]; keep = c.checked[s] != c.serial; }
-      const unsigned mk = ballot(keep);
-      if (keep) { const int dst = nn + popc(mk & lt); Ns[dst] = s; Nm[dst] = meta; Nb[dst] = xb; }
-      nn += popc(mk);
+    int nn = 1;
+    if (!setup) {
+      // refresh_kmers (:601): tuples whose mer is not in checked_kmers, order kept
+      BK_PH_BEGIN
+      nn = 0;
+      for (int t = 0; t < c.nK; t += WARP) {
+        const int e = t + lane();
+        bool keep = false;
+        int s = 0, meta = 0, xb = 0;
+        if (e < c.nK) { s = Ks[e]; meta = Km[e]; xb = Kb[e]; keep = c.checked[s] != c.serial; }
+        const unsigned mk = ballot(keep);
+        if (keep) { const int dst = nn + popc(mk & lt); Ns[dst] = s; Nm[dst] = meta; Nb[dst] = xb; }
+        nn += popc(mk);
+      }
+      c.nNK = nn;
+      syncwarp();
+      BK_PH_END(c, PH_REFRESH)
+      if (nn == 0) break;
     }
-    c.nNK = nn;
-    syncwarp();
-    BK_PH_END(c, PH_REFRESH)
-    if (nn == 0) break;
-    // The read stream of this snapshot: get_mer_reads (:604-614) for every tuple, in
-    // order.  It does not depend on how the alignments turn out (see find_reads).
+    // The read stream: setup -- find_reads(seed) over every remaining read (:14); grow -- get_mer_reads (:604-614) for
+    // every tuple of the snapshot, in order.  It does not depend on how the alignments turn out (see find_reads).
     int st = 0;
     for (int e = 0; e < nn; ++e) {
 #ifndef BK_SIM
-      if (e + 1 < nn) {                 // warm L1/L2 for the next tuple's posting list while this one is processed
+      if (!setup && e + 1 < nn) {       // warm L1/L2 for the next tuple's posting list while this one is processed
         const int64_t na = c.P->post_off[c.gm0 + Ns[e + 1]];
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c.P->post_read + na + lane()));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c.P->post_pos + na + lane()));
       }
 #endif
-      const int meta = Nm[e];
+      const int meta = setup ? 0 : Nm[e];
       const int lth = meta & 1, order = (meta >> 1) & 3;
-      const bool rev = (order == ORDER_MID) ? (lth == 0) : (order == ORDER_FOR);
-      st += find_reads(c, Ns[e], true, rev, st);
-      if (lane() == 0) Nend[e] = st;
+      const bool rev = setup ? false : ((order == ORDER_MID) ? (lth == 0) : (order == ORDER_FOR));
+      st += find_reads(c, setup ? seed_s : Ns[e], !setup, rev, st);
+      if (!setup && lane() == 0) Nend[e] = st;
     }
     c.st_n = st;
-    c.round_seed = -1;
     c.rnd_base = 0; c.rnd_cnt = 0;
     syncwarp();
     int pos = 0;
+    if (setup) {
+      add_used_mer(c, seed_s);                                         // buff.add_used_mer (:15)
+      if (st == 0) { c.setup_queued = false; return; }                 // no read holds the seed: nothing to set up
+      c.round_seed = seed_s;
+      c.seed_anchor = ASM_CAP + c.hit_pos[0];                          // contig_init puts the first read at ASM_CAP
+      c.rnd_cnt = 1;                                                   // slot 0 is the contig's own read: nothing to align
+      const int u0 = c.hit_u[0];
+      contig_init(c, seed_s, u0);
+      c.setup_queued = false;
+      if (!c.r_used[u0]) {                                             // buff.add_contig(read, ct) (Q20)
+        if (lane() == 0) c.r_used[u0] = 1;
+        c.setup_queued = true;
+        syncwarp();
+      }
+      pos = 1;
+    } else {
+      c.round_seed = -1;
+    }
     for (int e = 0; e < nn && c.status == ST_OK; ++e) {
       c.cur_e = e;
-      const int s = Ns[e];
-      const int end = Nend[e];
-      add_used_mer(c, s);                                              // buff.add_used_mer (:632)
+      const int s = setup ? seed_s : Ns[e];
+      const int end = setup ? st : Nend[e];
+      if (!setup) add_used_mer(c, s);                                  // buff.add_used_mer (:632)
       syncwarp();
       for (; pos < end && c.status == ST_OK; ++pos) {
         const int u = c.hit_u[pos];
-        if (check_read(c, s, pos, true)) {
-          if (c.r_queued[u] == 1) {                                    // buff.remove_contig(read.id) :639
+        if (setup && lane() == 0) c.r_buf[u] = c.serial;               // self.buffer.add(read.id) (:22)
+        if (check_read(c, s, pos, !setup)) {
+          if (!setup && c.r_queued[u] == 1) {                          // buff.remove_contig(read.id) :639
             if (lane() == 0) c.r_queued[u] = 2;
             syncwarp();
           }
         }
       }
       if (c.status != ST_OK) break;
-      finalize(c, false);
-      if (lane() == 0) c.checked[s] = c.serial;
+      finalize(c, setup);
+      if (!setup && lane() == 0) c.checked[s] = c.serial;
       syncwarp();
+    }
+    if (setup) {
+      setup = false;
+      if (!c.setup_queued) return;                                     // (Q20) the contig is not grown
     }
   }
 }
@@ -1197,21 +1207,23 @@ BK_DEV void assemble_region(RegionCtx& c) {
     }
     if (seed < 0) break;
     if (lane() == 0) atomic_add(&P.stats[3], 1ull);
-    const bool queued = setup_contigs(c, seed);
-    if (queued && c.status == ST_OK) {                               // it is the FIFO head (the queue was empty)
-      grow(c);
-      finish_contig(c, P.rc_thresh, read_len);
-    }
-    while (c.status == ST_OK) {                                      // while len(buff.contigs) > 0 (:50)
-      while (c.q_head < c.q_tail && c.r_queued[c.q_read[c.q_head]] != 1) ++c.q_head;
-      if (c.q_head >= c.q_tail) break;
-      const int u = c.q_read[c.q_head], s = c.q_seed[c.q_head];
-      ++c.q_head;
-      if (lane() == 0) c.r_queued[u] = 2;
-      syncwarp();
-      contig_init(c, s, u);
-      grow(c);
-      finish_contig(c, P.rc_thresh, read_len);
+    // setup_contigs (:11-26) for the seed, then `while len(buff.contigs) > 0` (:50): the set-up contig first if it was
+    // queued (the queue was empty, so it is the FIFO head), then whatever check_alt_reads queued
+    int mode = GROW_SETUP;
+    for (;;) {
+      if (mode == GROW_ONLY) {
+        while (c.q_head < c.q_tail && c.r_queued[c.q_read[c.q_head]] != 1) ++c.q_head;
+        if (c.q_head >= c.q_tail) break;
+        const int u = c.q_read[c.q_head], s = c.q_seed[c.q_head];
+        ++c.q_head;
+        if (lane() == 0) c.r_queued[u] = 2;
+        syncwarp();
+        contig_init(c, s, u);
+      }
+      grow(c, mode, seed);
+      if (c.status != ST_OK) break;
+      if (mode == GROW_ONLY || c.setup_queued) finish_contig(c, P.rc_thresh, read_len);
+      mode = GROW_ONLY;
     }
     // buff.remove_kmers (:358-360); remove_reads is a no-op (Q10)
     {
