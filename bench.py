@@ -557,7 +557,10 @@ def gpu_arm(args):
                      "kmer_occurrences": cnt["kmer_occ"], "sorted_keys": cnt["sorted"], "sample_only_kmers": cnt["sample_only"],
                      "note": "this rank's share of one step"},
         "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": asm_gbs / hbm_peak, "traffic": 34850560 if default_shape else None, "peak_source": peak_src,
+                     "frac": asm_gbs / hbm_peak, "traffic": 224056832 if default_shape else None, "peak_source": peak_src,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r2_assemble_kernel.md): 52 MB "
+                                     "read + 172 MB written; the writes are the per-warp DP score tables (scratch, ~280 MB footprint) "
+                                     "being evicted from L2, not re-reads of the inputs",
                      "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": asm_ms_per_launch,
                      "share_of_step": asm_ms / sum(lat_ms) if lat_ms else None,
                      "note": "the dominant kernel is an integer-issue/latency bound DP state machine that moves "
@@ -627,8 +630,12 @@ def kstage_rooflines(ktimes, kt_steps, pk, out, hbm_peak):
         "scan": 12 * n_sorted,
         "group_reads": nd + 12 * n_rec + 13 * NU,
         "index": nd + 24 * NU,
-        "aux_sort": 0,
+        "aux_sort": 0,                                     # (radix passes of the read-grouping and index sorts: launch-latency bound,
+                                                           #  a few hundred thousand elements; no meaningful HBM figure)
         "prep": 16 * out.n_regions,
+        # one CTA per region (region_kmers.cuh): every input base once (reference strand counted once)
+        # + (w + 4) B per sample-only k-mer out
+        "region_kmers": nd + ns + nr + nn + 12 * n_only,
     }
     res = {}
     whole_sort_ms = 0.0
