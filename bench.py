@@ -93,6 +93,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
+        self._stop_evt.wait(0.12)            # first sample well inside the timed region
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
@@ -102,7 +103,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)     # NVML queries contend with kernel launches of every process on the box: keep them sparse
+            self._stop_evt.wait(0.25)    # NVML queries contend with kernel launches of every process on the box: keep them sparse
 
     def stop(self):
         self._stop_evt.set()
@@ -238,6 +239,16 @@ class Dist:
             raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
+            # every rank keeps to its own share of the host cores (its one driving thread, the ingest threads of the
+            # from-files leg): ranks do not migrate onto each other's cores
+            try:
+                cores = sorted(os.sched_getaffinity(0))
+                per = max(1, len(cores) // self.world)
+                mine = cores[self.local_rank * per:(self.local_rank + 1) * per]
+                if mine and not os.environ.get("BK_BENCH_NO_PIN"):
+                    os.sched_setaffinity(0, mine)
+            except (AttributeError, OSError):
+                pass
             dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
 
     def barrier(self):
@@ -274,73 +285,145 @@ class Dist:
 
 
 class ShardRun:
-    """One workload, partitioned by region over the ranks; this rank's share as resident / host-buffer passes."""
+    """One workload, sharded by region over the ranks.
 
-    def __init__(self, D, workload, total, inflight, spec_width=0, call_regions=CALL_REGIONS, replicate=False):
+    The regions are cut into calls of at most `call_regions` by `shard.assign_lpt` on the static cost model (calls of
+    similar cost; every rank derives the same calls, no communication).  With one rank the calls simply cycle.  With
+    several ranks the calls of every pass are handed out through a host-side work queue -- an atomic counter in the
+    torch.distributed store, the only cross-rank traffic besides the final host-side gather: a rank takes the next call
+    when it has a free slot, so ranks whose calls turn out slower (per-region cost is only weakly predictable, and a
+    500-region call's time is not proportional to its DP work) simply take fewer.  `--static-shards` pins call c to
+    rank c % N instead (the plain LPT partition)."""
+
+    def __init__(self, D, workload, total, inflight, spec_width=0, call_regions=CALL_REGIONS, replicate=False, static=False):
         from breakmer_b200 import _lib, batch, shard, synth
         self.D = D
         self.workload = workload
         self.total = total
+        self.static = static or D.world == 1
         t0 = time.time()
-        # every rank derives the same partition from the same static costs (no communication)
         self.regions = [synth.config_region(workload, i) for i in range(total)]
         self.costs = [shard.region_cost(r) for r in self.regions]
-        self.owned = shard.assign_lpt(self.costs, D.world)
-        if replicate:                               # diagnostic: every rank runs the regions rank 0 owns (system effects only)
-            self.owned = [self.owned[0]] * D.world
-        self.mine = self.owned[D.rank]
-        self.chunks = shard.chunk_indices(self.mine, call_regions)
-        self.packed = [batch.PackedBatch([self.regions[i] for i in c]).pin() for c in self.chunks]
+        if total < D.world:
+            raise SystemExit("bench.py: %d regions cannot be sharded over %d ranks" % (total, D.world))
+        n_calls = max(D.world, (total + call_regions - 1) // call_regions)
+        self.calls = [c for c in shard.assign_lpt(self.costs, n_calls) if c]
+        if replicate:                               # diagnostic: every call is call 0 (system effects only)
+            self.calls = [self.calls[0]] * len(self.calls)
+        nc = len(self.calls)
+        # static: this rank only ever runs its own calls; dynamic: any call may come its way
+        self.mine = [c for c in range(nc) if c % D.world == D.rank] if self.static else list(range(nc))
+        self.packed = {c: batch.PackedBatch([self.regions[i] for i in self.calls[c]]).pin() for c in self.mine}
         self.gen_s = time.time() - t0
-        nc = max(1, len(self.chunks))
-        self.n_handles = nc * ((max(1, inflight) + nc - 1) // nc)      # a multiple of the chunk count
+        nm = max(1, len(self.mine))
+        reps = (max(1, inflight) + nm - 1) // nm
+        if not self.static:
+            reps = max(2, reps)                     # a rank may draw the same call twice in a row
+        self.inflight = max(1, inflight)
+        self.n_handles = nm * reps                  # every call resident on the same number of handles
         self.handles = [_lib.Handle(D.local_rank) for _ in range(self.n_handles)]
         for h in self.handles:
             h.set_option("blocking_sync", 1)        # the single host thread of this rank sleeps while it waits
             if spec_width:
                 h.set_option("spec_width", spec_width)
-        self.k = self.packed[0].k if self.packed else 15
+        self.handle_call = [self.mine[j % nm] for j in range(self.n_handles)] if self.mine else []
+        self.k = next(iter(self.packed.values())).k if self.packed else 15
         self.last = {}
 
-    def warm_passes(self, w=3):
-        """passes that give every handle at least three calls (its arenas are final after the second)"""
-        nc = max(1, len(self.packed))
-        return max(w, (3 * self.n_handles + nc - 1) // nc)
+    def warm(self, resident, w=3):
+        """untimed: every handle runs at least three calls of its own (with host buffers: every call that may come its
+        way, so its arenas have their final size), then `w` passes the way the timed region runs them"""
+        from breakmer_b200 import batch
+        nm = max(1, len(self.mine))
+        for rep in range(3 if resident else max(3, nm if not self.static else 3)):
+            for j, h in enumerate(self.handles):
+                batch.submit(h, None if resident else self.packed[self.mine[(j + rep) % nm]])
+            for h in self.handles:
+                batch.wait(h, decode=False)
+        self.run_pass(max(3, w), resident)
 
     def upload(self):
         from breakmer_b200 import batch
         for j, h in enumerate(self.handles):
-            if self.packed:
-                batch.upload(h, self.packed[j % len(self.packed)])
+            batch.upload(h, self.packed[self.handle_call[j]])
+
+    def _call_of(self, t):
+        """item t -> call: pass t // nc runs every call once; the order rotates by one per pass so that ranks drawing
+        items in lockstep do not keep drawing the same call"""
+        nc = len(self.calls)
+        return (t + t // nc) % nc
+
+    def _items(self, steps):
+        """the (pass, call) items of `steps` passes this rank runs, in order: its own calls (static) or whatever the
+        cross-rank queue hands out (dynamic)"""
+        nc = len(self.calls)
+        n_items = steps * nc
+        if self.static:
+            for t in range(n_items):
+                if self._call_of(t) in self.packed:
+                    yield t
+            return
+        from breakmer_b200 import shard
+        queue = shard.CallQueue(self.workload, n_items, self.D.world)
+        starve = os.environ.get("BK_BENCH_TEST_STARVE_RANK")       # test hook: that rank takes nothing of the last pass
+        t = 0
+        while True:
+            if starve is not None and int(starve) == self.D.rank and t >= n_items - 2 * nc:
+                return
+            t = queue.take()
+            if t is None:
+                return
+            yield t
 
     def run_pass(self, steps, resident, flush=None):
-        """steps passes over this rank's chunks from ONE host thread: bk_batch_submit keeps n_handles batches queued
-        on the device, bk_batch_wait collects them in order.  Returns the results of the last pass per chunk."""
+        """steps passes over the calls from ONE host thread: bk_batch_submit keeps up to n_handles batches queued on the
+        device, bk_batch_wait collects them in submission order.  Keeps the results of the last pass per call."""
         from breakmer_b200 import batch
-        nc = len(self.packed)
+        nc = len(self.calls)
         if nc == 0:
             return
-        H = self.n_handles
-        items = steps * nc
+        n_items = steps * nc
         t_sub = t_wait = 0.0
-        for t in range(items):
-            h = self.handles[t % H]
-            if t >= H:
-                t0 = time.perf_counter()
-                self.last[(t - H) % nc] = (t % H, batch.wait(h, decode=False))
-                t_wait += time.perf_counter() - t0
-            if flush is not None and H == 1:
+        fly = []                                    # (handle index, item) in submission order
+        busy = set()
+        done = 0
+
+        def drain_one():
+            nonlocal t_wait, done
+            j, t = fly.pop(0)
+            t0 = time.perf_counter()
+            res = batch.wait(self.handles[j], decode=False)
+            t_wait += time.perf_counter() - t0
+            busy.discard(j)
+            done += 1
+            if t >= n_items - nc:                   # the last pass: what the sharding check looks at
+                self.last[self._call_of(t)] = (j, res)
+
+        self.last = {}
+        for t in self._items(steps):
+            c = self._call_of(t)
+            cand = [j for j in range(self.n_handles) if (not resident or self.handle_call[j] == c)]
+            while len(fly) >= self.inflight:
+                drain_one()
+            while True:
+                free = [j for j in cand if j not in busy]
+                if free:
+                    break
+                drain_one()
+            j = free[0]
+            if flush is not None and self.n_handles == 1:
                 flush.zero_()                       # sequential mode: flush L2 between timed steps
             t0 = time.perf_counter()
-            batch.submit(h, None if resident else self.packed[t % nc])
+            batch.submit(self.handles[j], None if resident else self.packed[c])
             t_sub += time.perf_counter() - t0
-        for t in range(max(0, items - H), items):
-            t0 = time.perf_counter()
-            self.last[t % nc] = (t % H, batch.wait(self.handles[t % H], decode=False))
-            t_wait += time.perf_counter() - t0
+            fly.append((j, t))
+            busy.add(j)
+        while fly:
+            drain_one()
         post = [float(r.host_post_ms) for _j, r in self.last.values()]
-        self.host_ms = {"submit_ms_per_call": 1000.0 * t_sub / items, "wait_ms_per_call": 1000.0 * t_wait / items,
-                        "of_which_result_tables_ms": sum(post) / max(1, len(post)),
+        self.items_run = done
+        self.host_ms = {"submit_ms_per_call": 1000.0 * t_sub / max(1, done), "wait_ms_per_call": 1000.0 * t_wait / max(1, done),
+                        "of_which_result_tables_ms": sum(post) / max(1, len(post)), "calls_run_by_this_rank": done,
                         "note": "host thread: time inside bk_batch_submit (copies + launches) and bk_batch_wait (mostly blocked on the device)"}
 
     def timed(self, steps, resident, flush=None):
@@ -361,7 +444,7 @@ class ShardRun:
         return self.D.max(self.last_local_dev_s), self.D.max(wall)
 
     def counters(self):
-        """work counters of one pass over this rank's chunks (from the last results)"""
+        """work counters of the calls of the last pass this rank ran (summed over ranks: one whole pass)"""
         tot = {"contigs": 0, "check_align": 0, "dp_cells": 0, "kmer_occ": 0, "sorted": 0, "sample_only": 0}
         for c, (_j, res) in self.last.items():
             tot["contigs"] += int(res.n_contigs); tot["check_align"] += int(res.n_check_align)
@@ -370,8 +453,9 @@ class ShardRun:
         return tot
 
     def check_against_single_gpu(self):
-        """Host-side gather of the per-region result digests in target-name order; rank 0 runs ALL regions on its own
-        GPU and compares.  Returns (ok, digest of digests, regions) on rank 0, (None, None, n) elsewhere."""
+        """Host-side gather of the per-region result digests in target-name order (from whichever rank ran each call of
+        the last pass); rank 0 runs ALL regions on its own GPU and compares.  Returns (ok, digest of digests, regions) on
+        rank 0, (None, None, n) elsewhere."""
         from breakmer_b200 import batch, shard
         local = {}
         for c, (_j, res) in sorted(self.last.items()):
@@ -381,12 +465,12 @@ class ShardRun:
         ok, dig = None, None
         if self.D.rank == 0:
             single = {}
-            for c in shard.chunk_indices(range(self.total), CALL_REGIONS):
-                if self.D.world == 1 and len(self.chunks) == 1 and c == self.chunks[0]:
-                    single.update(local)          # one rank, one call: it IS the single-GPU run
-                    continue
-                pk = batch.PackedBatch([self.regions[i] for i in c])
-                single.update(shard.region_digests(batch.run(self.handles[0], pk), pk))
+            if self.D.world == 1 and len(self.calls) == 1:
+                single.update(local)              # one rank, one call: it IS the single-GPU run
+            else:
+                for c in shard.chunk_indices(range(self.total), CALL_REGIONS):
+                    pk = batch.PackedBatch([self.regions[i] for i in c])
+                    single.update(shard.region_digests(batch.run(self.handles[0], pk), pk))
             ok = bool(merged == dict(sorted(single.items())) and list(merged) == sorted(r.name for r in self.regions))
             dig = shard.digest_of_digests(merged)
         return ok, dig, len(local)
@@ -400,12 +484,14 @@ class ShardRun:
 def sharded_summary(D, workload, total, args, steps):
     """value / e2e / sharding check of one more workload (the c5_strong and c3_sharded keys of the line)."""
     # (C5 calls have long tails -- 2 % of the regions carry all the assembly work -- so more of them are kept in flight)
-    run = ShardRun(D, workload, total, max(args.inflight, 8) if workload == "C5" else args.inflight, args.spec_width)
+    run = ShardRun(D, workload, total, max(args.inflight, 8) if workload == "C5" else args.inflight, args.spec_width,
+                   static=args.static_shards)
     try:
         run.upload()
-        run.run_pass(run.warm_passes(), True)
+        run.warm(True)
         dev_s, _ = run.timed(steps, True)
-        run.run_pass(run.warm_passes(), False)
+        by_rank = [round(v, 3) for v in D.gather_floats(1000.0 * run.last_local_dev_s / steps)]
+        run.warm(False)
         _, e2e_s = run.timed(steps, False)
         cnt = run.counters()
         ok, dig, _n = run.check_against_single_gpu()
@@ -414,7 +500,11 @@ def sharded_summary(D, workload, total, args, steps):
                 "value": total * steps / dev_s, "unit": UNIT, "ms_per_pass": 1000.0 * dev_s / steps,
                 "e2e": {"value": total * steps / e2e_s, "unit": UNIT, "ms_per_pass": 1000.0 * e2e_s / steps},
                 "sample_only_kmers_per_s": D.sum(float(cnt["sample_only"])) * steps / dev_s,
-                "regions_per_rank": [len(o) for o in run.owned], "calls_per_pass_this_rank": len(run.chunks),
+                "dp_cells_per_pass": int(D.sum(float(cnt["dp_cells"]))),
+                "calls_per_pass": len(run.calls), "regions_per_call": [len(c) for c in run.calls][:16],
+                "calls_run_by_rank": [int(v) for v in D.gather_floats(float(run.items_run))],
+                "assignment": "static (call c on rank c % N)" if run.static else "dynamic (host-side queue over the ranks)",
+                "device_ms_per_pass_by_rank": by_rank,
                 "equal_to_single_gpu_run": ok, "result_digest": dig, "generate_s": round(run.gen_s, 1)}
     finally:
         run.close()
@@ -429,8 +519,8 @@ def gpu_arm(args):
     total = cfg["regions_total"]
     hbm_peak, peak_src = load_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    run = ShardRun(D, args.workload, total, args.inflight, args.spec_width, replicate=args.replicate)
-    H = run.n_handles
+    run = ShardRun(D, args.workload, total, args.inflight, args.spec_width, replicate=args.replicate, static=args.static_shards)
+    H = min(run.inflight, run.n_handles)
     h = run.handles[0]
 
     # ---- resident-input run: `value` -----------------------------------------------------
@@ -438,7 +528,7 @@ def gpu_arm(args):
     # (one handle = one stream + its own buffers each), so the tail of one batch -- a few regions with long serial
     # chains -- overlaps the bulk of the next.  inflight=1 is the strictly sequential mode (L2 flushed between steps).
     run.upload()
-    run.run_pass(run.warm_passes(args.warmup), True)   # >= W untimed warm-up steps, >= 3 calls on every handle (arenas reach steady state)
+    run.warm(True, args.warmup)            # >= W untimed warm-up steps, >= 3 calls on every handle (arenas reach steady state)
     # per-kernel device times: a short SEQUENTIAL pass on one handle with the library's CUDA-event timers on
     # (in the pipelined region kernels of different batches share the SMs, so their durations are not comparable)
     lat_ms = []
@@ -459,41 +549,45 @@ def gpu_arm(args):
     host_resident = run.host_ms
     clocks = sampler.stop()
     rank_ms = D.gather_floats(1000.0 * run.last_local_dev_s / args.steps)
+    calls_by_rank = [int(v) for v in D.gather_floats(float(run.items_run))]
     gpu_launches = 0
     for hh in run.handles:
         gpu_launches += int(sum(v[1] for v in hh.kernel_times().values()))
     value = total * args.steps / dev_s
-    cnt = run.counters()
+    cnt = {k: int(D.sum(float(v))) for k, v in sorted(run.counters().items())}     # one whole step, all ranks
     n_cells_rank = cnt["dp_cells"]
-    kmers_per_s = D.sum(float(cnt["sample_only"])) * args.steps / dev_s
-    cells_all = D.sum(float(n_cells_rank))
+    kmers_per_s = float(cnt["sample_only"]) * args.steps / dev_s
+    cells_all = float(n_cells_rank)
 
     # ---- end to end through the C ABI with host buffers: `e2e` ---------------------------------------
-    run.run_pass(run.warm_passes(), False)
+    run.warm(False)
     _, e2e_s = run.timed(args.steps, False)
     host_e2e = run.host_ms
     e2e_value = total * args.steps / e2e_s
-    pk0 = run.packed[0]
-    h2d = sum(pk.input_bytes + 8 * (len(pk.read_off) + len(pk.sc_off) + len(pk.ref_off)) + len(pk.read_flags) for pk in run.packed)
-    d2h = 0
+    pk0 = run.packed[run.mine[0]]
     outs = {c: batch.BatchOutput(res, run.packed[c]) for c, (_j, res) in run.last.items()}
+    # bytes of one whole step (all calls): inputs from the packed arrays, results from the calls this rank ran last
+    h2d = D.sum(float(sum(run.packed[c].input_bytes + 8 * (len(run.packed[c].read_off) + len(run.packed[c].sc_off) + len(run.packed[c].ref_off)) +
+                          len(run.packed[c].read_flags) for c in outs)))
+    d2h = 0
     for out in outs.values():
         d2h += int(out.seq.nbytes + out.kmer_locs.nbytes + out.indel_only.nbytes + out.others.nbytes + out.reads.nbytes +
                    out.kmer_mer.nbytes + 2 * out.kmer_pos.nbytes + out.so_mers.nbytes + out.so_counts.nbytes +
                    out.uniq_rec.nbytes + out.uniq_mult.nbytes)
+    d2h = D.sum(float(d2h))
     ok, digest, _nl = (None, None, 0) if args.replicate else run.check_against_single_gpu()
 
     # ---- same steps with the persistent reference k-mer cache (reported beside the headline, not as it) ----
     ref_cache = None
-    if not args.no_ref_cache_leg and len(run.packed) == 1:
-        regions_mine = [run.regions[i] for i in run.mine]
+    if not args.no_ref_cache_leg and len(run.calls) == 1:
+        regions_mine = [run.regions[i] for i in run.calls[0]]
         pk_nr = batch.PackedBatch(regions_mine, with_ref=False).pin()
         saved = run.packed
         for hh in run.handles:
             hh.ref_cache_build([r.ref_fwd for r in regions_mine], pk0.k)
-        run.packed = [pk_nr]
+        run.packed = {0: pk_nr}
         run.upload()
-        run.run_pass(run.warm_passes(), True)
+        run.warm(True)
         rc_s, _ = run.timed(args.steps, True)
         ref_cache = {"value": total * args.steps / rc_s, "unit": UNIT, "ms_per_step": 1000.0 * rc_s / args.steps,
                      "note": "reference k-mers of the targets counted once and kept on the device (bk_ref_cache_build), as the "
@@ -504,7 +598,7 @@ def gpu_arm(args):
 
     # ---- ingest row: the same steps starting from FASTA/FASTQ FILES (tmpfs) -------------------
     from_files = None
-    if not args.no_ingest_leg and len(run.packed) == 1:
+    if not args.no_ingest_leg:
         from_files = ingest_leg(args, D, run, total)
 
     # ---- the Python drop-in a BreaKmer user calls (sv_processor.compare_kmers_batch on target objects) -------------
@@ -515,7 +609,10 @@ def gpu_arm(args):
     # ---- roofline of the dominant kernel (the assembler) and of the k-mer stage kernels -----------------------------
     asm_ms, asm_n = ktimes["assemble"]
     asm_ms_per_launch = asm_ms / max(1, asm_n)
-    out0 = outs[0]
+    # (the call the sequential pass above timed: the one resident on this rank's first handle; with the work queue a rank
+    # may have run none of the calls of the last pass, so this is a run of its own)
+    pk0 = run.packed[run.handle_call[0]]
+    out0 = batch.run(run.handles[0], pk0)
     n_only0 = int(out0.so_off[-1])
     NU = int(out0.uniq_reg_off[-1])
     read_lens = pk0.read_off[1:] - pk0.read_off[:-1]
@@ -537,8 +634,10 @@ def gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": cfg,
-        "run": {"batches_in_flight": H, "host_threads_per_rank": 1, "calls_per_step_this_rank": len(run.chunks),
-                "regions_per_rank": [len(o) for o in run.owned], "input_bytes_this_rank": sum(pk.input_bytes for pk in run.packed),
+        "run": {"batches_in_flight": H, "host_threads_per_rank": 1, "calls_per_step": len(run.calls),
+                "regions_per_call": [len(c) for c in run.calls][:16], "calls_run_by_rank": calls_by_rank,
+                "assignment": "static (call c on rank c % N)" if run.static else "dynamic (host-side queue over the ranks)",
+                "input_bytes_per_step": sum(run.regions[i].input_bases() for c in run.calls for i in c),
                 "assembler_spec_width": args.spec_width or 4, "host_cores_per_rank": max(1, (os.cpu_count() or 1) // max(1, D.world)),
                 "l2": ("256 MB buffer written between timed steps (flush)" if H == 1 else
                        "%d independent batches in flight on separate buffers; the per-step working set (~1 GB of "
@@ -555,7 +654,7 @@ def gpu_arm(args):
         "with_ref_kmer_cache": ref_cache, "from_files": from_files, "e2e_dropin": dropin,
         "per_step": {"contigs": cnt["contigs"], "check_align_calls": cnt["check_align"], "dp_cells": n_cells_rank,
                      "kmer_occurrences": cnt["kmer_occ"], "sorted_keys": cnt["sorted"], "sample_only_kmers": cnt["sample_only"],
-                     "note": "this rank's share of one step"},
+                     "note": "one whole step (all calls, all ranks)"},
         "roofline": {"kernel": "assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": asm_gbs / hbm_peak, "traffic": 224056832 if default_shape else None, "peak_source": peak_src,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r2_assemble_kernel.md): 52 MB "
@@ -578,15 +677,17 @@ def gpu_arm(args):
         "kernel_ms_per_step": {k: round(v[0] / kt_steps, 4) for k, v in ktimes.items() if v[1]},
         "kernel_timing": "sequential pass of %d steps with L2 flush, CUDA events per kernel on the library stream" % kt_steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1000.0 * e2e_s / args.steps, "bytes_note": "this rank's share of one step"},
+                "ms_per_step": 1000.0 * e2e_s / args.steps, "bytes_note": "one whole step, all ranks"},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
     regions0 = run.regions
     run.close()
     if not args.no_extra_workloads and args.workload == "C2" and not args.regions:
-        line["c5_strong"] = sharded_summary(D, "C5", args.c5_regions, args, max(2, args.steps // 12))
-        line["c3_sharded"] = sharded_summary(D, "C3", 500 * D.world, args, max(2, args.steps // 4))
+        if "c5" in args.extra_workloads:
+            line["c5_strong"] = sharded_summary(D, "C5", args.c5_regions, args, max(2, args.steps // 6))
+        if "c3" in args.extra_workloads:
+            line["c3_sharded"] = sharded_summary(D, "C3", 500 * D.world, args, max(2, args.steps // 4))
     if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(args.workload, regions0)
         line["cpu_baseline"]["value_with_c_nw_for_context"] = cpu_c_nw_single(regions0)
@@ -667,7 +768,7 @@ def dropin_leg(run, device):
     root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     d = tempfile.mkdtemp(prefix="bk_dropin_", dir=root)
     try:
-        regions = [run.regions[i] for i in run.mine][:500]
+        regions = [run.regions[i] for i in run.calls[0]][:500]
         targets = [dropin_profile.Target(r, d) for r in regions]
         best = {}
         for label, kw in (("python_marshalling", dict(ingest="python")), ("native_ingest", dict(ingest="native"))):
@@ -704,9 +805,11 @@ def ingest_leg(args, D, run, total):
     import tempfile
     import torch
     from breakmer_b200 import batch, ingest
-    regions = [run.regions[i] for i in run.mine]
-    pk = run.packed[0]
+    own = [c for c in range(len(run.calls)) if c % D.world == D.rank]      # this leg: call c on rank c % N
+    regions = [run.regions[i] for c in own for i in run.calls[c]]
+    pk = run.packed[own[0]]
     handles = run.handles
+    handles = handles[:run.inflight]
     H = len(handles)
     root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     d = tempfile.mkdtemp(prefix="bk_bench_r%d_" % D.rank, dir=root)
@@ -802,15 +905,20 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--regions", type=int, default=0, help="override the workload's region count (per GPU if weak; debugging)")
     ap.add_argument("--spec-width", type=int, default=0, help="assembler warps per region (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) kept on the device at once")
+    ap.add_argument("--inflight", type=int, default=8,
+                    help="independent batches (steps) kept on the device at once (a batch lasts as long as its longest "
+                         "region's serial chain, 17-35 ms on the panel: the depth must cover it)")
     ap.add_argument("--c5-regions", type=int, default=20000, help="size of the c5_strong workload")
-    ap.add_argument("--replicate", action="store_true", help="diagnostic: every rank runs rank 0's regions (not the headline)")
+    ap.add_argument("--replicate", action="store_true", help="diagnostic: every call is call 0 (not the headline)")
+    ap.add_argument("--static-shards", action="store_true", help="call c always runs on rank c %% N (plain LPT partition) "
+                    "instead of the host-side work queue over the ranks")
     ap.add_argument("--no-clock-sampler", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cache-leg", action="store_true")
     ap.add_argument("--no-ingest-leg", action="store_true")
     ap.add_argument("--no-dropin-leg", action="store_true")
     ap.add_argument("--no-extra-workloads", action="store_true", help="skip the c5_strong / c3_sharded keys")
+    ap.add_argument("--extra-workloads", default="c5,c3", help="which of the two extra workloads to run (default both)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

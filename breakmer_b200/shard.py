@@ -8,9 +8,11 @@ iterates sorted names).
 
 Two ways to run it:
 
-  * one process per GPU (torchrun; what bench.py does): every rank computes the same
-    `assign_lpt` partition from the same static costs, runs its own regions, and
-    `gather_by_name` collects the per-region results on rank 0;
+  * one process per GPU (torchrun; what bench.py does): every rank cuts the regions into the
+    same calls with `assign_lpt` on the same static costs; the calls are either pinned to ranks
+    (call c on rank c % N) or handed out by `CallQueue` -- an atomic counter in the
+    torch.distributed key-value store, host side, no device traffic -- so that a rank whose calls
+    turn out slow takes fewer of them; `gather_by_name` collects the per-region results on rank 0;
   * one process, several devices: `run_sharded(regions, devices=[0, 1, ...])` -- one host
     thread per device pulls chunks of regions from a shared queue (largest first) and keeps
     `inflight` batches on its device with bk_batch_submit / bk_batch_wait.  This is what
@@ -61,6 +63,35 @@ def chunk_indices(indices, max_regions):
     n_chunks = (len(indices) + max_regions - 1) // max_regions
     per = (len(indices) + n_chunks - 1) // n_chunks
     return [indices[a:a + per] for a in range(0, len(indices), per)]
+
+
+class CallQueue:
+    """Work queue over the ranks of a one-process-per-GPU job: `n_items` numbered items, each taken by exactly one rank.
+    The queue is one counter in the key-value store torch.distributed already holds for rendezvous (rank 0 serves it
+    over TCP on the host; ~50 us per take): no collective, nothing on the device.  Every rank must construct the queues
+    of a job in the same order (the key carries a per-name sequence number).  With world_size 1 it is a local counter."""
+    _seq = {}
+
+    def __init__(self, name, n_items, world_size=1, store=None):
+        self.n_items = int(n_items)
+        self._local = 0
+        self._store = None
+        if world_size > 1:
+            if store is None:
+                from torch.distributed import distributed_c10d
+                store = distributed_c10d._get_default_store()
+            self._store = store
+            CallQueue._seq[name] = CallQueue._seq.get(name, 0) + 1
+            self._key = "bk_call_queue/%s/%d" % (name, CallQueue._seq[name])
+
+    def take(self):
+        """-> the next item number, or None when the queue is empty"""
+        if self._store is None:
+            t = self._local
+            self._local += 1
+        else:
+            t = self._store.add(self._key, 1) - 1
+        return t if t < self.n_items else None
 
 
 def gather_by_name(local_results, rank, world_size, group=None):

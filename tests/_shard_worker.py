@@ -28,11 +28,28 @@ def main():
     owned = shard.assign_lpt([shard.region_cost(r) for r in regions], world)
     local = {regions[i].name: work(regions[i]) for i in owned[rank]}
     merged = shard.gather_by_name(local, rank, world)
+    # the cross-rank call queue: every item is taken exactly once, by whichever rank asks first; two queues of the same
+    # name in a row do not share a counter
+    takes = []
+    for n_items in (37, 5):
+        q = shard.CallQueue("t", n_items, world)
+        mine = []
+        while True:
+            t = q.take()
+            if t is None:
+                break
+            mine.append(t)
+        assert q.take() is None
+        dist.barrier()
+        takes.append(mine)
+    all_takes = [None] * world if rank == 0 else None
+    dist.gather_object(takes, all_takes, dst=0)
     if rank == 0:
         serial = {r.name: work(r) for r in regions}
         ok = merged == dict(sorted(serial.items())) and list(merged) == sorted(merged)
         sizes = [len(o) for o in owned]
-        print(json.dumps({"ok": bool(ok), "sizes": sizes, "n": len(merged)}))
+        q_ok = all(sorted(t for r in all_takes for t in r[i]) == list(range(n)) for i, n in enumerate((37, 5)))
+        print(json.dumps({"ok": bool(ok), "sizes": sizes, "n": len(merged), "queue_ok": bool(q_ok)}))
     dist.barrier()
     dist.destroy_process_group()
 

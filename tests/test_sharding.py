@@ -33,6 +33,13 @@ def test_two_ranks_gloo():
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok"] and res["n"] == 46 and sum(res["sizes"]) == 46 and min(res["sizes"]) > 0
+    assert res["queue_ok"]
+
+
+def test_call_queue_single_rank_is_a_local_counter():
+    q = shard.CallQueue("x", 3)
+    assert [q.take(), q.take(), q.take(), q.take(), q.take()] == [0, 1, 2, None, None]
+    assert shard.CallQueue("x", 0).take() is None
 
 
 def test_chunks_cover_the_shard_and_respect_the_call_limit():
