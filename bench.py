@@ -52,7 +52,8 @@ def config_dict(workload, world, regions_override=0):
     total = n * world if scaling == "weak" else n
     return {"workload": desc, "regions_total": total, "regions_per_gpu": total / float(world), "scaling": scaling,
             "k": 21 if workload == "C4" else 15, "rc_thresh": 2,
-            "sharding": "by region: shard.assign_lpt on static costs, distinct regions per rank, host-side gather by target name"}
+            "sharding": "by region: C-ABI calls of similar static cost (shard.assign_lpt), every call of a step run by exactly one "
+                        "rank, host-side gather by target name; no data-path collective"}
 
 
 def load_peaks():
