@@ -10,6 +10,12 @@
 cache: it writes "<fa_fn>_<k>mers_dump" ("<MER> <count>" per line, the format
 `dump -c` produces) next to the input and touches ".<dump name>".  The
 `jellyfish` argument (path of the binary) is accepted and ignored.
+
+These are the drop-in's INTERFACE, so a few small pieces follow the reference's
+closely on purpose: `fq_read` has the reference's attributes, `get_marker_fn` and
+the head of `run_jellyfish` its file naming and marker cache, and `load_kmers`
+is the same ten-line dump reader (a dump line is "<mer> <count>"; counts of a
+mer seen in several files add up).  Everything that computes is new.
 """
 import logging
 import os
