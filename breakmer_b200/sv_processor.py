@@ -115,7 +115,7 @@ class CapacityError(RuntimeError):
         self.targets = list(names)
 
 
-def _apply_chunk(targets, pk, res, inputs_k, objs, ingest, write_contigs, failed):
+def _apply_chunk(targets, pk, res, inputs_k, objs, ingest, write_contigs, failed, ing=None):
     """Results of one device call -> the state target.compare_kmers leaves behind, for the targets of that call."""
     import numpy as np
     n = len(targets)
@@ -123,7 +123,7 @@ def _apply_chunk(targets, pk, res, inputs_k, objs, ingest, write_contigs, failed
     join = os.path.join
     sk_paths = [join(t.paths['kmers'], t.name) + "_sample_kmers.out" for t in targets]
     if ingest == "native":
-        ing = _get_ingest()
+        ing = ing or _get_ingest()
         all_ok = not any(status)
         if write_contigs:
             # contig.setup's files for every contig of every completed target in one pass (sv_processor.py:749-782,
@@ -180,7 +180,8 @@ def _pack_targets(targets, ingest, slot=0):
     raise ValueError("ingest must be 'python' or 'native'")
 
 
-def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False, devices=None, max_targets=160, inflight=3):
+def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False, devices=None, max_targets=125, inflight=4,
+                        apply_thread=False):
     """target.compare_kmers() for many targets (the region loop of sv_processor.py:185-201 as one call).
 
     The targets are cut into chunks of at most max_targets, most expensive first (static cost, breakmer_b200.shard), and
@@ -188,6 +189,12 @@ def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False,
     serial tail of one chunk's assembly overlaps the bulk of the next.  With `devices=[0, 1, ...]` the chunks are handed
     out dynamically to one host thread per GPU (region sharding, no collective); results are applied to the target objects
     as chunks complete.
+
+    `apply_thread=True` gives every device a second host thread that waits for the results and applies them to the
+    target objects while the first one parses and submits the next chunks.  (Measured neutral on a 500-target panel,
+    profiles/r2_experiments.md: a chunk's results arrive one assembly latency -- its longest region's chain, ~20 ms --
+    after it was submitted, whatever its size, and applying them is GIL-bound Python; the option pays when parsing is
+    the larger share, i.e. big inputs per target.)
 
     Targets that exceed a device limit do not disturb the others: everything else completes, then CapacityError lists
     them (their state is untouched)."""
@@ -204,7 +211,7 @@ def compare_kmers_batch(targets, device=0, ingest="python", write_contigs=False,
         res = batch.run(get_handle(devices[0]), pk, decode=False)
         _apply_chunk(targets, pk, res, ks, objs, ingest, write_contigs, failed)
     else:
-        _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed)
+        _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed, apply_thread)
     if failed:
         raise CapacityError(sorted(failed))
 
@@ -222,7 +229,7 @@ def _get_pipe(dev, inflight):
     return _pipes[key]
 
 
-def _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed):
+def _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, failed, apply_thread=False):
     """Chunked, pipelined (and with several devices region-sharded) pass: sv_processor.py:185-201 over `devices`."""
     import threading
     costs = [_target_cost(t) for t in targets]
@@ -251,14 +258,67 @@ def _sharded(targets, devices, ingest, write_contigs, max_targets, inflight, fai
         try:
             pipe = shard.DevicePipeline(dev, inflight=inflight) if own_pipe else _get_pipe(dev, inflight)
 
+            # (the writer the applying thread uses: made here so that it is cached under the calling thread's key)
+            apply_ing = _get_ingest("apply") if (apply_thread and ingest == "native") else None
+
             def drain_one():
                 res, pk, tag = pipe.pop(decode=False)
                 chunk, ks, objs = tag
                 mine = []
-                _apply_chunk(chunk, pk, res, ks, objs, ingest, write_contigs, mine)
+                _apply_chunk(chunk, pk, res, ks, objs, ingest, write_contigs, mine, apply_ing)
                 with lock:
                     failed.extend(mine)
 
+            if apply_thread:
+                # this thread parses and submits; a second one takes the results in submission order and applies them.
+                # A handle is free again only when its chunk has been applied (the result arrays live in its arena).
+                free = threading.Semaphore(inflight)
+                submitted = []                           # grows by append only; the applier follows it by index
+                more = threading.Condition()
+                state = {"done": False}
+
+                def applier():
+                    at = 0
+                    try:
+                        while True:
+                            with more:
+                                while at >= len(submitted) and not state["done"]:
+                                    more.wait()
+                                if at >= len(submitted):
+                                    return
+                            at += 1
+                            drain_one()
+                            free.release()
+                    except Exception as e:               # noqa: BLE001 -- re-raised on the calling thread
+                        errors.append(e)
+                        state["failed"] = True
+                        free.release()
+
+                helper = threading.Thread(target=applier)
+                helper.start()
+                try:
+                    while not state.get("failed"):
+                        idx = take()
+                        if idx is None:
+                            break
+                        chunk = [targets[i] for i in idx]
+                        pk, ks, objs = _pack_targets(chunk, ingest, slot=n_sub % (inflight + 1))
+                        free.acquire()
+                        if state.get("failed"):
+                            break
+                        n_sub += 1
+                        pipe.submit(pk, (chunk, ks, objs))
+                        with more:
+                            submitted.append(n_sub)
+                            more.notify()
+                finally:
+                    with more:
+                        state["done"] = True
+                        more.notify()
+                    helper.join()
+                if state.get("failed"):
+                    raise errors.pop()
+                return
             while True:
                 idx = take()
                 if idx is None:

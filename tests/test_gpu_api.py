@@ -232,6 +232,49 @@ def test_sharded_compare_kmers_batch_over_devices(tmp_path):
         assert [c.get_contig_seq() for c in a.kmers["clusters"]] == [c.get_contig_seq() for c in b.kmers["clusters"]]
 
 
+def test_compare_kmers_batch_with_an_applying_thread(tmp_path):
+    """apply_thread=True: one host thread parses and submits, a second waits for the results and applies them.  Same
+    state on the targets and the same contig files as the single-thread pass; an over-limit target is still isolated."""
+    from breakmer_b200 import sv_processor
+    regions = list(synth.config_regions("C2", 18, start=120)) + list(synth.config_regions("C5", 25, start=300))
+    long_r = synth.Region(name="zz_long", k=15, ref_fwd="ACGT" * 50, reads=[("@a:1:1:1:1/1_0", "ACGT" * 1100, "I" * 4400, False)],
+                          sc_records=[("a", "ACGT" * 10)])
+    d1, d2 = os.path.join(str(tmp_path), "a"), os.path.join(str(tmp_path), "b")
+    os.makedirs(d1); os.makedirs(d2)
+    plain = [_Target(r, d1) for r in regions]
+    piped = [_Target(r, d2) for r in regions + [long_r]]
+    for ts in (plain, piped):
+        for t in ts:
+            t.paths["contigs"] = os.path.join(t.paths["kmers"], t.name, "contigs")
+    sv_processor.compare_kmers_batch(plain, ingest="native", write_contigs=True, max_targets=1000)
+    with pytest.raises(sv_processor.CapacityError) as e:
+        sv_processor.compare_kmers_batch(piped, ingest="native", write_contigs=True, max_targets=6, inflight=3, apply_thread=True)
+    assert e.value.targets == ["zz_long"]
+    assert piped[-1].cleaned_read_recs is not None and "clusters" not in piped[-1].kmers
+    n_ctg = 0
+    for a, b in zip(plain, piped):
+        with open(a.files["sample_kmers"]) as fa, open(b.files["sample_kmers"]) as fb:
+            assert fa.read() == fb.read()
+        assert len(a.kmers["clusters"]) == len(b.kmers["clusters"])
+        for n, (x, y) in enumerate(zip(a.kmers["clusters"], b.kmers["clusters"]), 1):
+            assert x.get_contig_seq() == y.get_contig_seq() and x.kmers == y.kmers and x.get_kmer_locs() == y.get_kmer_locs()
+            assert x.get_contig_counts().others == y.get_contig_counts().others
+            assert sorted(r.id for r in x.reads) == sorted(r.id for r in y.reads)
+            for ext in ("fa", "fq"):
+                with open(os.path.join(a.paths["contigs"], "contig%d" % n, "contig%d.%s" % (n, ext))) as fa, \
+                        open(os.path.join(b.paths["contigs"], "contig%d" % n, "contig%d.%s" % (n, ext))) as fb:
+                    assert fa.read() == fb.read()
+            n_ctg += 1
+        assert b.cleaned_read_recs is None
+    assert n_ctg > 10
+    # python marshalling through the same two-thread pass, twice in a row (the pipeline and its writer are kept)
+    for _ in range(2):
+        third = [_Target(r, d2) for r in regions[:12]]
+        sv_processor.compare_kmers_batch(third, max_targets=5, apply_thread=True)
+        for a, b in zip(plain, third):
+            assert [c.get_contig_seq() for c in a.kmers["clusters"]] == [c.get_contig_seq() for c in b.kmers["clusters"]]
+
+
 def test_run_sharded_matches_one_call():
     from breakmer_b200 import _lib, batch, shard
     regions = list(synth.config_regions("C2", 20, start=200))

@@ -1,4 +1,4 @@
-"""Drop-in throughput for a few chunking / threading variants (experiments)."""
+"""Drop-in throughput for chunking / pipelining variants of sv_processor.compare_kmers_batch (experiments)."""
 import os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tools.dropin_profile import Target
@@ -7,12 +7,22 @@ from breakmer_b200 import sv_processor, synth
 regions = list(synth.config_regions("C2", 500))
 d = tempfile.mkdtemp(prefix="bk_dropin_", dir="/dev/shm")
 targets = [Target(r, d) for r in regions]
-for label, kw in [("1 thread, 160/chunk, inflight 3", dict()), ("1 thread, 260/chunk", dict(max_targets=260)),
-                  ("1 thread, 500 in one call", dict(max_targets=500)),
-                  ("2 threads on device 0, 130/chunk", dict(devices=[0, 0], max_targets=130)),
-                  ("2 threads, 260/chunk", dict(devices=[0, 0], max_targets=260)),
-                  ("3 threads, 170/chunk", dict(devices=[0, 0, 0], max_targets=170)),
-                  ("4 threads, 125/chunk", dict(devices=[0, 0, 0, 0], max_targets=125))]:
+variants = [("160/chunk, 3 in flight (default)", dict()),
+            ("160/chunk, 4 in flight", dict(inflight=4)),
+            ("125/chunk, 4 in flight", dict(max_targets=125, inflight=4)),
+            ("100/chunk, 5 in flight", dict(max_targets=100, inflight=5)),
+            ("84/chunk, 6 in flight", dict(max_targets=84, inflight=6)),
+            ("64/chunk, 8 in flight", dict(max_targets=64, inflight=8)),
+            ("500 in one call", dict(max_targets=500)),
+            ("apply thread, 160/chunk, 3 in flight", dict(apply_thread=True)),
+            ("apply thread, 125/chunk, 4 in flight", dict(apply_thread=True, max_targets=125, inflight=4)),
+            ("apply thread, 100/chunk, 5 in flight", dict(apply_thread=True, max_targets=100, inflight=5)),
+            ("apply thread, 64/chunk, 8 in flight", dict(apply_thread=True, max_targets=64, inflight=8)),
+            ("apply thread, 50/chunk, 6 in flight", dict(apply_thread=True, max_targets=50, inflight=6))]
+only = sys.argv[1:]
+for label, kw in variants:
+    if only and not any(o in label for o in only):
+        continue
     best = 1e9
     for rep in range(4):
         for t in targets:
@@ -20,4 +30,5 @@ for label, kw in [("1 thread, 160/chunk, inflight 3", dict()), ("1 thread, 260/c
         t0 = time.time()
         sv_processor.compare_kmers_batch(targets, ingest="native", **kw)
         best = min(best, time.time() - t0)
-    print("%-40s %6.1f ms  %6.0f targets/s" % (label, 1e3 * best, 500 / best))
+    n_ctg = sum(len(t.kmers["clusters"]) for t in targets)
+    print("%-42s %6.1f ms  %6.0f targets/s  (%d contigs)" % (label, 1e3 * best, 500 / best, n_ctg), flush=True)
