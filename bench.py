@@ -91,29 +91,43 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.ok = False
 
+    def _sample(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def run(self):
         if not self.ok:
             return
-        self._stop_evt.wait(0.12)            # first sample well inside the timed region
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.25)    # NVML queries contend with kernel launches of every process on the box: keep them sparse
+        # NVML queries contend with kernel launches of every process on the box: keep them sparse.  The first two come
+        # early so that a short timed region (few --steps) is still sampled under load.
+        for pause in (0.03, 0.09):
+            if self._stop_evt.wait(pause):
+                return
+            self._sample()
+        while not self._stop_evt.wait(0.25):
+            self._sample()
 
     def stop(self):
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
+        late = False
+        if self.ok and not self.samples:     # a timed region shorter than 30 ms: one sample right behind it
+            self._sample()
+            late = True
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if late:
+            out["sampled"] = "right after the timed region (it was shorter than the first sampling delay)"
+        return out
 
 
 # ---------------------------------------------------------------------------------
