@@ -27,6 +27,27 @@ inline void threadfence() {}
 inline int atomic_cas(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p = val; return o; }
 inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 }  // namespace bk
+#elif defined(BK_SIMT)
+// tests/sim only: the warp kernels on a 32-lane host emulator (tests/sim/simt_host.h, fibers + barriers at the warp
+// collectives).  Like BK_SIM this build is a test tool; it is never part of the shipped library.
+#include "simt_host.h"
+#define BK_DEV inline
+#define BK_HD inline
+namespace bk {
+constexpr int WARP = 32;
+inline int lane() { return simt::lane_id(); }
+inline void syncwarp() { __syncwarp(); }
+inline unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+template <typename T> inline T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+inline int popc(unsigned x) { return __builtin_popcount(x); }
+inline int ffs(unsigned x) { return __builtin_ffs((int)x); }
+// (lanes run one at a time between collectives, so plain read-modify-write is atomic here)
+inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline void threadfence() {}
+inline int atomic_cas(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p = val; return o; }
+inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+}  // namespace bk
 #else
 #include <cuda_runtime.h>
 #define BK_DEV __device__ __forceinline__

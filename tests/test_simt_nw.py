@@ -1,0 +1,131 @@
+"""The warp DP kernels of breakmer_b200/csrc/nw.cuh -- the product source, unmodified -- run on a 32-lane host emulator
+(tests/sim/simt_host.h: one fiber per lane, barriers at the warp collectives) and compared with the reference's own
+`olc.nw` outputs (tests/golden/nw_golden.json) and with the oracle on seeded pairs.  This is a CPU-side check of the
+kernel SOURCE (index arithmetic, table layout, traceback, lane exchange, missing __syncwarp()); parity of the compiled
+sm_100a kernels is tests/test_gpu_nw.py."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from oracle import nw_py
+
+SIM = os.path.join(ROOT, "tests", "sim")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = os.path.join(SIM, "libsimt_nw.so")
+    deps = [os.path.join(SIM, "simt_nw.cpp"), os.path.join(SIM, "simt_host.h")] + \
+           [os.path.join(ROOT, "breakmer_b200", "csrc", f) for f in ("nw.cuh", "common.cuh")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-I", SIM, "-o", so, deps[0]])
+    l = ctypes.CDLL(so)
+    l.simt_nw_dual.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                               ctypes.POINTER(ctypes.c_int)]
+    return l
+
+
+def run(lib, cs, rs, mode):
+    out = (ctypes.c_int * 10)()
+    rc = lib.simt_nw_dual(cs.encode(), len(cs), rs.encode(), len(rs), mode, out)
+    assert rc == 0, "simt_nw_dual rc %d (lanes disagree if < -1)" % rc
+    return list(out)
+
+
+def expected(cs, rs):
+    return list(nw_py.nw_fast(cs, rs)[2:]) + list(nw_py.nw_fast(rs, cs)[2:])
+
+
+def lazy_reads(exp, m, n):
+    """which traceback origins contig.check_align reads (sv_assembly.py:449-504), as nw.cuh's LAZY states them"""
+    sa, sb = exp[4], exp[9]
+    mn = min(m, n)
+    low_a, low_b = 4 * sa < mn, 4 * sb < mn
+    if sa == sb:
+        return (not low_a, not low_a)
+    first_a = sa > sb
+    if low_a if first_a else low_b:
+        return (False, False)
+    span = (m - exp[1]) if first_a else (n - exp[6])
+    bad1 = 200 * (sa if first_a else sb) < 179 * span
+    other = bad1 and not (low_b if first_a else low_a)
+    return (True, other) if first_a else (other, True)
+
+
+def check(lib, cs, rs, modes=(0, 1, 2)):
+    exp = expected(cs, rs)
+    for mode in modes:
+        got = run(lib, cs, rs, mode)
+        if mode == 1:
+            ra, rb = lazy_reads(exp, len(cs), len(rs))
+            keep = [0, 2, 4, 5, 7, 9] + ([1, 3] if ra else []) + ([6, 8] if rb else [])
+            assert [got[i] for i in keep] == [exp[i] for i in keep], (mode, cs, rs)
+        else:
+            assert got == exp, (mode, cs, rs)
+
+
+def test_reference_golden_pairs(lib):
+    """every pair the reference itself aligned for the golden file, both argument orders, all kernels"""
+    cases = golden("nw_golden.json")["cases"]
+    n = 0
+    for c in cases:
+        a, b = c["seq1"], c["seq2"]
+        if not a or not b:
+            continue
+        assert expected(a, b)[:5] == c["out"][2:]             # the oracle agrees with the reference (pinned elsewhere too)
+        check(lib, a, b)
+        if n % 4 == 0:
+            check(lib, b, a, modes=(0, 3))
+        n += 1
+    assert n > 350
+
+
+def test_seeded_pairs_all_kernels(lib):
+    """read x contig shapes of the assembler (overhangs at either end, repeats, indels, N), column counts on both sides
+    of every lane / block boundary"""
+    rng = random.Random(23)
+    pairs = []
+    for t in range(260):
+        la = rng.choice([1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 97, 100, 101, 124, 125, 126, 127, 128, 129, 150, 257, 300])
+        lb = rng.choice([1, 2, 3, 17, 64, 100, 150, 199, 200, 201, 260, 400])
+        g = "".join(rng.choice("ACGT") for _ in range(la + lb))
+        a = g[:la]
+        kind = t % 5
+        if kind == 0:
+            b = "".join(rng.choice("ACGTN") for _ in range(lb))
+        elif kind == 1:
+            ov = rng.randint(1, min(la, lb))
+            b = (a[la - ov:] + g[la:])[:lb]                    # b starts inside a and runs past its end
+        elif kind == 2:
+            ov = rng.randint(1, min(la, lb))
+            b = (g[la:la + lb - ov] + a[:ov])                   # b ends inside a's start
+        elif kind == 3:
+            unit = "".join(rng.choice("ACGT") for _ in range(rng.choice([1, 2, 3, 7])))
+            a = (unit * (la // len(unit) + 1))[:la]
+            b = (unit * (lb // len(unit) + 1))[:lb]            # repeats: ties everywhere
+        else:
+            b = g[max(0, la - lb // 2):][:lb]
+            cut = rng.randint(0, max(0, len(b) - 4))
+            b = b[:cut] + b[cut + rng.randint(1, 3):] if rng.random() < 0.5 else b[:cut] + "GG" + b[cut:]
+        b = "".join(c if rng.random() > 0.02 else rng.choice("ACGTN") for c in b) or "A"
+        pairs.append((a, b))
+    for a, b in pairs:
+        check(lib, a, b)
+
+
+def test_long_sequences_take_the_packed_kernel(lib):
+    rng = random.Random(5)
+    a = "".join(rng.choice("ACGT") for _ in range(700))
+    b = a[500:] + "".join(rng.choice("ACGT") for _ in range(300))
+    assert not lib.simt_nw_trace_fits(len(a), len(b)) and lib.simt_nw_trace_fits(100, 200)
+    check(lib, a, b, modes=(0, 1, 3))
+    check(lib, b, a, modes=(0, 2))
+    c = "".join(rng.choice("ACGT") for _ in range(100))
+    d = "".join(rng.choice("ACGT") for _ in range(1300))      # 100 columns, but more rows than the score table holds
+    assert not lib.simt_nw_trace_fits(len(c), len(d))
+    check(lib, c, d[:600] + c[40:] + d[600:], modes=(0, 1))
