@@ -811,7 +811,9 @@ BK_DEV bool check_read(RegionCtx& c, int seed_s, int pos, bool grow) {
 
 // ---- buffer.add_contig (:337-340) ----------------------------------------------------------------
 BK_DEV bool add_contig(RegionCtx& c, int u, int seed_s) {
-  if (c.r_used[u]) return false;            // (a queued read is always used, so `id in contigs` is implied)
+  const bool used = c.r_used[u];            // (a queued read is always used, so `id in contigs` is implied)
+  syncwarp();                               // every lane has read the flag before lane 0 sets it
+  if (used) return false;
   if (lane() == 0) {
     c.q_read[c.q_tail] = u; c.q_seed[c.q_tail] = seed_s;
     c.r_used[u] = 1; c.r_queued[u] = 1;
@@ -1091,7 +1093,7 @@ BK_DEV void grow(RegionCtx& c, int mode, int seed_s) {
     // every tuple of the snapshot, in order.  It does not depend on how the alignments turn out (see find_reads).
     int st = 0;
     for (int e = 0; e < nn; ++e) {
-#ifndef BK_SIM
+#if !defined(BK_SIM) && !defined(BK_SIMT)   // (PTX; a hint only, absent from the host builds of tests/sim)
       if (!setup && e + 1 < nn) {       // warm L1/L2 for the next tuple's posting list while this one is processed
         const int64_t na = c.P->post_off[c.gm0 + Ns[e + 1]];
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c.P->post_read + na + lane()));
@@ -1116,10 +1118,11 @@ BK_DEV void grow(RegionCtx& c, int mode, int seed_s) {
       c.rnd_cnt = 1;                                                   // slot 0 is the contig's own read: nothing to align
       const int u0 = c.hit_u[0];
       contig_init(c, seed_s, u0);
-      c.setup_queued = false;
-      if (!c.r_used[u0]) {                                             // buff.add_contig(read, ct) (Q20)
+      const bool fresh = !c.r_used[u0];                                // (every lane reads the flag before lane 0 sets it)
+      syncwarp();
+      c.setup_queued = fresh;
+      if (fresh) {                                                     // buff.add_contig(read, ct) (Q20)
         if (lane() == 0) c.r_used[u0] = 1;
-        c.setup_queued = true;
         syncwarp();
       }
       pos = 1;
@@ -1136,7 +1139,9 @@ BK_DEV void grow(RegionCtx& c, int mode, int seed_s) {
         const int u = c.hit_u[pos];
         if (setup && lane() == 0) c.r_buf[u] = c.serial;               // self.buffer.add(read.id) (:22)
         if (check_read(c, s, pos, !setup)) {
-          if (!setup && c.r_queued[u] == 1) {                          // buff.remove_contig(read.id) :639
+          const bool queued = !setup && c.r_queued[u] == 1;            // buff.remove_contig(read.id) :639
+          syncwarp();                                                  // (every lane has read the flag before lane 0 changes it)
+          if (queued) {
             if (lane() == 0) c.r_queued[u] = 2;
             syncwarp();
           }
@@ -1216,6 +1221,7 @@ BK_DEV void assemble_region(RegionCtx& c) {
         if (c.q_head >= c.q_tail) break;
         const int u = c.q_read[c.q_head], s = c.q_seed[c.q_head];
         ++c.q_head;
+        syncwarp();                                                  // every lane is past its scan of the queue flags
         if (lane() == 0) c.r_queued[u] = 2;
         syncwarp();
         contig_init(c, s, u);

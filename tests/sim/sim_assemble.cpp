@@ -1,10 +1,13 @@
-// tests/sim: host-compiled, single-lane build of the device assembler's control
-// logic (breakmer_b200/csrc/assemble.cuh with BK_SIM).  TEST/DEBUG TOOL ONLY: it
-// lets the state machine be checked against the oracle in the build container,
-// which has no GPU.  It is not part of the product library, is never loaded by
-// breakmer_b200, and is not a fallback -- the product path runs the same source
-// compiled by nvcc for sm_100a with 32-lane warps and the warp DP kernel.
+// tests/sim: host-compiled builds of the device assembler (breakmer_b200/csrc/assemble.cuh).  TEST/DEBUG TOOL ONLY:
+// they let the kernel source be checked against the oracle in the build container, which has no GPU.  They are not
+// part of the product library, are never loaded by breakmer_b200, and are not a fallback -- the product path runs the
+// same source compiled by nvcc for sm_100a.
+//   default (BK_SIM):  single-lane build of the control logic (a "warp" is one lane, scalar stand-in for the DP)
+//   -DBK_SIMT:         the kernel itself -- assemble_kernel<W>, W warps of 32 lanes, the round protocol between the
+//                      controller and the aligner warps, the warp DP kernels -- on the fiber emulator of simt_host.h
+#ifndef BK_SIMT
 #define BK_SIM 1
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -15,6 +18,14 @@
 #include "../../breakmer_b200/csrc/assemble.cuh"
 
 using namespace bk;
+
+#ifdef BK_SIMT
+// the kernel's `extern __shared__ uint8_t smem_raw[]`
+namespace bk { alignas(16) uint8_t smem_raw[256 * 1024]; }
+static int use_tab = 1;
+// 1 (default): aligner warps get a score table (score pass + traceback); 0: the packed-cell kernel, as with BK_NW_PACKED=1
+extern "C" void sim_use_score_table(int on) { use_tab = on; }
+#endif
 
 extern "C" int sim_assemble_region(
     const uint8_t* rbases, const int64_t* roff, int n_reads, const uint32_t* mult, const uint8_t* io,
@@ -106,6 +117,43 @@ extern "C" int sim_assemble_region(
   P.region_status = &status; P.region_ncontigs = &ncontigs;
   unsigned long long stats[16] = {0};
   P.stats = stats;
+#ifdef BK_SIMT
+  // one CTA with blockIdx.x = SLOT (so that the controller role sits on hardware warp SLOT % W, not on warp 0); the
+  // per-slot scratch arrays are re-pointed at arrays with SLOT + 1 slots
+  const int W = spec_w;
+  const int SLOT = 1;
+  const size_t NS = SLOT + 1;
+  std::vector<uint8_t> xw_cseq(NS * ASM_BUF);
+  std::vector<int32_t> xw_cnt(NS * 4 * ASM_BUF), xw_K(NS * 4 * ASM_KCAP), xw_NK(NS * 4 * ASM_KCAP), xw_diff(NS * (ASM_CAP + 1));
+  std::vector<uint64_t> xw_wcode(NS * ASM_CAP);
+  std::vector<int2> xw_edge(NS * W * 2 * ASM_CAP);
+  std::vector<uint2> xw_lastcol(NS * W * ASM_LASTCOL);
+  std::vector<uint8_t> xw_tab(NS * W * (size_t)NW_TAB_BYTES);
+  P.w_cseq = xw_cseq.data(); P.w_cnt = xw_cnt.data(); P.w_K = xw_K.data(); P.w_NK = xw_NK.data();
+  P.w_wcode = xw_wcode.data(); P.w_diff = xw_diff.data(); P.w_edge = xw_edge.data();
+  P.w_lastcol = xw_lastcol.data(); P.w_tab = use_tab ? xw_tab.data() : nullptr;
+  int max_len = 0;
+  for (int i = 0; i < n_reads; ++i) max_len = std::max(max_len, (int)(roff[i + 1] - roff[i]));
+  P.read_cap = std::min((int)ASM_CAP, (max_len + 2 + 15) & ~15);
+  int work_counter = 0;
+  int32_t work_order[1] = {0};
+  P.work_counter = &work_counter; P.work_order = work_order;
+  unsigned long long region_cells[1] = {0};
+  P.region_cells = region_cells;
+  if (assemble_smem_bytes(W, P.read_cap) > sizeof(bk::smem_raw)) return -100;
+  memset(bk::smem_raw, 0, sizeof(bk::smem_raw));
+  const AsmParams PP = P;
+  auto body = [&]() {
+    switch (W) {
+      case 1: assemble_kernel<1, 0>(PP); break;
+      case 2: assemble_kernel<2, 0>(PP); break;
+      case 8: assemble_kernel<8, 0>(PP); break;
+      default: assemble_kernel<4, 0>(PP); break;
+    }
+  };
+  simt::run_block(W, SLOT, body);
+  const int c_status = status;
+#else
   std::vector<uint8_t> s_reads((size_t)ASM_SPEC_W * ASM_CAP), s_contig(ASM_CAP), s_pred((size_t)ASM_SPEC_W * ASM_CAP);
   SpecShared sp;
   memset(&sp, 0, sizeof sp);
@@ -114,7 +162,9 @@ extern "C" int sim_assemble_region(
   bind_region(c, P, 0, 0, s_reads.data(), s_contig.data(), s_pred.data(), s_hash.data(), &sp, spec_w);
   assemble_region(c);
   stats[0] += c.n_align; stats[1] += c.n_cells;
+  const int c_status = c.status;
+#endif
   *n_contigs = (int64_t)cursor[4];
   for (int i = 0; i < 4; ++i) stats_out[i] = stats[i];
-  return c.status;
+  return c_status;
 }

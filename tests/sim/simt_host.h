@@ -4,9 +4,9 @@
 // TEST TOOL ONLY (compiled with -DBK_SIMT by tests/test_simt_nw.py).  It is not part of the product library, is never
 // loaded by breakmer_b200 and is not a fallback: the product fails without a CUDA device.
 //
-// Model: every lane of the warp is a fiber (ucontext) running the same function.  Lanes run one after the other until
-// they reach a warp collective (__shfl_*_sync, __ballot_sync, __syncwarp); a collective is a barrier across the 32
-// fibers with an exchange buffer.  Kernels that are correct under this model are race free at warp level as long as
+// Model: every thread of a block (up to 8 warps of 32 lanes) is a fiber (ucontext) running the same function.  Threads
+// run one after the other until they reach a warp collective (__shfl_*_sync, __ballot_sync, __syncwarp) -- a barrier
+// across the 32 fibers of that warp with an exchange buffer -- or __syncthreads(), a barrier across the block.  Kernels that are correct under this model are race free at warp level as long as
 // every cross-lane communication goes through a collective or is separated by __syncwarp() -- which is exactly what is
 // worth checking: a missing __syncwarp() shows up as a wrong result here (lanes run to the next collective one at a
 // time, in lane order, the most adversarial interleaving for producer/consumer code).
@@ -35,96 +35,210 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 namespace simt {
 
 constexpr int LANES = 32;
-constexpr size_t STACK_BYTES = 256 * 1024;
+constexpr int MAX_WARPS = 8;
+constexpr size_t STACK_BYTES = 512 * 1024;
 
-struct Warp {
-  ucontext_t sched;
-  ucontext_t ctx[LANES];
-  char* stacks = nullptr;
-  bool done[LANES];
-  int cur = 0;
-  // collective state
+struct WarpState {               // collective in progress on one warp
   int arrived = 0;
   unsigned generation = 0;
-  int op = 0;                      // kind of the collective in progress (all lanes must agree)
+  int op = 0;                    // kind of the collective (all lanes must agree)
   long long buf[LANES];
-  std::function<void(int)> body;
 };
 
-inline Warp*& current() {
-  static thread_local Warp* w = nullptr;
-  return w;
+// Fiber switch.  glibc's swapcontext saves and restores the signal mask with two system calls per switch, which is most
+// of the emulator's run time; on x86-64 a switch is therefore a dozen instructions of our own (callee-saved registers
+// and the stack pointer), ucontext elsewhere.
+#if defined(__x86_64__)
+#define SIMT_ASM_SWITCH 1
+extern "C" void simt_switch(void** save_sp, void* load_sp);
+__asm__(
+    ".text\n"
+    ".globl simt_switch\n"
+    ".hidden simt_switch\n"
+    ".type simt_switch,@function\n"
+    "simt_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size simt_switch,.-simt_switch\n");
+typedef void* Ctx;
+#else
+typedef ucontext_t Ctx;
+#endif
+
+struct Block {
+  int n_threads = 0;
+  unsigned block_idx = 0;
+  Ctx sched;
+  Ctx ctx[MAX_WARPS * LANES];
+  bool done[MAX_WARPS * LANES];
+  char* stacks = nullptr;
+  int cur = 0;
+  WarpState warp[MAX_WARPS];
+  int b_arrived = 0;             // __syncthreads
+  unsigned b_generation = 0;
+  unsigned long long progress = 0;
+  void* where[MAX_WARPS * LANES];   // return address of the barrier each thread waits at (deadlock report)
+  unsigned n_warp_bar[MAX_WARPS * LANES] = {0}, n_block_bar[MAX_WARPS * LANES] = {0};
+  void* hist[MAX_WARPS * LANES][16];
+  std::function<void()> body;
+};
+
+inline Block*& current() {
+  static thread_local Block* b = nullptr;
+  return b;
+}
+
+inline void report(Block* b) {
+  fprintf(stderr, "simt: %d threads at __syncthreads;", b->b_arrived);
+  for (int w = 0; w < b->n_threads / LANES; ++w)
+    fprintf(stderr, " warp %d: %d lanes at collective %d;", w, b->warp[w].arrived, b->warp[w].op);
+  fprintf(stderr, "\n");
+  for (int t = 0; t < b->n_threads; ++t)
+    if (!b->done[t] && (t == 0 || b->where[t] != b->where[t - 1]))
+      fprintf(stderr, "simt:   thread %d waits at %p (its %u-th warp collective, %u-th __syncthreads)\n", t, b->where[t],
+              b->n_warp_bar[t], b->n_block_bar[t]);
+  if (getenv("SIMT_HISTORY"))
+    for (int t = 0; t < b->n_threads; ++t)
+      if (!b->done[t] && (t == 0 || b->where[t] != b->where[t - 1])) {
+        fprintf(stderr, "simt:   thread %d last warp collectives (oldest first):", t);
+        for (unsigned i = b->n_warp_bar[t] > 16 ? b->n_warp_bar[t] - 16 : 0; i < b->n_warp_bar[t]; ++i) fprintf(stderr, " %p", b->hist[t][i & 15]);
+        fprintf(stderr, "\n");
+      }
+}
+
+inline void switch_ctx(Ctx* from, Ctx* to) {
+#ifdef SIMT_ASM_SWITCH
+  simt_switch(from, *to);
+#else
+  swapcontext(from, to);
+#endif
 }
 
 inline void trampoline() {
-  Warp* w = current();
-  const int l = w->cur;
-  w->body(l);
-  w->done[l] = true;
-  swapcontext(&w->ctx[l], &w->sched);
+  Block* b = current();
+  const int t = b->cur;
+  b->body();
+  b->done[t] = true;
+  ++b->progress;
+  switch_ctx(&b->ctx[t], &b->sched);
+  abort();                         // a finished fiber is never resumed
 }
 
-// run `body(lane)` on 32 emulated lanes until all of them have returned
-inline void run_warp(const std::function<void(int)>& body) {
-  Warp w;
-  w.body = body;
-  w.stacks = (char*)malloc(STACK_BYTES * LANES);
-  Warp* prev = current();
-  current() = &w;
-  for (int l = 0; l < LANES; ++l) {
-    w.done[l] = false;
-    getcontext(&w.ctx[l]);
-    w.ctx[l].uc_stack.ss_sp = w.stacks + STACK_BYTES * l;
-    w.ctx[l].uc_stack.ss_size = STACK_BYTES;
-    w.ctx[l].uc_link = &w.sched;
-    makecontext(&w.ctx[l], (void (*)())trampoline, 0);
+// run `body()` on n_warps x 32 emulated threads of one block until all of them have returned
+inline void run_block(int n_warps, unsigned block_idx, const std::function<void()>& body) {
+  Block* b = new Block;
+  b->n_threads = n_warps * LANES;
+  b->block_idx = block_idx;
+  b->body = body;
+  b->stacks = (char*)malloc(STACK_BYTES * b->n_threads);
+  Block* prev = current();
+  current() = b;
+  for (int t = 0; t < b->n_threads; ++t) {
+    b->done[t] = false;
+#ifdef SIMT_ASM_SWITCH
+    // a fresh stack that simt_switch "returns" into trampoline() from: six callee-saved registers, the entry address,
+    // and a null return address above it (rsp is 8 mod 16 at the entry, as after a call)
+    uintptr_t top = ((uintptr_t)(b->stacks + STACK_BYTES * (t + 1))) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;
+    *--sp = (void*)(void (*)())trampoline;
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;
+    b->ctx[t] = (void*)sp;
+#else
+    getcontext(&b->ctx[t]);
+    b->ctx[t].uc_stack.ss_sp = b->stacks + STACK_BYTES * t;
+    b->ctx[t].uc_stack.ss_size = STACK_BYTES;
+    b->ctx[t].uc_link = &b->sched;
+    makecontext(&b->ctx[t], (void (*)())trampoline, 0);
+#endif
   }
-  int live = LANES;
-  while (live > 0) {
-    live = 0;
-    for (int l = 0; l < LANES; ++l) {
-      if (w.done[l]) continue;
-      w.cur = l;
-      swapcontext(&w.sched, &w.ctx[l]);
-      if (!w.done[l]) ++live;
+  for (;;) {
+    int live = 0;
+    const unsigned long long before = b->progress;
+    for (int t = 0; t < b->n_threads; ++t) {
+      if (b->done[t]) continue;
+      b->cur = t;
+      switch_ctx(&b->sched, &b->ctx[t]);
+      if (!b->done[t]) ++live;
     }
-    if (live > 0 && live < LANES && w.arrived > 0 && w.arrived == live) {
-      fprintf(stderr, "simt: %d lanes wait at a collective that %d lanes have left the kernel without\n", live, LANES - live);
+    if (live == 0) break;
+    if (b->progress == before) {
+      fprintf(stderr, "simt: deadlock -- %d threads wait at barriers that the others never reach "
+                      "(a collective inside divergent control flow, or threads that left the kernel early)\n", live);
+      report(b);
       abort();
     }
   }
   current() = prev;
-  free(w.stacks);
+  free(b->stacks);
+  delete b;
 }
 
-inline int lane_id() { return current()->cur; }
-
-inline void yield_lane() {
-  Warp* w = current();
-  swapcontext(&w->ctx[w->cur], &w->sched);
+// one warp: body(lane)
+inline int lane_id();
+inline void run_warp(const std::function<void(int)>& body) {
+  run_block(1, 0, [&]() { body(lane_id()); });
 }
 
-// barrier across the 32 fibers; `op` identifies the call site's kind so that divergent collectives are caught
-inline void barrier(int op) {
-  Warp* w = current();
+inline int thread_id() { return current()->cur; }
+inline int lane_id() { return current()->cur & 31; }
+inline int warp_id() { return current()->cur >> 5; }
+
+inline void yield_thread() {
+  Block* b = current();
+  switch_ctx(&b->ctx[b->cur], &b->sched);
+}
+
+// barrier across the 32 fibers of the calling warp; `op` identifies the kind of collective so that lanes that
+// diverged into different collectives are caught
+__attribute__((noinline)) inline void barrier(int op) {
+  Block* b = current();
+  b->where[b->cur] = __builtin_return_address(0);
+  b->hist[b->cur][b->n_warp_bar[b->cur] & 15] = __builtin_return_address(0);
+  ++b->n_warp_bar[b->cur];
+  WarpState* w = &b->warp[b->cur >> 5];
   if (w->arrived == 0) w->op = op;
-  else if (w->op != op) { fprintf(stderr, "simt: lanes diverged into different collectives (%d vs %d)\n", w->op, op); abort(); }
+  else if (w->op != op) {
+    fprintf(stderr, "simt: lanes of a warp diverged into different collectives (%d vs %d; thread %d arrives at %p)\n", w->op, op, b->cur,
+            __builtin_return_address(0));
+    report(b);
+    abort();
+  }
   const unsigned gen = w->generation;
   if (++w->arrived == LANES) {
     w->arrived = 0;
     ++w->generation;
+    ++b->progress;
   } else {
-    while (w->generation == gen) yield_lane();
+    while (w->generation == gen) yield_thread();
+  }
+}
+
+__attribute__((noinline)) inline void block_barrier() {
+  Block* b = current();
+  b->where[b->cur] = __builtin_return_address(0);
+  ++b->n_block_bar[b->cur];
+  const unsigned gen = b->b_generation;
+  if (++b->b_arrived == b->n_threads) {
+    b->b_arrived = 0;
+    ++b->b_generation;
+    ++b->progress;
+  } else {
+    while (b->b_generation == gen) yield_thread();
   }
 }
 
 template <typename T>
 inline T exchange(T v, int src_lane, int op) {
   static_assert(sizeof(T) <= sizeof(long long), "exchange type too wide");
-  Warp* w = current();
+  Block* b = current();
+  WarpState* w = &b->warp[b->cur >> 5];
   long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
-  w->buf[w->cur] = raw;
+  w->buf[b->cur & 31] = raw;
   barrier(op);
   T out = v;
   if (src_lane >= 0 && src_lane < LANES) memcpy(&out, &w->buf[src_lane], sizeof(T));
@@ -132,10 +246,19 @@ inline T exchange(T v, int src_lane, int op) {
   return out;
 }
 
+struct Dim { unsigned x; };
+inline Dim thread_idx() { return Dim{(unsigned)current()->cur}; }
+inline Dim block_idx() { return Dim{current()->block_idx}; }
+
 }  // namespace simt
 
+#define threadIdx (simt::thread_idx())
+#define blockIdx (simt::block_idx())
+#define __shared__
+#define __align__(n)
+#define __launch_bounds__(...)
+
 // ---- the intrinsics nw.cuh uses --------------------------------------------------------------------------------
-struct SimtThreadIdx { int x_get() const { return simt::lane_id(); } };
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange(v, src & 31, 10); }
 template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
   const int l = simt::lane_id();
@@ -143,8 +266,9 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
 }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return simt::exchange(v, simt::lane_id() ^ m, 30); }
 inline unsigned __ballot_sync(unsigned, bool p) {
-  simt::Warp* w = simt::current();
-  w->buf[w->cur] = p ? 1 : 0;
+  simt::Block* b = simt::current();
+  simt::WarpState* w = &b->warp[b->cur >> 5];
+  w->buf[b->cur & 31] = p ? 1 : 0;
   simt::barrier(40);
   unsigned m = 0;
   for (int l = 0; l < simt::LANES; ++l) m |= (unsigned)(w->buf[l] & 1) << l;
@@ -152,6 +276,13 @@ inline unsigned __ballot_sync(unsigned, bool p) {
   return m;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier(50); }
+inline void __syncthreads() { simt::block_barrier(); }
+// (threads run one at a time between barriers, so plain read-modify-write is atomic here)
+template <typename T, typename V> inline T atomicAdd(T* p, V v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+template <typename T, typename V> inline T atomicMax(T* p, V v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <typename T, typename V> inline T atomicCAS(T* p, V cmp, V val) { const T o = *p; if (o == (T)cmp) *p = (T)val; return o; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __vimax3_s32(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }

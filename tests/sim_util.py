@@ -15,13 +15,18 @@ ORDER_NAMES = ["for", "rev", "mid"]
 _BASES = "ACGT"
 
 
-def build(asan=False):
-    name = "libsim_asan.so" if asan else "libsim.so"
+def build(asan=False, simt=False):
+    """libsim.so: single-lane build of the control logic; libsimt_asm.so (simt=True): assemble_kernel itself, W warps
+    of 32 lanes, on the fiber emulator of tests/sim/simt_host.h"""
+    name = "libsimt_asm.so" if simt else ("libsim_asan.so" if asan else "libsim.so")
     so = os.path.join(SIM_DIR, name)
     src = os.path.join(SIM_DIR, "sim_assemble.cpp")
-    deps = [src] + [os.path.join(HERE, "..", "breakmer_b200", "csrc", f) for f in ("assemble.cuh", "nw.cuh", "common.cuh")]
+    deps = [src, os.path.join(SIM_DIR, "simt_host.h")] + \
+           [os.path.join(HERE, "..", "breakmer_b200", "csrc", f) for f in ("assemble.cuh", "nw.cuh", "common.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         flags = ["-O1", "-g", "-fsanitize=address,undefined"] if asan else ["-O2"]
+        if simt:
+            flags = (["-O1", "-g"] if os.environ.get("SIMT_DEBUG") else ["-O2"]) + ["-w", "-DBK_SIMT", "-I", SIM_DIR]
         subprocess.check_call(["g++", "-std=c++17", "-fPIC", "-shared"] + flags + ["-o", so, src])
     return so
 
@@ -59,8 +64,10 @@ def decode_contigs(n_ctg, desc, o_seq, o_locs, o_io, o_ot, o_reads, o_mer, o_pos
     return out
 
 
-def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 23, spec_w=4):
-    lib = ctypes.CDLL(build(asan))
+def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 << 23, spec_w=4, simt=False, score_table=True):
+    lib = ctypes.CDLL(build(asan, simt))
+    if simt:
+        lib.sim_use_score_table(ctypes.c_int(1 if score_table else 0))
     uniq = assembler_py.group_reads(records)
     seqs = [u.seq.encode() for u in uniq]
     roff = np.zeros(len(seqs) + 1, dtype=np.int64)
