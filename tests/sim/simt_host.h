@@ -155,10 +155,24 @@ inline void run_block(int n_warps, unsigned block_idx, const std::function<void(
     makecontext(&b->ctx[t], (void (*)())trampoline, 0);
 #endif
   }
+  // order in which the runnable threads get their turn in a pass: ascending (default), descending, or a fresh
+  // pseudo-random permutation per pass (SIMT_ORDER=reverse|random[:seed]) -- different interleavings of the same kernel
+  const char* ord = getenv("SIMT_ORDER");
+  const int mode = !ord ? 0 : (ord[0] == 'r' && ord[1] == 'e') ? 1 : 2;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull ^ (ord && strchr(ord, ':') ? strtoull(strchr(ord, ':') + 1, nullptr, 10) : 1);
+  int order[MAX_WARPS * LANES];
+  for (int t = 0; t < b->n_threads; ++t) order[t] = mode == 1 ? b->n_threads - 1 - t : t;
   for (;;) {
     int live = 0;
     const unsigned long long before = b->progress;
-    for (int t = 0; t < b->n_threads; ++t) {
+    if (mode == 2)
+      for (int t = b->n_threads - 1; t > 0; --t) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        const int j = (int)(rng % (unsigned)(t + 1));
+        const int tmp = order[t]; order[t] = order[j]; order[j] = tmp;
+      }
+    for (int oi = 0; oi < b->n_threads; ++oi) {
+      const int t = order[oi];
       if (b->done[t]) continue;
       b->cur = t;
       switch_ctx(&b->sched, &b->ctx[t]);

@@ -41,3 +41,16 @@ def test_other_widths_and_the_packed_cell_kernel(spec_w, score_table):
         got, _gst = sim_util.sim_init_assembly(only, region.reads, region.k, region.rc_thresh, region.read_len, simt=True,
                                                spec_w=spec_w, score_table=score_table)
         assert got == exp, (name, spec_w, score_table)
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:7"])
+def test_other_interleavings_and_full_size_regions(order, monkeypatch):
+    """regions of the BASELINE configs (the panel's longest region, a tumour/normal one, a deep amplicon, exome regions)
+    with the threads taking their turns in descending / pseudo-random order instead of ascending"""
+    monkeypatch.setenv("SIMT_ORDER", order)
+    for wl, i in (("C2", 76), ("C3", 5), ("C5", 2), ("C4", 3)):
+        region = synth.config_region(wl, i)
+        _r, _c, _s, only = oracle_sample_only(region)
+        exp = assembler_py.init_assembly(only, region.reads, region.k, region.rc_thresh, region.read_len)
+        got, _gst = sim_util.sim_init_assembly(only, region.reads, region.k, region.rc_thresh, region.read_len, simt=True)
+        assert got == exp, (wl, i, order)

@@ -118,6 +118,17 @@ def test_seeded_pairs_all_kernels(lib):
         check(lib, a, b)
 
 
+def test_other_interleavings(lib, monkeypatch):
+    rng = random.Random(41)
+    for order in ("reverse", "random:5"):
+        monkeypatch.setenv("SIMT_ORDER", order)
+        for _ in range(30):
+            la, lb = rng.choice([37, 100, 101, 128]), rng.choice([60, 150, 260])
+            g = "".join(rng.choice("ACGT") for _ in range(la + lb))
+            ov = rng.randint(5, min(la, lb))
+            check(lib, g[:la], (g[la - ov:la] + g[la:])[:lb])
+
+
 def test_long_sequences_take_the_packed_kernel(lib):
     rng = random.Random(5)
     a = "".join(rng.choice("ACGT") for _ in range(700))
