@@ -1312,7 +1312,7 @@ inline size_t assemble_smem_bytes(int W, int read_cap) {
 // CTAS = resident CTAs per SM the register allocation is bounded for (0: the default of the width)
 template <int W, int CTAS = 0>
 __global__ void __launch_bounds__(32 * W, (CTAS > 0 ? CTAS : (W >= 8 ? 1 : (W == 4 ? ASM_W4_CTAS : (W == 2 ? 5 : ASM_W1_CTAS))))) assemble_kernel(AsmParams P) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BK_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* s_reads = smem_raw;
   uint8_t* s_contig = s_reads + (size_t)W * P.read_cap;
   uint8_t* s_pred = s_contig + ASM_CAP;

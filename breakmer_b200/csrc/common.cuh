@@ -33,6 +33,7 @@ inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o
 #include "simt_host.h"
 #define BK_DEV inline
 #define BK_HD inline
+#define BK_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(simt::dyn_smem())
 namespace bk {
 constexpr int WARP = 32;
 inline int lane() { return simt::lane_id(); }
@@ -52,6 +53,8 @@ inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o
 #include <cuda_runtime.h>
 #define BK_DEV __device__ __forceinline__
 #define BK_HD __host__ __device__ __forceinline__
+// the dynamic shared memory of a kernel (a macro so that the host emulator of tests/sim can supply it)
+#define BK_DYN_SMEM(T, name) extern __shared__ __align__(16) T name[]
 namespace bk {
 constexpr int WARP = 32;
 BK_DEV int lane() { return threadIdx.x & 31; }

@@ -164,7 +164,7 @@ __device__ __forceinline__ void rk_sort_pairs(uint64_t* keys, uint32_t* cnt, int
 }
 
 __global__ void __launch_bounds__(RK_THREADS) region_kmer_kernel(RegionKmerParams P) {
-  extern __shared__ __align__(16) uint8_t rk_smem[];
+  BK_DYN_SMEM(uint8_t, rk_smem);
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(rk_smem);
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_keys + P.smem_cap);
   uint8_t* s_code = reinterpret_cast<uint8_t*>(s_cnt + P.smem_cap);

@@ -20,8 +20,6 @@
 using namespace bk;
 
 #ifdef BK_SIMT
-// the kernel's `extern __shared__ uint8_t smem_raw[]`
-namespace bk { alignas(16) uint8_t smem_raw[256 * 1024]; }
 static int use_tab = 1;
 // 1 (default): aligner warps get a score table (score pass + traceback); 0: the packed-cell kernel, as with BK_NW_PACKED=1
 extern "C" void sim_use_score_table(int on) { use_tab = on; }
@@ -140,8 +138,8 @@ extern "C" int sim_assemble_region(
   P.work_counter = &work_counter; P.work_order = work_order;
   unsigned long long region_cells[1] = {0};
   P.region_cells = region_cells;
-  if (assemble_smem_bytes(W, P.read_cap) > sizeof(bk::smem_raw)) return -100;
-  memset(bk::smem_raw, 0, sizeof(bk::smem_raw));
+  if (assemble_smem_bytes(W, P.read_cap) > 256 * 1024) return -100;
+  memset(simt::dyn_smem(), 0, 256 * 1024);
   const AsmParams PP = P;
   auto body = [&]() {
     switch (W) {

@@ -35,7 +35,7 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 namespace simt {
 
 constexpr int LANES = 32;
-constexpr int MAX_WARPS = 8;
+constexpr int MAX_WARPS = 32;
 constexpr size_t STACK_BYTES = 512 * 1024;
 
 struct WarpState {               // collective in progress on one warp
@@ -70,7 +70,7 @@ typedef ucontext_t Ctx;
 
 struct Block {
   int n_threads = 0;
-  unsigned block_idx = 0;
+  unsigned block_idx = 0, grid_dim = 1;
   Ctx sched;
   Ctx ctx[MAX_WARPS * LANES];
   bool done[MAX_WARPS * LANES];
@@ -128,10 +128,11 @@ inline void trampoline() {
 }
 
 // run `body()` on n_warps x 32 emulated threads of one block until all of them have returned
-inline void run_block(int n_warps, unsigned block_idx, const std::function<void()>& body) {
+inline void run_block(int n_warps, unsigned block_idx, const std::function<void()>& body, unsigned grid_dim = 0) {
   Block* b = new Block;
   b->n_threads = n_warps * LANES;
   b->block_idx = block_idx;
+  b->grid_dim = grid_dim ? grid_dim : block_idx + 1;
   b->body = body;
   b->stacks = (char*)malloc(STACK_BYTES * b->n_threads);
   Block* prev = current();
@@ -263,12 +264,22 @@ inline T exchange(T v, int src_lane, int op) {
 struct Dim { unsigned x; };
 inline Dim thread_idx() { return Dim{(unsigned)current()->cur}; }
 inline Dim block_idx() { return Dim{current()->block_idx}; }
+inline Dim block_dim() { return Dim{(unsigned)current()->n_threads}; }
+inline Dim grid_dim() { return Dim{current()->grid_dim}; }
+
+// the dynamic shared memory of the block that is running (blocks run one at a time)
+inline uint8_t* dyn_smem() {
+  alignas(16) static uint8_t buf[256 * 1024];
+  return buf;
+}
 
 }  // namespace simt
 
 #define threadIdx (simt::thread_idx())
 #define blockIdx (simt::block_idx())
-#define __shared__
+#define blockDim (simt::block_dim())
+#define gridDim (simt::grid_dim())
+#define __shared__ static          // a function-scope __shared__ variable: one copy for all fibers of the (single) running block
 #define __align__(n)
 #define __launch_bounds__(...)
 
@@ -279,6 +290,10 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
   return simt::exchange(v, l - (int)d >= 0 ? l - (int)d : l, 20);
 }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m) { return simt::exchange(v, simt::lane_id() ^ m, 30); }
+template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+  const int l = simt::lane_id();
+  return simt::exchange(v, l + (int)d < simt::LANES ? l + (int)d : l, 60);
+}
 inline unsigned __ballot_sync(unsigned, bool p) {
   simt::Block* b = simt::current();
   simt::WarpState* w = &b->warp[b->cur >> 5];
@@ -293,6 +308,9 @@ inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier(50); }
 inline void __syncthreads() { simt::block_barrier(); }
 // (threads run one at a time between barriers, so plain read-modify-write is atomic here)
 template <typename T, typename V> inline T atomicAdd(T* p, V v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+template <typename T, typename V> inline T atomicOr(T* p, V v) { const T o = *p; *p = (T)(o | (T)v); return o; }
+inline void __threadfence_block() {}
+inline void __threadfence() {}
 template <typename T, typename V> inline T atomicMax(T* p, V v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
 template <typename T, typename V> inline T atomicCAS(T* p, V cmp, V val) { const T o = *p; if (o == (T)cmp) *p = (T)val; return o; }
 inline int min(int a, int b) { return a < b ? a : b; }
