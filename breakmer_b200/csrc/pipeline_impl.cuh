@@ -401,12 +401,14 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
       K.st_mer = h->dev.get<uint64_t>(p.sc.n_bases); K.st_cnt = h->dev.get<uint32_t>(p.sc.n_bases);
       K.seg_counts = seg_counts;
       const size_t smem = (size_t)K.smem_cap * 12 + RK_TILE + 64;
-      BK_CUDA(cudaFuncSetAttribute(region_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int per_sm = std::max<int>(1, (int)((220 * 1024) / (smem + 1024)));
       const int grid_k = (int)std::min<int64_t>(R, (int64_t)h->sm_count * std::min(per_sm, 4) * 2);
       {
         TimedLaunch t(h->timers, st, KF_REGION_KMERS);
+        std::lock_guard<std::mutex> hold(launch_attr_mutex());     // (the limit is per kernel, the size per batch)
+        BK_CUDA(cudaFuncSetAttribute(region_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         region_kmer_kernel<<<grid_k, RK_THREADS, smem, st>>>(K);
+        BK_CUDA(cudaGetLastError());
       }
       uint32_t* seg_excl = h->dev.get<uint32_t>(R + 1);
       uint32_t* stmp = h->dev.get<uint32_t>(scan_tmp_elems(R));
@@ -442,6 +444,7 @@ void pipeline_submit(bk_handle_t h, const bk_batch_input* in) {
       TimedLaunch t(h->timers, st, KF_INDEX);
       const int ws_stride = ((p.max_read_len + 31) / 32) * 32 + 32;
       const size_t idx_smem = (size_t)IDX_WARPS * ws_stride * sizeof(int32_t);
+      std::lock_guard<std::mutex> hold(launch_attr_mutex());
       if (idx_smem > 48 * 1024) BK_CUDA(cudaFuncSetAttribute(index_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)idx_smem));
       index_emit_kernel<<<nblk(NUB, IDX_WARPS), 32 * IDX_WARPS, idx_smem, st>>>(p.reads.bases, p.reads.off, u_off, u_rec, R, d_NU, so_off,
                                                                                 so_mer, k, ik, iv, ik2, iv2, u_bits, s_bits, ws_stride,
