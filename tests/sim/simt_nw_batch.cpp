@@ -1,0 +1,48 @@
+// tests/sim: nw_batch_kernel (breakmer_b200/csrc/nw_batch.cuh, the device side of bk_nw_batch: one warp per pair, four
+// warps per block, optional pointer table + alignment strings) on the host SIMT emulator.  TEST TOOL ONLY.  The host side
+// restates what api.cu does around the launch: scratch sizing and the final flip of the alignment strings.
+#define BK_SIMT 1
+#include <algorithm>
+#include <vector>
+
+#include "../../breakmer_b200/csrc/nw_batch.cuh"
+
+using namespace bk;
+
+// out: n_pairs x 10 ints; aln1 / aln2: caller buffers with aln_off[p] + len(seq1) + len(seq2) bytes per pair
+extern "C" int simt_nw_batch(const uint8_t* seqs, const int64_t* seq_off, int n_seq, const int32_t* pair_a, const int32_t* pair_b,
+                             int64_t n_pairs, int grid, int use_tab, int32_t* out, int want_aln, uint8_t* aln1, uint8_t* aln2,
+                             const int64_t* aln_off, int32_t* aln_len) {
+  (void)n_seq;
+  NwBatchParams P;
+  memset(&P, 0, sizeof P);
+  P.seqs = seqs; P.seq_off = seq_off; P.pair_a = pair_a; P.pair_b = pair_b; P.n_pairs = n_pairs; P.out = out;
+  if (grid < 1) grid = 1;
+  const int64_t warps = (int64_t)grid * NWB_WARPS;
+  std::vector<int2> edge((size_t)warps * 2 * (NW_MAX_LEN + 1));
+  std::vector<uint2> lastcol((size_t)warps * (NW_MAX_LEN / 2 + 1));
+  std::vector<uint8_t> tab(use_tab ? (size_t)warps * NW_TAB_BYTES : 1);
+  P.edge = edge.data(); P.edge_stride = NW_MAX_LEN + 1;
+  P.lastcol = lastcol.data();
+  P.tab = use_tab ? tab.data() : nullptr;
+  P.want_aln = want_aln;
+  std::vector<int64_t> ptr_off(n_pairs + 1, 0);
+  std::vector<uint8_t> ptr;
+  if (want_aln) {
+    for (int64_t p = 0; p < n_pairs; ++p) {
+      const int64_t m = seq_off[pair_a[p] + 1] - seq_off[pair_a[p]], n = seq_off[pair_b[p] + 1] - seq_off[pair_b[p]];
+      ptr_off[p + 1] = ptr_off[p] + (n + 1) * (m + 1);
+    }
+    ptr.assign((size_t)ptr_off[n_pairs] + 1, 0xCC);
+    P.ptr_scratch = ptr.data(); P.ptr_off = ptr_off.data();
+    P.aln1 = aln1; P.aln2 = aln2; P.aln_off = aln_off; P.aln_len = aln_len;
+  }
+  for (int b = 0; b < grid; ++b)
+    simt::run_block(NWB_WARPS, (unsigned)b, [&]() { nw_batch_kernel(P); }, (unsigned)grid);
+  if (want_aln)
+    for (int64_t p = 0; p < n_pairs; ++p) {                       // api.cu: the strings are stored reversed
+      std::reverse(aln1 + aln_off[p], aln1 + aln_off[p] + aln_len[p]);
+      std::reverse(aln2 + aln_off[p], aln2 + aln_off[p] + aln_len[p]);
+    }
+  return 0;
+}

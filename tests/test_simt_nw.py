@@ -140,3 +140,57 @@ def test_long_sequences_take_the_packed_kernel(lib):
     d = "".join(rng.choice("ACGT") for _ in range(1300))      # 100 columns, but more rows than the score table holds
     assert not lib.simt_nw_trace_fits(len(c), len(d))
     check(lib, c, d[:600] + c[40:] + d[600:], modes=(0, 1))
+
+
+# ---- nw_batch_kernel: the device side of bk_nw_batch (four warps per block, pairs strided over the warps) ------------
+@pytest.fixture(scope="module")
+def batch_lib():
+    so = os.path.join(SIM, "libsimt_nw_batch.so")
+    deps = [os.path.join(SIM, "simt_nw_batch.cpp"), os.path.join(SIM, "simt_host.h")] + \
+           [os.path.join(ROOT, "breakmer_b200", "csrc", f) for f in ("nw_batch.cuh", "nw.cuh", "common.cuh")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-I", SIM, "-o", so, deps[0]])
+    return ctypes.CDLL(so)
+
+
+def run_batch(lib, pairs, want_aln, grid=2, use_tab=True):
+    seqs, pa, pb = [], [], []
+    for a, b in pairs:
+        pa.append(len(seqs)); seqs.append(a)
+        pb.append(len(seqs)); seqs.append(b)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    blob = np.frombuffer(("".join(seqs) + "\0").encode(), dtype=np.uint8).copy()
+    pa = np.array(pa, dtype=np.int32); pb = np.array(pb, dtype=np.int32)
+    n = len(pairs)
+    out = np.zeros(n * 10, dtype=np.int32)
+    aln_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(a) + len(b) for a, b in pairs], out=aln_off[1:])
+    a1 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8); a2 = np.zeros_like(a1)
+    alen = np.zeros(n, dtype=np.int32)
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.simt_nw_batch(p(blob), p(off), ctypes.c_int(len(seqs)), p(pa), p(pb), ctypes.c_int64(n), ctypes.c_int(grid),
+                           ctypes.c_int(1 if use_tab else 0), p(out), ctypes.c_int(1 if want_aln else 0), p(a1), p(a2), p(aln_off), p(alen))
+    assert rc == 0
+    res = []
+    for i in range(n):
+        s = int(aln_off[i])
+        res.append((bytes(a1[s:s + alen[i]]).decode(), bytes(a2[s:s + alen[i]]).decode(), [int(v) for v in out[10 * i:10 * i + 10]]))
+    return res
+
+
+def test_batch_kernel_alignment_strings_of_the_reference(batch_lib):
+    """the full tuple olc.nw returns -- both alignment strings and the five integers -- for every golden pair"""
+    cases = [c for c in golden("nw_golden.json")["cases"] if c["seq1"] and c["seq2"]]
+    got = run_batch(batch_lib, [(c["seq1"], c["seq2"]) for c in cases], want_aln=True, grid=3)
+    for c, (a1, a2, o) in zip(cases, got):
+        assert [a1, a2] + o[:5] == c["out"], (c["seq1"], c["seq2"])
+        assert o[5:] == list(nw_py.nw_fast(c["seq2"], c["seq1"])[2:])
+
+
+def test_batch_kernel_without_strings(batch_lib):
+    cases = [c for c in golden("nw_golden.json")["cases"] if c["seq1"] and c["seq2"]][::3]
+    for use_tab in (True, False):
+        got = run_batch(batch_lib, [(c["seq1"], c["seq2"]) for c in cases], want_aln=False, grid=1, use_tab=use_tab)
+        for c, (_a1, _a2, o) in zip(cases, got):
+            assert o[:5] == c["out"][2:]
