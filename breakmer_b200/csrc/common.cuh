@@ -28,9 +28,10 @@ inline int atomic_cas(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p =
 inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 }  // namespace bk
 #elif defined(BK_SIMT)
-// tests/sim only: the warp kernels on a 32-lane host emulator (tests/sim/simt_host.h, fibers + barriers at the warp
-// collectives).  Like BK_SIM this build is a test tool; it is never part of the shipped library.
-#include "simt_host.h"
+// tests/sim only: the kernels on a host SIMT emulator (tests/sim/simt_host.h, fibers + barriers at the warp and block
+// collectives; tests/sim/cuda_runtime.h stands in for the runtime).  Like BK_SIM this build is a test tool; it is
+// never part of the shipped library.
+#include "cuda_runtime.h"
 #define BK_DEV inline
 #define BK_HD inline
 #define BK_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(simt::dyn_smem())

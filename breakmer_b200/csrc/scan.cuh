@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
   }
 }
 
-#ifndef BK_SIMT   // (host launch code: not part of the emulator build of tests/sim)
 // host helper.  `tmp` needs ceil(n / SCAN_TILE) uint32.  out may alias in.
 inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* tmp, uint32_t* grand_total,
                                cudaStream_t st) {
@@ -106,7 +105,6 @@ inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uin
   scan_spine_kernel<<<1, SCAN_THREADS, 0, st>>>(tmp, tiles, grand_total);
   scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, tmp, out);
 }
-#endif
 inline int64_t scan_tmp_elems(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
 
 }  // namespace bk

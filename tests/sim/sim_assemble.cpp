@@ -15,7 +15,11 @@
 #include <algorithm>
 #include <vector>
 
+#ifdef BK_SIMT
+#include "assemble.cuh"                  // the copy under tests/sim/_gen (gen_simt_sources.py)
+#else
 #include "../../breakmer_b200/csrc/assemble.cuh"
+#endif
 
 using namespace bk;
 

@@ -15,9 +15,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <ucontext.h>
 
 #include <functional>
+#include <mutex>
 
 #define __device__
 #define __host__
@@ -39,6 +41,7 @@ constexpr int MAX_WARPS = 32;
 constexpr size_t STACK_BYTES = 512 * 1024;
 
 struct WarpState {               // collective in progress on one warp
+  int lanes = LANES;             // threads of this warp (the last warp of a block may be partial)
   int arrived = 0;
   unsigned generation = 0;
   int op = 0;                    // kind of the collective (all lanes must agree)
@@ -87,7 +90,7 @@ struct Block {
 };
 
 inline Block*& current() {
-  static thread_local Block* b = nullptr;
+  static Block* b = nullptr;       // (guarded by device_mutex: one block at a time)
   return b;
 }
 
@@ -128,13 +131,43 @@ inline void trampoline() {
 }
 
 // run `body()` on n_warps x 32 emulated threads of one block until all of them have returned
-inline void run_block(int n_warps, unsigned block_idx, const std::function<void()>& body, unsigned grid_dim = 0) {
-  Block* b = new Block;
-  b->n_threads = n_warps * LANES;
+// stacks of the fibers: one pool, grown on demand and kept (blocks run one at a time)
+inline char* stack_pool(size_t bytes) {
+  static char* pool = nullptr;
+  static size_t cap = 0;
+  if (bytes > cap) {
+    free(pool);
+    pool = (char*)malloc(bytes);
+    cap = bytes;
+  }
+  return pool;
+}
+
+// one block runs at a time, process-wide: the stack pool, the dynamic shared memory and the function-scope __shared__
+// variables are single copies (host threads that launch concurrently -- two DevicePipelines on one device -- take turns)
+inline std::recursive_mutex& device_mutex() {
+  static std::recursive_mutex m;
+  return m;
+}
+
+inline void run_threads(int n_threads, unsigned block_idx, const std::function<void()>& body, unsigned grid_dim) {
+  std::lock_guard<std::recursive_mutex> hold(device_mutex());
+  if (n_threads < 1 || n_threads > MAX_WARPS * LANES) { fprintf(stderr, "simt: block of %d threads\n", n_threads); abort(); }
+  static Block* reuse = nullptr;
+  Block* b = reuse ? reuse : (reuse = new Block);
+  b->n_threads = n_threads;
   b->block_idx = block_idx;
   b->grid_dim = grid_dim ? grid_dim : block_idx + 1;
   b->body = body;
-  b->stacks = (char*)malloc(STACK_BYTES * b->n_threads);
+  b->b_arrived = 0; b->b_generation = 0; b->progress = 0;
+  for (int w = 0; w < MAX_WARPS; ++w) {
+    b->warp[w] = WarpState();
+    const int left = n_threads - w * LANES;
+    b->warp[w].lanes = left >= LANES ? LANES : (left > 0 ? left : 0);
+  }
+  memset(b->n_warp_bar, 0, sizeof b->n_warp_bar);
+  memset(b->n_block_bar, 0, sizeof b->n_block_bar);
+  b->stacks = stack_pool(STACK_BYTES * (size_t)b->n_threads);
   Block* prev = current();
   current() = b;
   for (int t = 0; t < b->n_threads; ++t) {
@@ -188,8 +221,16 @@ inline void run_block(int n_warps, unsigned block_idx, const std::function<void(
     }
   }
   current() = prev;
-  free(b->stacks);
-  delete b;
+}
+
+inline void run_block(int n_warps, unsigned block_idx, const std::function<void()>& body, unsigned grid_dim = 0) {
+  run_threads(n_warps * LANES, block_idx, body, grid_dim);
+}
+
+// kernel<<<grid, block, smem, stream>>>(args): the blocks one after the other (tests/sim/gen_simt_sources.py rewrites
+// the launch statements of the product's host code into calls of this)
+inline void launch(long long grid, long long block, const std::function<void()>& body) {
+  for (long long g = 0; g < grid; ++g) run_threads((int)block, (unsigned)g, body, (unsigned)grid);
 }
 
 // one warp: body(lane)
@@ -223,7 +264,7 @@ __attribute__((noinline)) inline void barrier(int op) {
     abort();
   }
   const unsigned gen = w->generation;
-  if (++w->arrived == LANES) {
+  if (++w->arrived == w->lanes) {
     w->arrived = 0;
     ++w->generation;
     ++b->progress;
@@ -300,8 +341,21 @@ inline unsigned __ballot_sync(unsigned, bool p) {
   w->buf[b->cur & 31] = p ? 1 : 0;
   simt::barrier(40);
   unsigned m = 0;
-  for (int l = 0; l < simt::LANES; ++l) m |= (unsigned)(w->buf[l] & 1) << l;
+  for (int l = 0; l < w->lanes; ++l) m |= (unsigned)(w->buf[l] & 1) << l;
   simt::barrier(41);
+  return m;
+}
+template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
+  static_assert(sizeof(T) <= sizeof(long long), "match type too wide");
+  simt::Block* b = simt::current();
+  simt::WarpState* w = &b->warp[b->cur >> 5];
+  long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  w->buf[b->cur & 31] = raw;
+  simt::barrier(70);
+  unsigned m = 0;
+  for (int l = 0; l < w->lanes; ++l) m |= (unsigned)(w->buf[l] == raw) << l;
+  simt::barrier(71);
   return m;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier(50); }
@@ -316,6 +370,7 @@ template <typename T, typename V> inline T atomicCAS(T* p, V cmp, V val) { const
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
+inline float __log2f(float x) { return log2f(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __vimax3_s32(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
 inline int __viaddmax_s32(int a, int b, int c) { const int s = a + b; return s > c ? s : c; }

@@ -7,7 +7,11 @@
 #include <algorithm>
 #include <vector>
 
+#ifdef BK_SIMT
+#include "region_kmers.cuh"                  // the copy under tests/sim/_gen (gen_simt_sources.py)
+#else
 #include "../../breakmer_b200/csrc/region_kmers.cuh"
+#endif
 
 using namespace bk;
 

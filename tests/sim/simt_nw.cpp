@@ -3,7 +3,11 @@
 #define BK_SIMT 1
 #include <vector>
 
+#ifdef BK_SIMT
+#include "nw.cuh"                  // the copy under tests/sim/_gen (gen_simt_sources.py)
+#else
 #include "../../breakmer_b200/csrc/nw.cuh"
+#endif
 
 using namespace bk;
 

@@ -5,7 +5,11 @@
 #include <algorithm>
 #include <vector>
 
+#ifdef BK_SIMT
+#include "nw_batch.cuh"                  // the copy under tests/sim/_gen (gen_simt_sources.py)
+#else
 #include "../../breakmer_b200/csrc/nw_batch.cuh"
+#endif
 
 using namespace bk;
 

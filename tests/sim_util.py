@@ -15,18 +15,52 @@ ORDER_NAMES = ["for", "rev", "mid"]
 _BASES = "ACGT"
 
 
+CSRC = os.path.join(HERE, "..", "breakmer_b200", "csrc")
+GEN_DIR = os.path.join(SIM_DIR, "_gen")
+
+
+def _csrc_files():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+
+
+def generate_simt_sources():
+    """tests/sim/_gen: the product sources with their launch statements rewritten for the emulator (gen_simt_sources.py)"""
+    import importlib.util
+    gen = os.path.join(SIM_DIR, "gen_simt_sources.py")
+    stamp = os.path.join(GEN_DIR, "all.cpp")
+    if not os.path.isfile(stamp) or any(os.path.getmtime(d) > os.path.getmtime(stamp) for d in _csrc_files() + [gen]):
+        spec = importlib.util.spec_from_file_location("gen_simt_sources", gen)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.main(GEN_DIR)
+    return GEN_DIR
+
+
+def build_simt(so_name, src_name, extra=()):
+    """an emulator build (tests/sim/simt_host.h + cuda_runtime.h shim) of one harness under tests/sim"""
+    gen_dir = generate_simt_sources()
+    so = os.path.join(SIM_DIR, so_name)
+    src = os.path.join(gen_dir, src_name) if src_name == "all.cpp" else os.path.join(SIM_DIR, src_name)
+    deps = [src, os.path.join(SIM_DIR, "simt_host.h"), os.path.join(SIM_DIR, "cuda_runtime.h"), os.path.join(gen_dir, "all.cpp")]
+    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        flags = ["-O1", "-g"] if os.environ.get("SIMT_DEBUG") else ["-O2"]
+        subprocess.check_call(["g++", "-std=c++17", "-fPIC", "-shared", "-w", "-DBK_SIMT"] + flags + list(extra) +
+                              ["-I", SIM_DIR, "-I", gen_dir, "-o", so, src, "-lpthread"])
+    return so
+
+
 def build(asan=False, simt=False):
     """libsim.so: single-lane build of the control logic; libsimt_asm.so (simt=True): assemble_kernel itself, W warps
     of 32 lanes, on the fiber emulator of tests/sim/simt_host.h"""
-    name = "libsimt_asm.so" if simt else ("libsim_asan.so" if asan else "libsim.so")
+    if simt:
+        return build_simt("libsimt_asm.so", "sim_assemble.cpp")
+    name = "libsim_asan.so" if asan else "libsim.so"
     so = os.path.join(SIM_DIR, name)
     src = os.path.join(SIM_DIR, "sim_assemble.cpp")
     deps = [src, os.path.join(SIM_DIR, "simt_host.h")] + \
            [os.path.join(HERE, "..", "breakmer_b200", "csrc", f) for f in ("assemble.cuh", "nw.cuh", "common.cuh")]
     if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         flags = ["-O1", "-g", "-fsanitize=address,undefined"] if asan else ["-O2"]
-        if simt:
-            flags = (["-O1", "-g"] if os.environ.get("SIMT_DEBUG") else ["-O2"]) + ["-w", "-DBK_SIMT", "-I", SIM_DIR]
         subprocess.check_call(["g++", "-std=c++17", "-fPIC", "-shared"] + flags + ["-o", so, src])
     return so
 
@@ -96,3 +130,9 @@ def sim_init_assembly(mers, records, k, rc_thresh, read_len, asan=False, cap=1 <
     rec_ids = [u.rep_id for u in uniq]
     out = decode_contigs(n_ctg.value, desc, o_seq, o_locs, o_io, o_ot, o_reads, o_mer, o_pos, o_meta, k, rec_ids)
     return out, {"check_align": int(stats[0]), "cells": int(stats[1]), "find_reads": int(stats[2]), "seeds": int(stats[3])}
+
+
+if __name__ == "__main__":
+    so = build_simt("libbreakmer_simt_TESTONLY.so", "all.cpp")
+    print("built", so)
+    print("the GPU tests on the emulator:  BK_LIB=%s python -m pytest tests -m gpu -q --deselect tests/test_bench_contract.py" % so)

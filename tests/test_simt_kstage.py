@@ -21,12 +21,8 @@ BASES = "ACGT"
 
 @pytest.fixture(scope="module")
 def lib():
-    so = os.path.join(SIM, "libsimt_kstage.so")
-    deps = [os.path.join(SIM, "simt_kstage.cpp"), os.path.join(SIM, "simt_host.h")] + \
-           [os.path.join(ROOT, "breakmer_b200", "csrc", f) for f in ("region_kmers.cuh", "kmers.cuh", "scan.cuh", "common.cuh")]
-    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-DBK_SIMT", "-I", SIM, "-o", so, deps[0]])
-    return ctypes.CDLL(so)
+    import sim_util
+    return ctypes.CDLL(sim_util.build_simt("libsimt_kstage.so", "simt_kstage.cpp"))
 
 
 def _pack(per_region):

@@ -19,15 +19,8 @@ SIM = os.path.join(ROOT, "tests", "sim")
 
 @pytest.fixture(scope="module")
 def lib():
-    so = os.path.join(SIM, "libsimt_nw.so")
-    deps = [os.path.join(SIM, "simt_nw.cpp"), os.path.join(SIM, "simt_host.h")] + \
-           [os.path.join(ROOT, "breakmer_b200", "csrc", f) for f in ("nw.cuh", "common.cuh")]
-    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-I", SIM, "-o", so, deps[0]])
-    l = ctypes.CDLL(so)
-    l.simt_nw_dual.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
-                               ctypes.POINTER(ctypes.c_int)]
-    return l
+    import sim_util
+    return ctypes.CDLL(sim_util.build_simt("libsimt_nw.so", "simt_nw.cpp"))
 
 
 def run(lib, cs, rs, mode):
@@ -145,12 +138,8 @@ def test_long_sequences_take_the_packed_kernel(lib):
 # ---- nw_batch_kernel: the device side of bk_nw_batch (four warps per block, pairs strided over the warps) ------------
 @pytest.fixture(scope="module")
 def batch_lib():
-    so = os.path.join(SIM, "libsimt_nw_batch.so")
-    deps = [os.path.join(SIM, "simt_nw_batch.cpp"), os.path.join(SIM, "simt_host.h")] + \
-           [os.path.join(ROOT, "breakmer_b200", "csrc", f) for f in ("nw_batch.cuh", "nw.cuh", "common.cuh")]
-    if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-shared", "-I", SIM, "-o", so, deps[0]])
-    return ctypes.CDLL(so)
+    import sim_util
+    return ctypes.CDLL(sim_util.build_simt("libsimt_nw_batch.so", "simt_nw_batch.cpp"))
 
 
 def run_batch(lib, pairs, want_aln, grid=2, use_tab=True):
