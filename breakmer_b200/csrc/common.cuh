@@ -43,12 +43,11 @@ inline unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 template <typename T> inline T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 inline int popc(unsigned x) { return __builtin_popcount(x); }
 inline int ffs(unsigned x) { return __builtin_ffs((int)x); }
-// (lanes run one at a time between collectives, so plain read-modify-write is atomic here)
-inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
-inline unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline int atomic_add(int* p, int v) { return atomicAdd(p, v); }                    // (the emulator's, simt_host.h)
+inline unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 inline void threadfence() {}
-inline int atomic_cas(int* p, int cmp, int val) { int o = *p; if (o == cmp) *p = val; return o; }
-inline unsigned atomic_max(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+inline int atomic_cas(int* p, int cmp, int val) { return atomicCAS(p, cmp, val); }
+inline unsigned atomic_max(unsigned* p, unsigned v) { return atomicMax(p, v); }
 }  // namespace bk
 #else
 #include <cuda_runtime.h>

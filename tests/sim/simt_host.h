@@ -21,6 +21,17 @@
 #include <functional>
 #include <mutex>
 
+// SIMT_TSAN: the emulator under ThreadSanitizer.  Every emulated thread is a TSan fiber, fiber switches carry NO
+// synchronisation, and the only happens-before edges are the ones the kernel asks for: warp collectives, __syncthreads,
+// kernel boundaries (atomics are real atomics).  TSan then reports what CUDA calls a race: two threads of a block
+// touching the same address, at least one writing, with no barrier in between.
+#ifdef SIMT_TSAN
+#include <sanitizer/tsan_interface.h>
+#define SIMT_NO_TSAN __attribute__((no_sanitize("thread")))
+#else
+#define SIMT_NO_TSAN
+#endif
+
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -83,13 +94,21 @@ struct Block {
   int b_arrived = 0;             // __syncthreads
   unsigned b_generation = 0;
   unsigned long long progress = 0;
+#ifdef SIMT_TSAN
+  void* tsan_fiber[MAX_WARPS * LANES];
+  void* tsan_sched = nullptr;
+  // addresses TSan hangs the happens-before edges on.  Two per barrier, alternating with its generation: a thread that
+  // is still waking from barrier n must not acquire what faster threads release when they arrive at barrier n + 1
+  char sync_launch = 0, sync_done = 0, sync_block[2] = {0, 0};
+  char sync_warp[MAX_WARPS][2];
+#endif
   void* where[MAX_WARPS * LANES];   // return address of the barrier each thread waits at (deadlock report)
   unsigned n_warp_bar[MAX_WARPS * LANES] = {0}, n_block_bar[MAX_WARPS * LANES] = {0};
   void* hist[MAX_WARPS * LANES][16];
   std::function<void()> body;
 };
 
-inline Block*& current() {
+SIMT_NO_TSAN inline Block*& current() {
   static Block* b = nullptr;       // (guarded by device_mutex: one block at a time)
   return b;
 }
@@ -112,7 +131,7 @@ inline void report(Block* b) {
       }
 }
 
-inline void switch_ctx(Ctx* from, Ctx* to) {
+SIMT_NO_TSAN inline void switch_ctx(Ctx* from, Ctx* to) {
 #ifdef SIMT_ASM_SWITCH
   simt_switch(from, *to);
 #else
@@ -120,12 +139,21 @@ inline void switch_ctx(Ctx* from, Ctx* to) {
 #endif
 }
 
-inline void trampoline() {
+SIMT_NO_TSAN inline void trampoline() {
   Block* b = current();
   const int t = b->cur;
+#ifdef SIMT_TSAN
+  __tsan_acquire(&b->sync_launch);           // everything before the launch happens before the kernel's threads
+#endif
   b->body();
+#ifdef SIMT_TSAN
+  __tsan_release(&b->sync_done);             // and the threads happen before whatever follows the block
+#endif
   b->done[t] = true;
   ++b->progress;
+#ifdef SIMT_TSAN
+  __tsan_switch_to_fiber(b->tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
   switch_ctx(&b->ctx[t], &b->sched);
   abort();                         // a finished fiber is never resumed
 }
@@ -168,6 +196,11 @@ inline void run_threads(int n_threads, unsigned block_idx, const std::function<v
   memset(b->n_warp_bar, 0, sizeof b->n_warp_bar);
   memset(b->n_block_bar, 0, sizeof b->n_block_bar);
   b->stacks = stack_pool(STACK_BYTES * (size_t)b->n_threads);
+#ifdef SIMT_TSAN
+  b->tsan_sched = __tsan_get_current_fiber();
+  for (int t = 0; t < b->n_threads; ++t) b->tsan_fiber[t] = __tsan_create_fiber(0);
+  __tsan_release(&b->sync_launch);
+#endif
   Block* prev = current();
   current() = b;
   for (int t = 0; t < b->n_threads; ++t) {
@@ -209,6 +242,9 @@ inline void run_threads(int n_threads, unsigned block_idx, const std::function<v
       const int t = order[oi];
       if (b->done[t]) continue;
       b->cur = t;
+#ifdef SIMT_TSAN
+      __tsan_switch_to_fiber(b->tsan_fiber[t], __tsan_switch_to_fiber_no_sync);
+#endif
       switch_ctx(&b->sched, &b->ctx[t]);
       if (!b->done[t]) ++live;
     }
@@ -220,6 +256,10 @@ inline void run_threads(int n_threads, unsigned block_idx, const std::function<v
       abort();
     }
   }
+#ifdef SIMT_TSAN
+  __tsan_acquire(&b->sync_done);
+  for (int t = 0; t < b->n_threads; ++t) __tsan_destroy_fiber(b->tsan_fiber[t]);
+#endif
   current() = prev;
 }
 
@@ -239,18 +279,21 @@ inline void run_warp(const std::function<void(int)>& body) {
   run_block(1, 0, [&]() { body(lane_id()); });
 }
 
-inline int thread_id() { return current()->cur; }
-inline int lane_id() { return current()->cur & 31; }
-inline int warp_id() { return current()->cur >> 5; }
+SIMT_NO_TSAN inline int thread_id() { return current()->cur; }
+SIMT_NO_TSAN inline int lane_id() { return current()->cur & 31; }
+SIMT_NO_TSAN inline int warp_id() { return current()->cur >> 5; }
 
-inline void yield_thread() {
+SIMT_NO_TSAN inline void yield_thread() {
   Block* b = current();
+#ifdef SIMT_TSAN
+  __tsan_switch_to_fiber(b->tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
   switch_ctx(&b->ctx[b->cur], &b->sched);
 }
 
 // barrier across the 32 fibers of the calling warp; `op` identifies the kind of collective so that lanes that
 // diverged into different collectives are caught
-__attribute__((noinline)) inline void barrier(int op) {
+SIMT_NO_TSAN __attribute__((noinline)) inline void barrier(int op) {
   Block* b = current();
   b->where[b->cur] = __builtin_return_address(0);
   b->hist[b->cur][b->n_warp_bar[b->cur] & 15] = __builtin_return_address(0);
@@ -264,6 +307,10 @@ __attribute__((noinline)) inline void barrier(int op) {
     abort();
   }
   const unsigned gen = w->generation;
+#ifdef SIMT_TSAN
+  char* sync = &b->sync_warp[b->cur >> 5][gen & 1];
+  __tsan_release(sync);
+#endif
   if (++w->arrived == w->lanes) {
     w->arrived = 0;
     ++w->generation;
@@ -271,13 +318,20 @@ __attribute__((noinline)) inline void barrier(int op) {
   } else {
     while (w->generation == gen) yield_thread();
   }
+#ifdef SIMT_TSAN
+  __tsan_acquire(sync);
+#endif
 }
 
-__attribute__((noinline)) inline void block_barrier() {
+SIMT_NO_TSAN __attribute__((noinline)) inline void block_barrier() {
   Block* b = current();
   b->where[b->cur] = __builtin_return_address(0);
   ++b->n_block_bar[b->cur];
   const unsigned gen = b->b_generation;
+#ifdef SIMT_TSAN
+  char* sync = &b->sync_block[gen & 1];
+  __tsan_release(sync);
+#endif
   if (++b->b_arrived == b->n_threads) {
     b->b_arrived = 0;
     ++b->b_generation;
@@ -285,10 +339,13 @@ __attribute__((noinline)) inline void block_barrier() {
   } else {
     while (b->b_generation == gen) yield_thread();
   }
+#ifdef SIMT_TSAN
+  __tsan_acquire(sync);
+#endif
 }
 
 template <typename T>
-inline T exchange(T v, int src_lane, int op) {
+SIMT_NO_TSAN inline T exchange(T v, int src_lane, int op) {
   static_assert(sizeof(T) <= sizeof(long long), "exchange type too wide");
   Block* b = current();
   WarpState* w = &b->warp[b->cur >> 5];
@@ -303,10 +360,10 @@ inline T exchange(T v, int src_lane, int op) {
 }
 
 struct Dim { unsigned x; };
-inline Dim thread_idx() { return Dim{(unsigned)current()->cur}; }
-inline Dim block_idx() { return Dim{current()->block_idx}; }
-inline Dim block_dim() { return Dim{(unsigned)current()->n_threads}; }
-inline Dim grid_dim() { return Dim{current()->grid_dim}; }
+SIMT_NO_TSAN inline Dim thread_idx() { return Dim{(unsigned)current()->cur}; }
+SIMT_NO_TSAN inline Dim block_idx() { return Dim{current()->block_idx}; }
+SIMT_NO_TSAN inline Dim block_dim() { return Dim{(unsigned)current()->n_threads}; }
+SIMT_NO_TSAN inline Dim grid_dim() { return Dim{current()->grid_dim}; }
 
 // the dynamic shared memory of the block that is running (blocks run one at a time)
 inline uint8_t* dyn_smem() {
@@ -335,7 +392,7 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   const int l = simt::lane_id();
   return simt::exchange(v, l + (int)d < simt::LANES ? l + (int)d : l, 60);
 }
-inline unsigned __ballot_sync(unsigned, bool p) {
+SIMT_NO_TSAN inline unsigned __ballot_sync(unsigned, bool p) {
   simt::Block* b = simt::current();
   simt::WarpState* w = &b->warp[b->cur >> 5];
   w->buf[b->cur & 31] = p ? 1 : 0;
@@ -345,7 +402,7 @@ inline unsigned __ballot_sync(unsigned, bool p) {
   simt::barrier(41);
   return m;
 }
-template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
+template <typename T> SIMT_NO_TSAN inline unsigned __match_any_sync(unsigned, T v) {
   static_assert(sizeof(T) <= sizeof(long long), "match type too wide");
   simt::Block* b = simt::current();
   simt::WarpState* w = &b->warp[b->cur >> 5];
@@ -360,13 +417,29 @@ template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier(50); }
 inline void __syncthreads() { simt::block_barrier(); }
-// (threads run one at a time between barriers, so plain read-modify-write is atomic here)
+// (threads run one at a time between barriers, so plain read-modify-write is atomic here; under SIMT_TSAN they are real
+// atomics so that TSan knows them as such)
+#ifdef SIMT_TSAN
+template <typename T, typename V> inline T atomicAdd(T* p, V v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+template <typename T, typename V> inline T atomicOr(T* p, V v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_RELAXED); }
+template <typename T, typename V> inline T atomicMax(T* p, V v) {
+  T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while ((T)v > o && !__atomic_compare_exchange_n(p, &o, (T)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return o;
+}
+template <typename T, typename V> inline T atomicCAS(T* p, V cmp, V val) {
+  T o = (T)cmp;
+  __atomic_compare_exchange_n(p, &o, (T)val, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+  return o;
+}
+#else
 template <typename T, typename V> inline T atomicAdd(T* p, V v) { const T o = *p; *p = (T)(o + (T)v); return o; }
 template <typename T, typename V> inline T atomicOr(T* p, V v) { const T o = *p; *p = (T)(o | (T)v); return o; }
-inline void __threadfence_block() {}
-inline void __threadfence() {}
 template <typename T, typename V> inline T atomicMax(T* p, V v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
 template <typename T, typename V> inline T atomicCAS(T* p, V cmp, V val) { const T o = *p; if (o == (T)cmp) *p = (T)val; return o; }
+#endif
+inline void __threadfence_block() {}
+inline void __threadfence() {}
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int __ffs(int x) { return __builtin_ffs(x); }

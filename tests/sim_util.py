@@ -49,6 +49,19 @@ def build_simt(so_name, src_name, extra=()):
     return so
 
 
+def build_tsan_driver():
+    """tests/sim/simt_tsan_driver: the whole emulated library in one executable built with -fsanitize=thread; every
+    emulated GPU thread is a TSan fiber and the kernels' barriers are the only happens-before edges"""
+    gen_dir = generate_simt_sources()
+    exe = os.path.join(SIM_DIR, "simt_tsan_driver")
+    src = os.path.join(SIM_DIR, "simt_tsan_driver.cpp")
+    deps = [src, os.path.join(SIM_DIR, "simt_host.h"), os.path.join(SIM_DIR, "cuda_runtime.h"), os.path.join(gen_dir, "all.cpp")]
+    if not os.path.isfile(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-DBK_SIMT", "-DSIMT_TSAN", "-fsanitize=thread",
+                               "-I", SIM_DIR, "-I", gen_dir, "-o", exe, src, "-lpthread"])
+    return exe
+
+
 def build(asan=False, simt=False):
     """libsim.so: single-lane build of the control logic; libsimt_asm.so (simt=True): assemble_kernel itself, W warps
     of 32 lanes, on the fiber emulator of tests/sim/simt_host.h"""

@@ -1,0 +1,81 @@
+"""Race detection for the kernel source: the emulator of tests/sim/simt_host.h under ThreadSanitizer.  Every emulated GPU
+thread is a TSan fiber; fiber switches carry no synchronisation, so the only happens-before edges TSan sees are the ones
+the kernels create -- warp collectives, __syncthreads(), kernel boundaries; atomics are real atomics.  A report is then
+what CUDA calls a data race: two threads of a block touching the same address, at least one writing, with no barrier
+between them.  (compute-sanitizer's racecheck covers shared memory on the device; this covers global memory too, in the
+container without a GPU.)
+
+  * the detector is tested on the pattern it was built for, with and without the barrier;
+  * the whole library (tests/sim/simt_tsan_driver.cpp: ingest -> bk_compare_kmers_batch, every kernel) runs golden
+    regions under it: no reports, results equal to the oracle."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+import sim_util
+from breakmer_b200 import synth
+from oracle import assembler_py
+from oracle.make_golden import oracle_sample_only, region_scenarios
+
+ENV = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+
+
+def _tsan_works():
+    return subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", os.devnull], input="int main(){return 0;}",
+                          capture_output=True, text=True).returncode == 0
+
+
+pytestmark = pytest.mark.skipif(not _tsan_works(), reason="g++ -fsanitize=thread is not usable here")
+
+
+def test_the_detector_sees_the_flag_race_and_accepts_the_fix(tmp_path):
+    exe = os.path.join(str(tmp_path), "selftest")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-DSIMT_TSAN", "-fsanitize=thread", "-I", sim_util.SIM_DIR,
+                           "-o", exe, os.path.join(sim_util.SIM_DIR, "simt_tsan_selftest.cpp")])
+    racy = subprocess.run([exe, "racy"], env=ENV, capture_output=True, text=True)
+    assert racy.stderr.count("WARNING: ThreadSanitizer: data race") >= 1 and "simt_tsan_selftest.cpp" in racy.stderr
+    fixed = subprocess.run([exe, "fixed"], env=ENV, capture_output=True, text=True)
+    assert fixed.returncode == 0 and "ThreadSanitizer" not in fixed.stderr and "done" in fixed.stdout
+
+
+def _write_region(r, d):
+    base = os.path.join(d, r.name)
+    with open(base + "_ref.fa", "w") as f:
+        f.write(">%s\n%s\n" % (r.name, r.ref_fwd))
+    with open(base + ".fastq", "w") as f:
+        for rid, seq, qual, _io in r.reads:
+            f.write("%s\n%s\n+\n%s\n" % (rid, seq, qual))
+    with open(base + "_sc.fa", "w") as f:
+        for name, seq in r.sc_records:
+            f.write(">%s\n%s\n" % (name, seq))
+    return "\t".join([base + "_ref.fa", base + ".fastq", base + "_sc.fa"])
+
+
+@pytest.mark.parametrize("order", [None, "random:3"])
+def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
+    exe = sim_util.build_tsan_driver()
+    scen = [s for s in region_scenarios() if s[1]["k"] == 15]
+    regions = [synth.make_region(n, **kw) for n, kw in (scen[i] for i in (0, 2, 4, 9, 13, 14))]
+    d = tempfile.mkdtemp(prefix="bk_tsan_")
+    man = os.path.join(d, "manifest.txt")
+    with open(man, "w") as f:
+        f.write("\n".join(_write_region(r, d) for r in regions) + "\n")
+    env = dict(ENV)
+    if order:
+        env["SIMT_ORDER"] = order
+    out = subprocess.run([exe, man, "15", str(regions[0].rc_thresh)], env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[:4000]
+    got, cur = {}, None
+    for line in out.stdout.splitlines():
+        p = line.split()
+        if p[0] == "region":
+            cur = int(p[1]); got[cur] = (int(p[5]), [])
+        elif p[0] == "contig":
+            got[cur][1].append(p[1])
+    for i, r in enumerate(regions):
+        _a, _b, _c, only = oracle_sample_only(r)
+        exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
+        assert got[i] == (len(only), [c["seq"] for c in exp]), r.name
