@@ -19,7 +19,8 @@ from breakmer_b200 import synth
 from oracle import assembler_py
 from oracle.make_golden import oracle_sample_only, region_scenarios
 
-ENV = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+SUPP = os.path.join(sim_util.SIM_DIR, "tsan_suppressions.txt")      # one documented benign race (plain read next to an atomicOr)
+ENV = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 suppressions=%s" % SUPP)
 
 
 def _tsan_works():
@@ -50,7 +51,13 @@ def _write_region(r, d):
     with open(base + "_sc.fa", "w") as f:
         for name, seq in r.sc_records:
             f.write(">%s\n%s\n" % (name, seq))
-    return "\t".join([base + "_ref.fa", base + ".fastq", base + "_sc.fa"])
+    cols = [base + "_ref.fa", base + ".fastq", base + "_sc.fa"]
+    if r.normal_reads:
+        with open(base + "_normal.fastq", "w") as f:
+            for rec in r.normal_reads:
+                f.write("@%s\n%s\n+\n%s\n" % (rec[0].lstrip("@"), rec[1], "I" * len(rec[1])))
+        cols.append(base + "_normal.fastq")
+    return "\t".join(cols)
 
 
 @pytest.mark.parametrize("order", [None, "random:3"])
@@ -58,6 +65,8 @@ def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
     exe = sim_util.build_tsan_driver()
     scen = [s for s in region_scenarios() if s[1]["k"] == 15]
     regions = [synth.make_region(n, **kw) for n, kw in (scen[i] for i in (0, 2, 4, 9, 13, 14))]
+    if order:
+        regions.append(synth.config_region("C3", 2))            # a tumour / normal region (normal subtraction, K4)
     d = tempfile.mkdtemp(prefix="bk_tsan_")
     man = os.path.join(d, "manifest.txt")
     with open(man, "w") as f:
@@ -79,3 +88,4 @@ def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
         _a, _b, _c, only = oracle_sample_only(r)
         exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
         assert got[i] == (len(only), [c["seq"] for c in exp]), r.name
+    assert "ThreadSanitizer" not in out.stderr
