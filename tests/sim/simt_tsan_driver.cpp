@@ -54,6 +54,65 @@ int main(int argc, char** argv) {
     for (int64_t c = res.ctg_reg_off[r]; c < res.ctg_reg_off[r + 1]; ++c)
       printf("contig %.*s\n", (int)res.ctg_seq_off[2 * c + 1], res.ctg_seq + res.ctg_seq_off[2 * c]);
   }
+  // ---- the other entry points, on the records of region 0 (their kernels are not on the batched path) -------------
+  {
+    const int64_t r0 = in.read_reg_off[0], r1 = in.read_reg_off[1];
+    const int64_t n_rec = r1 - r0;
+    std::vector<int64_t> off(n_rec + 1);
+    for (int64_t i = 0; i <= n_rec; ++i) off[i] = in.read_off[r0 + i] - in.read_off[r0];
+    const char* bases = in.read_bases + in.read_off[r0];
+    const uint64_t *m_case, *m_sc, *m_ref, *m_only;
+    const uint32_t *c_case, *c_sc, *c_ref, *c_only;
+    int64_t n_case = 0, n_sc = 0, n_ref = 0, n_only = 0;
+    int rc = bk_count_kmers(h, bases, off.data(), n_rec, nullptr, in.k, &m_case, &c_case, &n_case);
+    std::vector<uint64_t> case_m(m_case, m_case + n_case);
+    std::vector<uint32_t> case_c(c_case, c_case + n_case);
+    const int64_t s0 = in.sc_reg_off[0], s1 = in.sc_reg_off[1];
+    std::vector<int64_t> soff(s1 - s0 + 1);
+    for (int64_t i = 0; i <= s1 - s0; ++i) soff[i] = in.sc_off[s0 + i] - in.sc_off[s0];
+    rc |= bk_count_kmers(h, in.sc_bases + in.sc_off[s0], soff.data(), s1 - s0, nullptr, in.k, &m_sc, &c_sc, &n_sc);
+    std::vector<uint64_t> sc_m(m_sc, m_sc + n_sc);
+    int64_t roff[2] = {0, in.ref_off[1] - in.ref_off[0]};
+    rc |= bk_count_kmers(h, in.ref_bases, roff, 1, nullptr, in.k, &m_ref, &c_ref, &n_ref);
+    std::vector<uint64_t> ref_m(m_ref, m_ref + n_ref);
+    rc |= bk_sample_only(h, in.k, case_m.data(), case_c.data(), n_case, sc_m.data(), n_sc, ref_m.data(), n_ref, nullptr, 0,
+                         &m_only, &c_only, &n_only);
+    printf("count_kmers rc %d case %lld sc %lld ref %lld sample_only(forward reference only) %lld\n", rc, (long long)n_case,
+           (long long)n_sc, (long long)n_ref, (long long)n_only);
+    // olc.nw over neighbouring reads, with and without alignment strings
+    const int64_t n_pairs = n_rec > 41 ? 40 : (n_rec > 1 ? n_rec - 1 : 0);
+    if (n_pairs > 0) {
+      std::vector<int32_t> pa(n_pairs), pb(n_pairs), out(n_pairs * 10), alen(n_pairs);
+      std::vector<int64_t> aoff(n_pairs + 1, 0);
+      for (int64_t p = 0; p < n_pairs; ++p) {
+        pa[p] = (int32_t)p; pb[p] = (int32_t)p + 1;
+        aoff[p + 1] = aoff[p] + (off[p + 1] - off[p]) + (off[p + 2] - off[p + 1]);
+      }
+      std::vector<char> a1(aoff[n_pairs] + 1), a2(aoff[n_pairs] + 1);
+      int rn = bk_nw_batch(h, bases, off.data(), n_rec, pa.data(), pb.data(), n_pairs, out.data(), 1, a1.data(), a2.data(), aoff.data(), alen.data());
+      long long sum = 0;
+      for (int64_t p = 0; p < n_pairs; ++p) sum += out[p * 10 + 4] + alen[p];
+      rn |= bk_nw_batch(h, bases, off.data(), n_rec, pa.data(), pb.data(), n_pairs, out.data(), 0, nullptr, nullptr, nullptr, nullptr);
+      printf("nw_batch rc %d pairs %lld checksum %lld\n", rn, (long long)n_pairs, sum);
+      // read redundancy: the first reads as two batches
+      const int64_t nd = n_rec > 16 ? 16 : n_rec;
+      std::vector<int32_t> mer_pos(nd, 0);
+      int64_t boff[3] = {0, nd / 2, nd};
+      std::vector<uint8_t> check(nd), flags(nd);
+      int64_t npairs = 0; int32_t nl = 0;
+      int rd = bk_dedup_reads(h, bases, off.data(), nd, mer_pos.data(), boff, 2, 0.90, check.data(), flags.data(), &npairs, &nl);
+      printf("dedup rc %d alignments %lld launches %d\n", rd, (long long)npairs, nl);
+    }
+    // the reference k-mer cache instead of the reference sequences
+    const long long contigs_before = (long long)res.n_contigs;
+    int rcache = bk_ref_cache_build(h, in.ref_bases, in.ref_off, R, in.k);
+    bk_batch_input in2 = in;
+    in2.ref_bases = nullptr; in2.ref_off = nullptr;
+    bk_batch_result res2;
+    rcache |= bk_compare_kmers_batch(h, &in2, &res2);
+    printf("ref_cache rc %d contigs %lld (with sequences: %lld)\n", rcache, (long long)res2.n_contigs, contigs_before);
+    bk_ref_cache_clear(h);
+  }
   bk_destroy(h);
   bk_ingest_destroy(g);
   return 0;

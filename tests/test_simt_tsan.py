@@ -6,8 +6,9 @@ between them.  (compute-sanitizer's racecheck covers shared memory on the device
 container without a GPU.)
 
   * the detector is tested on the pattern it was built for, with and without the barrier;
-  * the whole library (tests/sim/simt_tsan_driver.cpp: ingest -> bk_compare_kmers_batch, every kernel) runs golden
-    regions under it: no reports, results equal to the oracle."""
+  * the whole library (tests/sim/simt_tsan_driver.cpp: ingest -> bk_compare_kmers_batch, then bk_count_kmers,
+    bk_sample_only, bk_nw_batch, bk_dedup_reads and the reference k-mer cache: every kernel) runs golden regions under
+    it: no reports, results equal to the oracle."""
 import os
 import subprocess
 import tempfile
@@ -89,3 +90,8 @@ def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
         exp = assembler_py.init_assembly(only, r.reads, r.k, r.rc_thresh, r.read_len)
         assert got[i] == (len(only), [c["seq"] for c in exp]), r.name
     assert "ThreadSanitizer" not in out.stderr
+    # the entry points beside the batched path ran under the detector too (bk_count_kmers / bk_sample_only, bk_nw_batch
+    # with and without alignment strings, bk_dedup_reads, the reference k-mer cache)
+    legs = {l.split()[0]: l.split() for l in out.stdout.splitlines() if l.split()[0] in ("count_kmers", "nw_batch", "dedup", "ref_cache")}
+    assert sorted(legs) == ["count_kmers", "dedup", "nw_batch", "ref_cache"] and all(v[1:3] == ["rc", "0"] for v in legs.values())
+    assert legs["ref_cache"][4] == legs["ref_cache"][-1].rstrip(")")            # same contigs with the cache as with the sequences
