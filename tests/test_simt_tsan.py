@@ -37,6 +37,8 @@ def test_the_detector_sees_the_flag_race_and_accepts_the_fix(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-DSIMT_TSAN", "-fsanitize=thread", "-I", sim_util.SIM_DIR,
                            "-o", exe, os.path.join(sim_util.SIM_DIR, "simt_tsan_selftest.cpp")])
     racy = subprocess.run([exe, "racy"], env=ENV, capture_output=True, text=True)
+    if "unexpected memory mapping" in racy.stderr:
+        pytest.skip("the ThreadSanitizer runtime cannot map its shadow memory on this kernel configuration")
     assert racy.stderr.count("WARNING: ThreadSanitizer: data race") >= 1 and "simt_tsan_selftest.cpp" in racy.stderr
     fixed = subprocess.run([exe, "fixed"], env=ENV, capture_output=True, text=True)
     assert fixed.returncode == 0 and "ThreadSanitizer" not in fixed.stderr and "done" in fixed.stdout
@@ -76,6 +78,8 @@ def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
     if order:
         env["SIMT_ORDER"] = order
     out = subprocess.run([exe, man, "15", str(regions[0].rc_thresh)], env=env, capture_output=True, text=True, timeout=1200)
+    if "unexpected memory mapping" in out.stderr:
+        pytest.skip("the ThreadSanitizer runtime cannot map its shadow memory on this kernel configuration")
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ThreadSanitizer" not in out.stderr, out.stderr[:4000]
     got, cur = {}, None
