@@ -160,6 +160,7 @@ SIMT_NO_TSAN inline void trampoline() {
 
 // run `body()` on n_warps x 32 emulated threads of one block until all of them have returned
 // stacks of the fibers: one pool, grown on demand and kept (blocks run one at a time)
+inline uint8_t* dyn_smem();
 inline char* stack_pool(size_t bytes) {
   static char* pool = nullptr;
   static size_t cap = 0;
@@ -196,6 +197,7 @@ inline void run_threads(int n_threads, unsigned block_idx, const std::function<v
   memset(b->n_warp_bar, 0, sizeof b->n_warp_bar);
   memset(b->n_block_bar, 0, sizeof b->n_block_bar);
   b->stacks = stack_pool(STACK_BYTES * (size_t)b->n_threads);
+  if (!getenv("SIMT_KEEP_SMEM")) memset(dyn_smem(), 0xEE, 232 * 1024);  // shared memory of a new block holds garbage
 #ifdef SIMT_TSAN
   b->tsan_sched = __tsan_get_current_fiber();
   for (int t = 0; t < b->n_threads; ++t) b->tsan_fiber[t] = __tsan_create_fiber(0);
