@@ -25,6 +25,10 @@
 // synchronisation, and the only happens-before edges are the ones the kernel asks for: warp collectives, __syncthreads,
 // kernel boundaries (atomics are real atomics).  TSan then reports what CUDA calls a race: two threads of a block
 // touching the same address, at least one writing, with no barrier in between.
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define SIMT_ASAN 1
+#endif
 #ifdef SIMT_TSAN
 #include <sanitizer/tsan_interface.h>
 #define SIMT_NO_TSAN __attribute__((no_sanitize("thread")))
@@ -139,9 +143,18 @@ SIMT_NO_TSAN inline void switch_ctx(Ctx* from, Ctx* to) {
 #endif
 }
 
+#ifdef SIMT_ASAN
+// AddressSanitizer has to be told about every stack switch (stack bounds of the destination)
+struct AsanStacks { const void* sched_bottom = nullptr; size_t sched_size = 0; };
+inline AsanStacks& asan_stacks() { static AsanStacks a; return a; }
+#endif
+
 SIMT_NO_TSAN inline void trampoline() {
   Block* b = current();
   const int t = b->cur;
+#ifdef SIMT_ASAN
+  __sanitizer_finish_switch_fiber(nullptr, &asan_stacks().sched_bottom, &asan_stacks().sched_size);
+#endif
 #ifdef SIMT_TSAN
   __tsan_acquire(&b->sync_launch);           // everything before the launch happens before the kernel's threads
 #endif
@@ -153,6 +166,9 @@ SIMT_NO_TSAN inline void trampoline() {
   ++b->progress;
 #ifdef SIMT_TSAN
   __tsan_switch_to_fiber(b->tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
+#ifdef SIMT_ASAN
+  __sanitizer_start_switch_fiber(nullptr, asan_stacks().sched_bottom, asan_stacks().sched_size);   // this fiber is done
 #endif
   switch_ctx(&b->ctx[t], &b->sched);
   abort();                         // a finished fiber is never resumed
@@ -247,7 +263,14 @@ inline void run_threads(int n_threads, unsigned block_idx, const std::function<v
 #ifdef SIMT_TSAN
       __tsan_switch_to_fiber(b->tsan_fiber[t], __tsan_switch_to_fiber_no_sync);
 #endif
+#ifdef SIMT_ASAN
+      void* fake = nullptr;
+      __sanitizer_start_switch_fiber(&fake, b->stacks + STACK_BYTES * (size_t)t, STACK_BYTES);
+#endif
       switch_ctx(&b->sched, &b->ctx[t]);
+#ifdef SIMT_ASAN
+      __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
       if (!b->done[t]) ++live;
     }
     if (live == 0) break;
@@ -290,7 +313,14 @@ SIMT_NO_TSAN inline void yield_thread() {
 #ifdef SIMT_TSAN
   __tsan_switch_to_fiber(b->tsan_sched, __tsan_switch_to_fiber_no_sync);
 #endif
+#ifdef SIMT_ASAN
+  void* fake = nullptr;
+  __sanitizer_start_switch_fiber(&fake, asan_stacks().sched_bottom, asan_stacks().sched_size);
+#endif
   switch_ctx(&b->ctx[b->cur], &b->sched);
+#ifdef SIMT_ASAN
+  __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
 }
 
 // barrier across the 32 fibers of the calling warp; `op` identifies the kind of collective so that lanes that

@@ -62,6 +62,20 @@ def build_tsan_driver():
     return exe
 
 
+def build_asan_driver():
+    """tests/sim/simt_asan_driver: the same executable under AddressSanitizer + UBSan, with every arena allocation of the
+    library turned into an exact-size malloc (-DSIMT_ARENA_MALLOC, patched in by gen_simt_sources.py), so that a kernel
+    touching one element past ANY device or pinned array is reported with its source line"""
+    gen_dir = generate_simt_sources()
+    exe = os.path.join(SIM_DIR, "simt_asan_driver")
+    src = os.path.join(SIM_DIR, "simt_tsan_driver.cpp")
+    deps = [src, os.path.join(SIM_DIR, "simt_host.h"), os.path.join(SIM_DIR, "cuda_runtime.h"), os.path.join(gen_dir, "all.cpp")]
+    if not os.path.isfile(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-w", "-DBK_SIMT", "-DSIMT_ARENA_MALLOC", "-fsanitize=address,undefined",
+                               "-I", SIM_DIR, "-I", gen_dir, "-o", exe, src, "-lpthread"])
+    return exe
+
+
 def build(asan=False, simt=False):
     """libsim.so: single-lane build of the control logic; libsimt_asm.so (simt=True): assemble_kernel itself, W warps
     of 32 lanes, on the fiber emulator of tests/sim/simt_host.h"""

@@ -63,6 +63,25 @@ def _write_region(r, d):
     return "\t".join(cols)
 
 
+def test_whole_library_under_address_sanitizer():
+    """The same executable under AddressSanitizer + UBSan with every arena allocation turned into an exact-size malloc: a
+    kernel touching one element past any device / pinned array would be reported.  Opt-in (BK_TEST_ASAN=1: the build takes
+    a minute); the result on the final source is in profiles/r2_emulator_runs.md."""
+    if not os.environ.get("BK_TEST_ASAN"):
+        pytest.skip("set BK_TEST_ASAN=1 to build and run the AddressSanitizer executable")
+    exe = sim_util.build_asan_driver()
+    scen = [s for s in region_scenarios() if s[1]["k"] == 15]
+    regions = [synth.make_region(n, **kw) for n, kw in scen[:8]] + [synth.config_region("C3", 2)]
+    d = tempfile.mkdtemp(prefix="bk_asan_")
+    man = os.path.join(d, "manifest.txt")
+    with open(man, "w") as f:
+        f.write("\n".join(_write_region(r, d) for r in regions) + "\n")
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+    out = subprocess.run([exe, man, "15", str(regions[0].rc_thresh)], env=env, capture_output=True, text=True, timeout=1800)
+    assert out.returncode == 0 and "Sanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[:4000]
+    assert out.stdout.count("region ") == len(regions)
+
+
 @pytest.mark.parametrize("order", ["random:3"])
 def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
     exe = sim_util.build_tsan_driver()
