@@ -11,6 +11,7 @@
 #include "kmers.cuh"
 #include "region_kmers.cuh"
 #include "nw_batch.cuh"
+#include "nw_long.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "pipeline.cuh"
@@ -260,24 +261,37 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
         if (seq_off[q + 1] < seq_off[q]) fail(BK_ERR_ARG, "bk_nw_batch: seq_off not monotone at %lld", (long long)q);
     }
     int max_m = 0;
-    std::vector<int64_t> ptr_off;
-    int64_t ptr_total = 0, aln_total = 0, aln_end_prev = 0;
+    std::vector<int64_t> ptr_off, long_idx, long_ptr_off;
+    int64_t ptr_total = 0, aln_total = 0, aln_end_prev = 0, long_max = 0, long_ptr_total = 0;
     if (want_aln) ptr_off.resize(n_pairs);
     for (int64_t p = 0; p < n_pairs; ++p) {
       const int a = pair_a[p], b = pair_b[p];
       if (a < 0 || a >= n_seq || b < 0 || b >= n_seq) fail(BK_ERR_ARG, "bk_nw_batch: pair %lld out of range", (long long)p);
       const int64_t m = seq_off[a + 1] - seq_off[a], n = seq_off[b + 1] - seq_off[b];
       if (m <= 0 || n <= 0) fail(BK_ERR_EMPTY_SEQ, "nw: empty sequence in pair %lld (olc.nw raises NameError)", (long long)p);
-      if (m > NW_MAX_LEN || n > NW_MAX_LEN)
-        fail(BK_ERR_CAPACITY, "nw: sequence longer than %d bases in pair %lld", NW_MAX_LEN, (long long)p);
-      max_m = std::max<int>(max_m, (int)m);
+      // olc.nw has no length limit (olc.py:40-52): pairs beyond the packed-cell kernels' 4095 bases take nw_long_kernel
+      const bool is_long = m > NW_MAX_LEN || n > NW_MAX_LEN;
+      if (m >= (int64_t(1) << 30) || n >= (int64_t(1) << 30))
+        fail(BK_ERR_CAPACITY, "nw: sequence of 2^30 bases or more in pair %lld", (long long)p);
+      if (is_long) {
+        long_idx.push_back(p);
+        long_max = std::max(long_max, std::max(m, n));
+      } else {
+        max_m = std::max<int>(max_m, (int)m);
+      }
       if (want_aln) {
         // the two strings of pair p occupy [aln_off[p], aln_off[p] + m + n): non-negative, and not overlapping the next pair's
         if (aln_off[p] < 0 || (p > 0 && aln_off[p] < aln_end_prev))
           fail(BK_ERR_ARG, "bk_nw_batch: aln_off[%lld] is negative or overlaps the previous pair's strings", (long long)p);
         aln_end_prev = aln_off[p] + m + n;
-        ptr_off[p] = ptr_total;
-        ptr_total += (m + 1) * (n + 1);
+        if (is_long) {
+          long_ptr_off.push_back(long_ptr_total);
+          long_ptr_total += (m + 1) * (n + 1);
+          ptr_off[p] = 0;
+        } else {
+          ptr_off[p] = ptr_total;
+          ptr_total += (m + 1) * (n + 1);
+        }
         aln_total = std::max<int64_t>(aln_total, aln_off[p] + m + n);
       }
     }
@@ -335,6 +349,33 @@ void nw_batch_run(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64
       nw_batch_kernel<<<grid, NWB_WARPS * 32, 0, h->st>>>(P);
     }
     BK_CUDA(cudaGetLastError());
+    if (!long_idx.empty()) {                           // rare: one CTA per (pair, direction), 32-bit anti-diagonal sweep
+      NwLongParams Q{};
+      const size_t n_long = long_idx.size();
+      Q.seqs = P.seqs;
+      Q.seq_off = P.seq_off;
+      Q.pair_a = P.pair_a;
+      Q.pair_b = P.pair_b;
+      Q.long_idx = to_device(h, h->dev, long_idx.data(), n_long);
+      Q.out = P.out;
+      Q.diag_stride = (long_max + 1 + 31) & ~int64_t(31);
+      Q.diag = h->dev.get<int32_t>(2 * n_long * 9 * (size_t)Q.diag_stride);
+      Q.want_aln = want_aln;
+      if (want_aln) {
+        Q.ptr_scratch = h->dev.get<uint8_t>((size_t)long_ptr_total);
+        Q.ptr_off = to_device(h, h->dev, long_ptr_off.data(), n_long);
+        Q.aln1 = P.aln1;
+        Q.aln2 = P.aln2;
+        Q.aln_off = P.aln_off;
+        Q.aln_len = P.aln_len;
+      }
+      if (2 * n_long > (size_t)0x7fffffff) fail(BK_ERR_CAPACITY, "bk_nw_batch: more than 2^30 pairs above %d bases", NW_MAX_LEN);
+      {
+        TimedLaunch t(h->timers, h->st, KF_NW_BATCH);
+        nw_long_kernel<<<(unsigned)(2 * n_long), NWL_THREADS, 0, h->st>>>(Q);
+      }
+      BK_CUDA(cudaGetLastError());
+    }
     BK_CUDA(cudaMemcpyAsync(out, P.out, n_pairs * 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
     if (want_aln) {
       BK_CUDA(cudaMemcpyAsync(aln1, P.aln1, aln_total, cudaMemcpyDeviceToHost, h->st));

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(NWB_WARPS * 32) nw_batch_kernel(NwBatchParams 
     const int ia = p.pair_a[pi], ib = p.pair_b[pi];
     const int64_t oa = p.seq_off[ia], ob = p.seq_off[ib];
     const int m = (int)(p.seq_off[ia + 1] - oa), n = (int)(p.seq_off[ib + 1] - ob);
+    if (m > NW_MAX_LEN || n > NW_MAX_LEN) continue;                      // nw_long_kernel's (nw_long.cuh); warp-uniform
     __syncwarp();
     for (int x = L; x < m; x += 32) s1[x] = p.seqs[oa + x];
     for (int x = L; x < n; x += 32) s2[x] = p.seqs[ob + x];

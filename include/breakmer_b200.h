@@ -35,7 +35,8 @@ extern "C" {
 #define BK_ERR_CUDA (-1)
 #define BK_ERR_ARG (-2)
 #define BK_ERR_NOMEM (-3)
-#define BK_ERR_CAPACITY (-4)  /* a sequence exceeds a device-side hard limit (4095 bases for nw) */
+#define BK_ERR_CAPACITY (-4)  /* a device-side hard limit is exceeded (a read or contig above 4095 bases inside the
+                                  batched assembler; bk_nw_batch itself has no length limit) */
 #define BK_ERR_EMPTY_SEQ (-5) /* olc.nw raises NameError on an empty sequence (olc.py:86-87) */
 #define BK_ERR_FORMAT (-6)    /* malformed FASTQ record (FastqFile raises, utils.py:704-719) */
 #define BK_ERR_IO (-7)        /* an input file cannot be read */
@@ -56,7 +57,10 @@ const char* bk_last_error(bk_handle_t h);
  *                    sweep; check_align always needs both).
  * If want_aln != 0, align1/align2 of nw(seq1, seq2) (tuple fields [0:2]) are
  * written to aln1/aln2 at aln_off[p] (capacity len(seq1)+len(seq2) each) and
- * their common length to aln_len[p]. */
+ * their common length to aln_len[p].
+ * Like olc.nw (olc.py:40-52) the call has no length limit: pairs with a sequence above 4095 bases
+ * (the packed-cell warp kernels' range) are run by a 32-bit anti-diagonal kernel, one thread block
+ * per direction (csrc/nw_long.cuh); memory is O(m+n) per pair, (m+1)(n+1) bytes more with want_aln. */
 int bk_nw_batch(bk_handle_t h, const char* seqs, const int64_t* seq_off, int64_t n_seq,
                 const int32_t* pair_a, const int32_t* pair_b, int64_t n_pairs, int32_t* out,
                 int want_aln, char* aln1, char* aln2, const int64_t* aln_off, int32_t* aln_len);

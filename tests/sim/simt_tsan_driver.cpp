@@ -103,6 +103,24 @@ int main(int argc, char** argv) {
       int rd = bk_dedup_reads(h, bases, off.data(), nd, mer_pos.data(), boff, 2, 0.90, check.data(), flags.data(), &npairs, &nl);
       printf("dedup rc %d alignments %lld launches %d\n", rd, (long long)npairs, nl);
     }
+    // olc.nw above the packed-cell kernels' 4095 bases (nw_long_kernel): the reference sequence of region 0 repeated to
+    // 4,300 bases against its mutated tail; checksum only (parity is tests/test_gpu_nw.py's job)
+    {
+      const int64_t L0 = in.ref_off[1] - in.ref_off[0];
+      std::string a, b;
+      while ((int64_t)a.size() < 4300) a.append(in.ref_bases, (size_t)std::min<int64_t>(L0, 4300 - (int64_t)a.size()));
+      b = a.substr(4000) + a.substr(100, 150);
+      for (size_t x = 7; x < b.size(); x += 41) b[x] = b[x] == 'A' ? 'C' : 'A';
+      std::string both = a + b;
+      int64_t loff[3] = {0, (int64_t)a.size(), (int64_t)both.size()};
+      int32_t lpa[1] = {0}, lpb[1] = {1}, lout[10], lalen[1];
+      int64_t laoff[2] = {0, (int64_t)both.size()};
+      std::vector<char> l1(both.size() + 1), l2(both.size() + 1);
+      int rl = bk_nw_batch(h, both.data(), loff, 2, lpa, lpb, 1, lout, 1, l1.data(), l2.data(), laoff, lalen);
+      const int score_with_strings = lout[4];
+      rl |= bk_nw_batch(h, both.data(), loff, 2, lpa, lpb, 1, lout, 0, nullptr, nullptr, nullptr, nullptr);
+      printf("nw_long rc %d score %d (with strings %d) aln_len %d\n", rl, lout[4], score_with_strings, lalen[0]);
+    }
     // the reference k-mer cache instead of the reference sequences
     const long long contigs_before = (long long)res.n_contigs;
     int rcache = bk_ref_cache_build(h, in.ref_bases, in.ref_off, R, in.k);

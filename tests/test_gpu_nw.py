@@ -66,7 +66,7 @@ def test_random_pairs_incl_long_and_n(handle):
         assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (a, b)
 
 
-def test_max_length_and_limits(handle):
+def test_max_packed_length_and_empty_sequence(handle):
     from breakmer_b200 import _lib
     rng = random.Random(3)
     a = "".join(rng.choice("ACGT") for _ in range(4095))
@@ -74,9 +74,6 @@ def test_max_length_and_limits(handle):
     out, _ = _run(handle, [(a, b), (b, a)])
     assert list(out[0][:5]) == list(nw_py.nw_fast(a, b)[2:])
     assert list(out[1][:5]) == list(nw_py.nw_fast(b, a)[2:])
-    with pytest.raises(_lib.BreakmerError) as e:
-        _run(handle, [(a + "A", b)])
-    assert e.value.code == _lib.BK_ERR_CAPACITY
     with pytest.raises(_lib.BreakmerError) as e:
         _run(handle, [("", "ACGT")])
     assert e.value.code == _lib.BK_ERR_EMPTY_SEQ      # the reference raises NameError here
@@ -125,3 +122,41 @@ def test_score_pass_traceback_equals_packed_cell_kernel(handle, monkeypatch):
     for (a, b), o in list(zip(pairs, fast))[::7]:
         assert list(o[:5]) == list(nw_py.nw_fast(a, b)[2:]), (a, b)
         assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (a, b)
+
+
+def _long_pairs():
+    """pairs with a sequence above the packed-cell kernels' 4095 bases (olc.nw has no limit, olc.py:40-52): overlaps,
+    containment, unrelated, one base against a long one, repeats (ties), both long"""
+    rng = random.Random(41)
+    g = "".join(rng.choice("ACGT") for _ in range(12000))
+    mut = lambda s, p: "".join(c if rng.random() > p else rng.choice("ACGTN") for c in s)
+    rep = ("AC" * 3000)
+    return [
+        (g[:4096], g[3500:4700]),                 # suffix of seq1 overlaps the prefix of seq2, seq1 one base over the limit
+        (g[3500:4700], g[:4096]),
+        (g[:5000], mut(g[4200:5600], 0.03)),      # overlap with mismatches
+        (g[:4600], g[1000:1300]),                 # seq2 contained in seq1
+        (g[1000:1300], g[:4600]),
+        (g[:4100], g[6000:6300]),                 # unrelated
+        ("A", g[:4200]),
+        (g[:4200], "T"),
+        (rep[:4300], rep[1:901]),                 # low complexity: ties everywhere
+        (g[:4500], mut(g[300:4900], 0.01)),       # both above the limit
+        (g[:100], g[50:150]),                     # an ordinary pair in the same call
+    ]
+
+
+def test_pairs_above_4095_bases(handle):
+    pairs = _long_pairs()
+    out, _ = _run(handle, pairs)
+    for (a, b), o in zip(pairs, out):
+        assert list(o[:5]) == list(nw_py.nw_fast(a, b)[2:]), (len(a), len(b))
+        assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (len(a), len(b))
+
+
+def test_alignment_strings_above_4095_bases(handle):
+    pairs = _long_pairs()[:4] + _long_pairs()[6:9] + _long_pairs()[10:]
+    out, alns = _run(handle, pairs, want_aln=True)
+    for (a, b), o, (a1, a2) in zip(pairs, out, alns):
+        assert (a1, a2) + tuple(o[:5]) == tuple(nw_py.nw_fast(a, b)), (len(a), len(b))
+        assert list(o[5:]) == list(nw_py.nw_fast(b, a)[2:]), (len(a), len(b))

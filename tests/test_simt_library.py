@@ -26,7 +26,7 @@ SUBSETS = [
      "other_k or empty_and_ragged or given_mers or capacity_is_reported or odd_inputs", 7),
     (["tests/test_gpu_api.py", "tests/test_handoff.py", "tests/test_ingest.py"],
      "not sharded and not applying_thread and not ingested_batch_equals", 8),
-    (["tests/test_gpu_nw.py", "tests/test_gpu_redundancy.py"], "golden or incremental or signature", 3),
+    (["tests/test_gpu_nw.py", "tests/test_gpu_redundancy.py"], "golden or incremental or signature or above_4095", 5),
 ]
 
 

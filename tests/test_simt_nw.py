@@ -142,7 +142,7 @@ def batch_lib():
     return ctypes.CDLL(sim_util.build_simt("libsimt_nw_batch.so", "simt_nw_batch.cpp"))
 
 
-def run_batch(lib, pairs, want_aln, grid=2, use_tab=True):
+def run_batch(lib, pairs, want_aln, grid=2, use_tab=True, long_kernel=False):
     seqs, pa, pb = [], [], []
     for a, b in pairs:
         pa.append(len(seqs)); seqs.append(a)
@@ -158,8 +158,12 @@ def run_batch(lib, pairs, want_aln, grid=2, use_tab=True):
     a1 = np.zeros(int(aln_off[-1]) + 1, dtype=np.uint8); a2 = np.zeros_like(a1)
     alen = np.zeros(n, dtype=np.int32)
     p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.simt_nw_batch(p(blob), p(off), ctypes.c_int(len(seqs)), p(pa), p(pb), ctypes.c_int64(n), ctypes.c_int(grid),
-                           ctypes.c_int(1 if use_tab else 0), p(out), ctypes.c_int(1 if want_aln else 0), p(a1), p(a2), p(aln_off), p(alen))
+    if long_kernel:
+        rc = lib.simt_nw_long(p(blob), p(off), ctypes.c_int(len(seqs)), p(pa), p(pb), ctypes.c_int64(n), p(out),
+                              ctypes.c_int(1 if want_aln else 0), p(a1), p(a2), p(aln_off), p(alen))
+    else:
+        rc = lib.simt_nw_batch(p(blob), p(off), ctypes.c_int(len(seqs)), p(pa), p(pb), ctypes.c_int64(n), ctypes.c_int(grid),
+                               ctypes.c_int(1 if use_tab else 0), p(out), ctypes.c_int(1 if want_aln else 0), p(a1), p(a2), p(aln_off), p(alen))
     assert rc == 0
     res = []
     for i in range(n):
@@ -183,3 +187,43 @@ def test_batch_kernel_without_strings(batch_lib):
         got = run_batch(batch_lib, [(c["seq1"], c["seq2"]) for c in cases], want_aln=False, grid=1, use_tab=use_tab)
         for c, (_a1, _a2, o) in zip(cases, got):
             assert o[:5] == c["out"][2:]
+
+
+# ---- nw_long_kernel: bk_nw_batch's kernel for pairs above 4095 bases (one block per direction, 32-bit anti-diagonals) ---
+def test_long_kernel_on_the_reference_golden_pairs(batch_lib):
+    """the kernel has no LOWER length bound, so every golden pair of the reference runs through it: full tuple of
+    nw(seq1, seq2) incl. both alignment strings, and the five integers of nw(seq2, seq1)"""
+    cases = [c for c in golden("nw_golden.json")["cases"] if c["seq1"] and c["seq2"]]
+    got = run_batch(batch_lib, [(c["seq1"], c["seq2"]) for c in cases], want_aln=True, long_kernel=True)
+    for c, (a1, a2, o) in zip(cases, got):
+        assert [a1, a2] + o[:5] == c["out"], (c["seq1"], c["seq2"])
+        assert o[5:] == list(nw_py.nw_fast(c["seq2"], c["seq1"])[2:])
+
+
+def test_long_kernel_equals_the_warp_kernels_on_seeded_pairs(batch_lib):
+    """no pointer table (the stop position is carried forward with the score): ties, repeats, N, one-base sequences,
+    lengths around the 256-thread stride"""
+    rng = random.Random(17)
+    pairs = []
+    for t in range(160):
+        la = rng.choice([1, 2, 3, 31, 100, 255, 256, 257, 300, 513, 700])
+        lb = rng.choice([1, 2, 33, 100, 150, 256, 258, 400])
+        g = "".join(rng.choice("ACGT") for _ in range(la + lb))
+        a = g[:la]
+        mode = t % 4
+        if mode == 0:
+            b = "".join(rng.choice("ACGTN") for _ in range(lb))
+        elif mode == 1:
+            ov = rng.randint(1, min(la, lb))
+            b = (a[la - ov:] + g[la:])[:lb]
+        elif mode == 2:
+            unit = "".join(rng.choice("AC") for _ in range(rng.randint(1, 3)))
+            a = (unit * 800)[:la]; b = (unit * 800)[1:1 + lb]
+        else:
+            b = g[max(0, la - lb // 2):][:lb]
+        b = "".join(c if rng.random() > 0.02 else rng.choice("ACGTN") for c in b)
+        pairs.append((a, b) if t % 2 else (b, a))
+    got = run_batch(batch_lib, pairs, want_aln=False, long_kernel=True)
+    for (a, b), (_a1, _a2, o) in zip(pairs, got):
+        assert o[:5] == list(nw_py.nw_fast(a, b)[2:]), (a, b)
+        assert o[5:] == list(nw_py.nw_fast(b, a)[2:]), (a, b)

@@ -114,7 +114,10 @@ def test_whole_library_has_no_warp_or_block_level_race_on_golden_regions(order):
         assert got[i] == (len(only), [c["seq"] for c in exp]), r.name
     assert "ThreadSanitizer" not in out.stderr
     # the entry points beside the batched path ran under the detector too (bk_count_kmers / bk_sample_only, bk_nw_batch
-    # with and without alignment strings, bk_dedup_reads, the reference k-mer cache)
-    legs = {l.split()[0]: l.split() for l in out.stdout.splitlines() if l.split()[0] in ("count_kmers", "nw_batch", "dedup", "ref_cache")}
-    assert sorted(legs) == ["count_kmers", "dedup", "nw_batch", "ref_cache"] and all(v[1:3] == ["rc", "0"] for v in legs.values())
+    # with and without alignment strings, bk_dedup_reads, the reference k-mer cache, a pair above 4,095 bases = nw_long_kernel)
+    legs = {l.split()[0]: l.split() for l in out.stdout.splitlines()
+            if l.split()[0] in ("count_kmers", "nw_batch", "nw_long", "dedup", "ref_cache")}
+    assert sorted(legs) == ["count_kmers", "dedup", "nw_batch", "nw_long", "ref_cache"]
+    assert all(v[1:3] == ["rc", "0"] for v in legs.values())
+    assert int(legs["nw_long"][4]) > 100 and legs["nw_long"][4] == legs["nw_long"][7].rstrip(")")      # (a 4,300-base pair)
     assert legs["ref_cache"][4] == legs["ref_cache"][-1].rstrip(")")            # same contigs with the cache as with the sequences
