@@ -25,6 +25,19 @@ def test_olc_nw_signature_and_values():
     assert (olc.match_award, olc.mismatch_penalty, olc.gap_penalty) == (1, -2, -2)
 
 
+def test_olc_nw_has_no_length_limit():
+    """olc.py:40-52 allocates its tables for any length; the drop-in routes a pair beyond the packed-cell kernels' 4095
+    bases to nw_long_kernel and returns the same 7-tuple"""
+    import random
+    from breakmer_b200 import olc
+    from oracle import nw_py
+    rng = random.Random(5)
+    contig = "".join(rng.choice("ACGT") for _ in range(4500))
+    read = contig[4420:] + "".join(rng.choice("ACGT") for _ in range(70))
+    assert olc.nw(contig, read) == nw_py.nw_fast(contig, read)
+    assert olc.nw(read, contig) == nw_py.nw_fast(read, contig)
+
+
 def _write_region_files(region, d):
     ref_f = os.path.join(d, region.name + "_forward_refseq.fa")
     ref_r = os.path.join(d, region.name + "_reverse_refseq.fa")
