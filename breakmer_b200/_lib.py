@@ -12,6 +12,8 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int3
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# BK_LIB: explicit path of another BUILD of the same library (instrumented builds of tools/, the test-only emulator build of
+# tests/sim).  Never chosen automatically: unset, only the in-tree CUDA library is loaded, and load() raises without it.
 LIB_PATH = os.environ.get("BK_LIB") or os.path.join(_HERE, "lib", "libbreakmer_b200.so")
 
 BK_OK = 0

@@ -72,7 +72,7 @@ int guarded(bk_handle_t h, F&& f) {
     snprintf(buf, sizeof buf, "CUDA error %d (%s) at api line %d: %s", (int)e.e, cudaGetErrorString(e.e), e.line, e.what);
     h->err = buf;
     cudaGetLastError();
-    return BK_ERR_CUDA;
+    return e.e == cudaErrorMemoryAllocation ? BK_ERR_NOMEM : BK_ERR_CUDA;       // (out of device / pinned memory: not sticky)
   } catch (const std::bad_alloc&) {
     h->err = "host allocation failed";
     return BK_ERR_NOMEM;

@@ -80,3 +80,18 @@ def test_errors():
         get_handle(0).dedup_reads(["ACGT", "ACGT"], [0, 1], [0, 1], 0.9)      # batch_off does not cover the reads
     with pytest.raises(_lib.BreakmerError):
         get_handle(0).dedup_reads(["ACGT", "ACGT"], [0, 1], [0, 2], 1.5)      # threshold out of range
+
+
+def test_batch_with_reads_above_4095_bases():
+    """the alignments behind the decision chain go through bk_nw_batch, which has no length limit (olc.py:40-52): a batch
+    mixing 4,200-4,400-base sequences (a duplicate, a contained one, a shifted one, an unrelated one) with short reads"""
+    from breakmer_b200 import sv_assembly_mm2 as mm2
+    rng = random.Random(77)
+    g = "".join(rng.choice("ACGT") for _ in range(9000))
+    batch = [("L0", g[:4300], 0), ("L1", g[:4300], 0), ("L2", g[40:4240], 0), ("s0", g[100:200], 0),
+             ("L3", g[60:4400], 0), ("L4", g[4500:8800], 0), ("s1", g[100:200], 0), ("L5", g[4500:8800], 0)]
+    for frac in (R.SUBSEQ_FRAC_MM2, R.SUBSEQ_FRAC_LIVE):
+        got = mm2.dedup_batches([as_batch(batch)], frac=frac)[0]
+        exp = R.dedup_batch(batch, frac)
+        assert unpack(got) == (exp[0], exp[1], exp[2], exp[3])
+    assert not all(R.dedup_batch(batch)[0])            # (some read was found redundant, i.e. the chain did something)
