@@ -227,3 +227,19 @@ def test_long_kernel_equals_the_warp_kernels_on_seeded_pairs(batch_lib):
     for (a, b), (_a1, _a2, o) in zip(pairs, got):
         assert o[:5] == list(nw_py.nw_fast(a, b)[2:]), (a, b)
         assert o[5:] == list(nw_py.nw_fast(b, a)[2:]), (a, b)
+
+
+def test_long_kernel_on_tie_heavy_short_pairs(batch_lib):
+    """small alphabets and short sequences: nearly every cell is a tie, so the pointer priority diag > up > left and the
+    stop position carried forward with the score are exercised at every branch; full tuple incl. strings (3,000 such pairs
+    were run once by hand: 0 mismatches)"""
+    rng = random.Random(2026)
+    pairs = []
+    for _ in range(800):
+        alpha = rng.choice(["A", "AC", "ACG", "ACGT", "ACGTN"])
+        pairs.append(("".join(rng.choice(alpha) for _ in range(rng.randint(1, 40))),
+                      "".join(rng.choice(alpha) for _ in range(rng.randint(1, 40)))))
+    got = run_batch(batch_lib, pairs, want_aln=True, long_kernel=True)
+    for (a, b), (a1, a2, o) in zip(pairs, got):
+        assert (a1, a2) + tuple(o[:5]) == tuple(nw_py.nw_fast(a, b)), (a, b)
+        assert o[5:] == list(nw_py.nw_fast(b, a)[2:]), (a, b)
