@@ -1,0 +1,47 @@
+"""Random-scenario fuzz of the whole device path against the oracle: regions with random k (11-31), read length (36-250),
+coverage (0-300x), error / N / indel rates, event type and size, allele fraction and spurious-read fraction, one region per
+C-ABI call (batch.run), sample-only k-mers and every contig record compared with the oracle.  TEST TOOL.
+
+On a B200:          python tools/simt_fuzz_regions.py <seed> <n_regions>
+Without a GPU:      BK_LIB=tests/sim/libbreakmer_simt_TESTONLY.so python tools/simt_fuzz_regions.py <seed> <n_regions>
+                    (the library on the host SIMT emulator of tests/sim; `python tests/sim_util.py` builds it)
+"""
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from breakmer_b200 import _lib, batch, synth
+from test_gpu_pipeline import oracle_region
+seed0 = int(sys.argv[1]); n = int(sys.argv[2])
+rng = random.Random(seed0)
+h = _lib.Handle(0)
+bad = 0; nctg = 0
+t0 = time.time()
+for it in range(n):
+    k = rng.choice([11, 15, 15, 21, 25, 31])
+    rl = rng.choice([36, 50, 76, 100, 100, 150, 250])
+    if rl <= k + 4: rl = k + 20
+    ev = rng.choice([("del", rng.randint(20, 600), None), ("ins", rng.randint(5, 80)), ("tdup", rng.randint(30, 300)),
+                     ("inv", rng.randint(100, 500)), ("none",), ("trl",)])
+    kw = dict(seed=seed0 * 1000 + it, L=rng.randint(400, 2500), cov=rng.choice([0, 3, 10, 40, 120, 300]), k=k,
+              e=rng.choice([0.0, 0.002, 0.01, 0.03, 0.06]), event=ev, vaf=rng.choice([1.0, 0.5, 0.15]), rl=rl,
+              n_rate=rng.choice([0.0, 0.001, 0.02]), indel_p=rng.choice([0.0, 0.3, 0.8]),
+              spurious_frac=rng.choice([0.0, 0.0, 0.05, 0.3]), rl_jitter=rng.choice([0, 0, 10, 30]))
+    try:
+        r = synth.make_region("f%d_%d" % (seed0, it), **kw)
+    except Exception as ex:
+        print("gen skipped", kw["event"], type(ex).__name__, ex); continue
+    try:
+        only, ctg = oracle_region(r)
+        out = batch.run(h, batch.PackedBatch([r]))
+        ok = out.region_status[0] == 0 and out.sample_only(0) == only and out.contig_records(0) == ctg
+    except Exception as ex:
+        ok = False; print("EXC", type(ex).__name__, ex)
+    nctg = nctg + len(ctg) if ok else nctg
+    if not ok:
+        bad += 1; print("MISMATCH", kw)
+print("seed", seed0, "regions", n, "contigs", nctg, "mismatches", bad, "%.0fs" % (time.time() - t0))
