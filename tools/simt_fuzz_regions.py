@@ -2,7 +2,7 @@
 coverage (0-300x), error / N / indel rates, event type and size, allele fraction and spurious-read fraction, one region per
 C-ABI call (batch.run), sample-only k-mers and every contig record compared with the oracle.  TEST TOOL.
 
-On a B200:          python tools/simt_fuzz_regions.py <seed> <n_regions>
+On a B200:          python tools/simt_fuzz_regions.py <seed> <n_regions> [max regions per call, default 1]
 Without a GPU:      BK_LIB=tests/sim/libbreakmer_simt_TESTONLY.so python tools/simt_fuzz_regions.py <seed> <n_regions>
                     (the library on the host SIMT emulator of tests/sim; `python tests/sim_util.py` builds it)
 """
@@ -21,6 +21,8 @@ rng = random.Random(seed0)
 h = _lib.Handle(0)
 bad = 0; nctg = 0
 t0 = time.time()
+max_call = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # regions per C-ABI call: 1 .. max_call, same k
+by_k = {}
 for it in range(n):
     k = rng.choice([11, 15, 15, 21, 25, 31])
     rl = rng.choice([36, 50, 76, 100, 100, 150, 250])
@@ -31,17 +33,21 @@ for it in range(n):
               e=rng.choice([0.0, 0.002, 0.01, 0.03, 0.06]), event=ev, vaf=rng.choice([1.0, 0.5, 0.15]), rl=rl,
               n_rate=rng.choice([0.0, 0.001, 0.02]), indel_p=rng.choice([0.0, 0.3, 0.8]),
               spurious_frac=rng.choice([0.0, 0.0, 0.05, 0.3]), rl_jitter=rng.choice([0, 0, 10, 30]))
-    try:
-        r = synth.make_region("f%d_%d" % (seed0, it), **kw)
-    except Exception as ex:
-        print("gen skipped", kw["event"], type(ex).__name__, ex); continue
-    try:
-        only, ctg = oracle_region(r)
-        out = batch.run(h, batch.PackedBatch([r]))
-        ok = out.region_status[0] == 0 and out.sample_only(0) == only and out.contig_records(0) == ctg
-    except Exception as ex:
-        ok = False; print("EXC", type(ex).__name__, ex)
-    nctg = nctg + len(ctg) if ok else nctg
-    if not ok:
-        bad += 1; print("MISMATCH", kw)
-print("seed", seed0, "regions", n, "contigs", nctg, "mismatches", bad, "%.0fs" % (time.time() - t0))
+    by_k.setdefault(k, []).append((kw, synth.make_region("f%d_%d" % (seed0, it), **kw)))
+n_calls = 0
+for k, items in sorted(by_k.items()):
+    while items:
+        take = rng.randint(1, max_call)
+        call, items = items[:take], items[take:]
+        n_calls += 1
+        try:
+            exp = [oracle_region(r) for _kw, r in call]
+            out = batch.run(h, batch.PackedBatch([r for _kw, r in call]))
+            for i, ((kw, r), (only, ctg)) in enumerate(zip(call, exp)):
+                ok = out.region_status[i] == 0 and out.sample_only(i) == only and out.contig_records(i) == ctg
+                nctg += len(ctg)
+                if not ok:
+                    bad += 1; print("MISMATCH (region %d of a call of %d)" % (i, len(call)), kw)
+        except Exception as ex:
+            bad += 1; print("EXC", type(ex).__name__, ex, [kw for kw, _r in call])
+print("seed", seed0, "regions", n, "calls", n_calls, "contigs", nctg, "mismatches", bad, "%.0fs" % (time.time() - t0))
