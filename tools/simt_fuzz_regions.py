@@ -2,7 +2,7 @@
 coverage (0-300x), error / N / indel rates, event type and size, allele fraction and spurious-read fraction, one region per
 C-ABI call (batch.run), sample-only k-mers and every contig record compared with the oracle.  TEST TOOL.
 
-On a B200:          python tools/simt_fuzz_regions.py <seed> <n_regions> [max regions per call, default 1]
+On a B200:          python tools/simt_fuzz_regions.py <seed> <n_regions> [max regions per call, default 1] [normal]
 Without a GPU:      BK_LIB=tests/sim/libbreakmer_simt_TESTONLY.so python tools/simt_fuzz_regions.py <seed> <n_regions>
                     (the library on the host SIMT emulator of tests/sim; `python tests/sim_util.py` builds it)
 """
@@ -22,6 +22,7 @@ h = _lib.Handle(0)
 bad = 0; nctg = 0
 t0 = time.time()
 max_call = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # regions per C-ABI call: 1 .. max_call, same k
+with_normal = len(sys.argv) > 4 and sys.argv[4] == "normal"     # (draws after the other knobs: seeds stay comparable)
 by_k = {}
 for it in range(n):
     k = rng.choice([11, 15, 15, 21, 25, 31])
@@ -33,6 +34,8 @@ for it in range(n):
               e=rng.choice([0.0, 0.002, 0.01, 0.03, 0.06]), event=ev, vaf=rng.choice([1.0, 0.5, 0.15]), rl=rl,
               n_rate=rng.choice([0.0, 0.001, 0.02]), indel_p=rng.choice([0.0, 0.3, 0.8]),
               spurious_frac=rng.choice([0.0, 0.0, 0.05, 0.3]), rl_jitter=rng.choice([0, 0, 10, 30]))
+    if with_normal and rng.random() < 0.6:                        # tumour / normal pair: K4 normal subtraction
+        kw.update(germline=True, normal_cov=rng.choice([5, 30, 100]))
     by_k.setdefault(k, []).append((kw, synth.make_region("f%d_%d" % (seed0, it), **kw)))
 n_calls = 0
 for k, items in sorted(by_k.items()):
