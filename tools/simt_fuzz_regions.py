@@ -14,43 +14,61 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
-from breakmer_b200 import _lib, batch, synth
-from test_gpu_pipeline import oracle_region
-seed0 = int(sys.argv[1]); n = int(sys.argv[2])
-rng = random.Random(seed0)
-h = _lib.Handle(0)
-bad = 0; nctg = 0
-t0 = time.time()
-max_call = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # regions per C-ABI call: 1 .. max_call, same k
-with_normal = len(sys.argv) > 4 and sys.argv[4] == "normal"     # (draws after the other knobs: seeds stay comparable)
-by_k = {}
-for it in range(n):
-    k = rng.choice([11, 15, 15, 21, 25, 31])
-    rl = rng.choice([36, 50, 76, 100, 100, 150, 250])
-    if rl <= k + 4: rl = k + 20
-    ev = rng.choice([("del", rng.randint(20, 600), None), ("ins", rng.randint(5, 80)), ("tdup", rng.randint(30, 300)),
-                     ("inv", rng.randint(100, 500)), ("none",), ("trl",)])
-    kw = dict(seed=seed0 * 1000 + it, L=rng.randint(400, 2500), cov=rng.choice([0, 3, 10, 40, 120, 300]), k=k,
-              e=rng.choice([0.0, 0.002, 0.01, 0.03, 0.06]), event=ev, vaf=rng.choice([1.0, 0.5, 0.15]), rl=rl,
-              n_rate=rng.choice([0.0, 0.001, 0.02]), indel_p=rng.choice([0.0, 0.3, 0.8]),
-              spurious_frac=rng.choice([0.0, 0.0, 0.05, 0.3]), rl_jitter=rng.choice([0, 0, 10, 30]))
-    if with_normal and rng.random() < 0.6:                        # tumour / normal pair: K4 normal subtraction
-        kw.update(germline=True, normal_cov=rng.choice([5, 30, 100]))
-    by_k.setdefault(k, []).append((kw, synth.make_region("f%d_%d" % (seed0, it), **kw)))
-n_calls = 0
-for k, items in sorted(by_k.items()):
-    while items:
-        take = rng.randint(1, max_call)
-        call, items = items[:take], items[take:]
-        n_calls += 1
-        try:
+from breakmer_b200 import _lib, batch, synth                      # noqa: E402
+
+
+def scenarios(seed0, n, with_normal=False):
+    """-> (rng, {k: [(kwargs, Region), ...]})"""
+    rng = random.Random(seed0)
+    by_k = {}
+    for it in range(n):
+        k = rng.choice([11, 15, 15, 21, 25, 31])
+        rl = rng.choice([36, 50, 76, 100, 100, 150, 250])
+        if rl <= k + 4:
+            rl = k + 20
+        ev = rng.choice([("del", rng.randint(20, 600), None), ("ins", rng.randint(5, 80)), ("tdup", rng.randint(30, 300)),
+                         ("inv", rng.randint(100, 500)), ("none",), ("trl",)])
+        kw = dict(seed=seed0 * 1000 + it, L=rng.randint(400, 2500), cov=rng.choice([0, 3, 10, 40, 120, 300]), k=k,
+                  e=rng.choice([0.0, 0.002, 0.01, 0.03, 0.06]), event=ev, vaf=rng.choice([1.0, 0.5, 0.15]), rl=rl,
+                  n_rate=rng.choice([0.0, 0.001, 0.02]), indel_p=rng.choice([0.0, 0.3, 0.8]),
+                  spurious_frac=rng.choice([0.0, 0.0, 0.05, 0.3]), rl_jitter=rng.choice([0, 0, 10, 30]))
+        if with_normal and rng.random() < 0.6:                        # tumour / normal pair: K4 normal subtraction
+            kw.update(germline=True, normal_cov=rng.choice([5, 30, 100]))   # (drawn after the other knobs: seeds stay comparable)
+        by_k.setdefault(k, []).append((kw, synth.make_region("f%d_%d" % (seed0, it), **kw)))
+    return rng, by_k
+
+
+def run_calls(h, rng, by_k, max_call, oracle_region):
+    """every region through the device path in calls of 1..max_call regions of one k -> (calls, contigs, [mismatch descriptions])"""
+    n_calls, nctg, bad = 0, 0, []
+    for _k, items in sorted(by_k.items()):
+        while items:
+            take = rng.randint(1, max_call)
+            call, items = items[:take], items[take:]
+            n_calls += 1
             exp = [oracle_region(r) for _kw, r in call]
             out = batch.run(h, batch.PackedBatch([r for _kw, r in call]))
-            for i, ((kw, r), (only, ctg)) in enumerate(zip(call, exp)):
-                ok = out.region_status[i] == 0 and out.sample_only(i) == only and out.contig_records(i) == ctg
+            for i, ((kw, _r), (only, ctg)) in enumerate(zip(call, exp)):
                 nctg += len(ctg)
-                if not ok:
-                    bad += 1; print("MISMATCH (region %d of a call of %d)" % (i, len(call)), kw)
-        except Exception as ex:
-            bad += 1; print("EXC", type(ex).__name__, ex, [kw for kw, _r in call])
-print("seed", seed0, "regions", n, "calls", n_calls, "contigs", nctg, "mismatches", bad, "%.0fs" % (time.time() - t0))
+                if not (out.region_status[i] == 0 and out.sample_only(i) == only and out.contig_records(i) == ctg):
+                    bad.append("region %d of a call of %d: %r" % (i, len(call), kw))
+    return n_calls, nctg, bad
+
+
+def main(argv):
+    from test_gpu_pipeline import oracle_region
+    seed0, n = int(argv[0]), int(argv[1])
+    max_call = int(argv[2]) if len(argv) > 2 else 1
+    rng, by_k = scenarios(seed0, n, len(argv) > 3 and argv[3] == "normal")
+    h = _lib.Handle(0)
+    t0 = time.time()
+    n_calls, nctg, bad = run_calls(h, rng, by_k, max_call, oracle_region)
+    for b in bad:
+        print("MISMATCH", b)
+    print("seed", seed0, "regions", n, "calls", n_calls, "contigs", nctg, "mismatches", len(bad), "%.0fs" % (time.time() - t0))
+    h.close()
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
